@@ -1,0 +1,798 @@
+/* CPU ORACLE -- TEST INFRASTRUCTURE ONLY (see sspsd_oracle.h for scope and parity status).
+ *
+ * Restates, in plain C and in the reference's own f32 evaluation order (no FMA contraction:
+ * build with -ffp-contract=off), the hot path of quartiq/stabilizer-stream:
+ *   src/psd.rs      Window, Detrend, Psd<N>, PsdCascade<N>, Break, MergeOpts, AvgOpts
+ *   src/de/{frame,data}.rs  Header::parse, Frame::from_bytes, AdcDac/Fls/ThermostatEem/Mpll::traces
+ *   src/loss.rs     Loss::update / analyze
+ *   src/var.rs      Var::eval
+ * plus the two crates.io dependencies on that path that are not on disk:
+ *   rustfft 6.4.1   -> orc_fft_forward (own Stockham radix-4/2 FFT, same DFT definition)
+ *   idsp 0.20.0 hbf -> orc_hbf8_* (taps from tools/gen_hbf_taps.py; PARITY UNPINNED)
+ */
+#include "sspsd_oracle.h"
+#include "hbf_taps.h"
+
+#include <assert.h>
+#include <math.h>
+#include <stdlib.h>
+#include <string.h>
+
+/* ------------------------------------------------------------------------------------------
+ * idsp::hbf restatement
+ * One half-band decimate-by-2 stage with M unique taps is the causal linear-phase FIR
+ *   y[j] = 0.5 * ( x[c] + sum_{i=0}^{M-1} t[i] * (x[c-(2k+1)] + x[c+(2k+1)]) ),
+ *   k = M-1-i,  c = 2*j - 2*M + 2,   newest input used: x[2*j+1]
+ * with zero initial state.  HbfDec8 chains three of them, highest rate first, using tap sets
+ * 2, 1, 0 (the lowest-rate stage has the longest filter).  psd.rs:246-253 feeds it chunks of
+ * 8 items and gets one item per chunk.
+ * ------------------------------------------------------------------------------------------ */
+typedef struct {
+    int m;            /* unique taps */
+    const float *t;   /* outermost -> innermost */
+    float *hist;      /* last 4m-2 inputs */
+} hbf2;
+
+struct orc_hbf8 {
+    int preset;
+    hbf2 st[3]; /* st[0] = highest rate (tap set 2) ... st[2] = lowest rate (tap set 0) */
+    float *work[3];
+    size_t work_cap;
+};
+
+orc_hbf8 *orc_hbf8_new(int preset)
+{
+    if (preset < 0 || preset >= ORC_HBF_NPRESET)
+        return NULL;
+    orc_hbf8 *h = (orc_hbf8 *)calloc(1, sizeof(*h));
+    h->preset = preset;
+    for (int s = 0; s < 3; s++) {
+        int set = 2 - s;
+        h->st[s].m = orc_hbf_ntaps[preset][set];
+        h->st[s].t = orc_hbf_taps[preset][set];
+        h->st[s].hist = (float *)calloc((size_t)(4 * h->st[s].m - 2), sizeof(float));
+    }
+    return h;
+}
+
+static orc_hbf8 *hbf8_clone(const orc_hbf8 *src)
+{
+    orc_hbf8 *h = orc_hbf8_new(src->preset);
+    for (int s = 0; s < 3; s++)
+        memcpy(h->st[s].hist, src->st[s].hist, (size_t)(4 * h->st[s].m - 2) * sizeof(float));
+    return h;
+}
+
+void orc_hbf8_free(orc_hbf8 *h)
+{
+    if (!h)
+        return;
+    for (int s = 0; s < 3; s++) {
+        free(h->st[s].hist);
+        free(h->work[s]);
+    }
+    free(h);
+}
+
+/* e = hist ++ x (2k new inputs) -> y (k outputs); hist <- last 4m-2 of e */
+static void hbf2_block(hbf2 *f, float *e, size_t k, float *y)
+{
+    const int m = f->m;
+    const int hl = 4 * m - 2;
+    const float *t = f->t;
+    for (size_t j = 0; j < k; j++) {
+        const float *c = e + 2 * m + 2 * j; /* centre tap */
+        float acc = 0.0f;
+        for (int i = 0; i < m; i++) {
+            int d = 2 * (m - 1 - i) + 1;
+            acc += (c[-d] + c[d]) * t[i];
+        }
+        y[j] = (c[0] + acc) * 0.5f;
+    }
+    memmove(f->hist, e + 2 * k, (size_t)hl * sizeof(float));
+}
+
+void orc_hbf8_block(orc_hbf8 *h, const float *x, size_t n_chunks, float *y)
+{
+    if (n_chunks == 0)
+        return;
+    if (n_chunks > h->work_cap) {
+        for (int s = 0; s < 3; s++) {
+            free(h->work[s]);
+            size_t n_in = (n_chunks * 8) >> s;
+            h->work[s] = (float *)malloc((n_in + (size_t)(4 * h->st[s].m - 2)) * sizeof(float));
+        }
+        h->work_cap = n_chunks;
+    }
+    /* work[s] = hist_s ++ input_s; each stage writes its output directly behind the history slot
+     * of the next stage's work buffer */
+    memcpy(h->work[0] + (4 * h->st[0].m - 2), x, n_chunks * 8 * sizeof(float));
+    for (int s = 0; s < 3; s++) {
+        size_t n_in = (n_chunks * 8) >> s;
+        int hl = 4 * h->st[s].m - 2;
+        memcpy(h->work[s], h->st[s].hist, (size_t)hl * sizeof(float));
+        float *out = (s == 2) ? y : (h->work[s + 1] + (4 * h->st[s + 1].m - 2));
+        hbf2_block(&h->st[s], h->work[s], n_in / 2, out);
+    }
+}
+
+int orc_hbf_response_length(int preset)
+{
+    return orc_hbf_drain[preset];
+}
+
+float orc_hbf_passband(void)
+{
+    return 0.4f;
+}
+
+/* ------------------------------------------------------------------------------------------
+ * rustfft restatement: forward, unnormalised, X[k] = sum_n x[n] e^{-2 pi i nk/N}.
+ * Stockham autosort, radix 4 with one radix-2 pass when log2(N) is odd.  Twiddles from f64.
+ * ------------------------------------------------------------------------------------------ */
+typedef struct {
+    int n;
+    float *tw; /* interleaved cos, -sin of 2 pi k / n, k < n */
+    float *tmp;
+} fft_plan;
+
+static fft_plan g_plans[32];
+
+static fft_plan *fft_get_plan(int n)
+{
+    int l = 0;
+    while ((1 << l) < n)
+        l++;
+    assert((1 << l) == n && l < 32);
+    fft_plan *p = &g_plans[l];
+    if (p->n != n) {
+        p->n = n;
+        p->tw = (float *)malloc(sizeof(float) * 2 * (size_t)n);
+        p->tmp = (float *)malloc(sizeof(float) * 2 * (size_t)n);
+        for (int k = 0; k < n; k++) {
+            double a = -2.0 * M_PI * (double)k / (double)n;
+            p->tw[2 * k] = (float)cos(a);
+            p->tw[2 * k + 1] = (float)sin(a);
+        }
+    }
+    return p;
+}
+
+void orc_fft_forward(float *c, int n)
+{
+    if (n <= 1)
+        return;
+    fft_plan *pl = fft_get_plan(n);
+    float *x = c, *y = pl->tmp;
+    const float *tw = pl->tw;
+    int len = n, s = 1;
+    while (len > 1) {
+        if (len % 4 == 0) {
+            int m = len / 4;
+            int tws = n / len; /* twiddle stride: W_len^p = tw[p*tws] */
+            for (int p = 0; p < m; p++) {
+                float w1r = tw[2 * (p * tws)], w1i = tw[2 * (p * tws) + 1];
+                float w2r = tw[2 * (2 * p * tws)], w2i = tw[2 * (2 * p * tws) + 1];
+                float w3r = tw[2 * (3 * p * tws)], w3i = tw[2 * (3 * p * tws) + 1];
+                const float *xa = x + 2 * (size_t)(s * p);
+                const float *xb = x + 2 * (size_t)(s * (p + m));
+                const float *xc = x + 2 * (size_t)(s * (p + 2 * m));
+                const float *xd = x + 2 * (size_t)(s * (p + 3 * m));
+                float *y0 = y + 2 * (size_t)(s * (4 * p));
+                float *y1 = y + 2 * (size_t)(s * (4 * p + 1));
+                float *y2 = y + 2 * (size_t)(s * (4 * p + 2));
+                float *y3 = y + 2 * (size_t)(s * (4 * p + 3));
+                for (int q = 0; q < s; q++) {
+                    float ar = xa[2 * q], ai = xa[2 * q + 1];
+                    float br = xb[2 * q], bi = xb[2 * q + 1];
+                    float cr = xc[2 * q], ci = xc[2 * q + 1];
+                    float dr = xd[2 * q], di = xd[2 * q + 1];
+                    float apcr = ar + cr, apci = ai + ci;
+                    float amcr = ar - cr, amci = ai - ci;
+                    float bpdr = br + dr, bpdi = bi + di;
+                    /* -i * (b - d) */
+                    float jr = bi - di, ji = -(br - dr);
+                    y0[2 * q] = apcr + bpdr;
+                    y0[2 * q + 1] = apci + bpdi;
+                    float t1r = amcr + jr, t1i = amci + ji;
+                    y1[2 * q] = t1r * w1r - t1i * w1i;
+                    y1[2 * q + 1] = t1r * w1i + t1i * w1r;
+                    float t2r = apcr - bpdr, t2i = apci - bpdi;
+                    y2[2 * q] = t2r * w2r - t2i * w2i;
+                    y2[2 * q + 1] = t2r * w2i + t2i * w2r;
+                    float t3r = amcr - jr, t3i = amci - ji;
+                    y3[2 * q] = t3r * w3r - t3i * w3i;
+                    y3[2 * q + 1] = t3r * w3i + t3i * w3r;
+                }
+            }
+            len = m;
+            s *= 4;
+        } else {
+            int m = len / 2;
+            int tws = n / len;
+            for (int p = 0; p < m; p++) {
+                float wr = tw[2 * (p * tws)], wi = tw[2 * (p * tws) + 1];
+                const float *xa = x + 2 * (size_t)(s * p);
+                const float *xb = x + 2 * (size_t)(s * (p + m));
+                float *y0 = y + 2 * (size_t)(s * (2 * p));
+                float *y1 = y + 2 * (size_t)(s * (2 * p + 1));
+                for (int q = 0; q < s; q++) {
+                    float ar = xa[2 * q], ai = xa[2 * q + 1];
+                    float br = xb[2 * q], bi = xb[2 * q + 1];
+                    y0[2 * q] = ar + br;
+                    y0[2 * q + 1] = ai + bi;
+                    float tr = ar - br, ti = ai - bi;
+                    y1[2 * q] = tr * wr - ti * wi;
+                    y1[2 * q + 1] = tr * wi + ti * wr;
+                }
+            }
+            len = m;
+            s *= 2;
+        }
+        float *t = x;
+        x = y;
+        y = t;
+    }
+    if (x != c)
+        memcpy(c, x, sizeof(float) * 2 * (size_t)n);
+}
+
+/* ------------------------------------------------------------------------------------------
+ * Window (psd.rs:12-56)
+ * ------------------------------------------------------------------------------------------ */
+void orc_window(int n, int window, float *win, float *power, float *nenbw, size_t *overlap)
+{
+    if (window == ORC_WINDOW_RECT) { /* psd.rs:24-32 */
+        for (int i = 0; i < n; i++)
+            win[i] = 1.0f;
+        *power = 1.0f;
+        *nenbw = 1.0f;
+        *overlap = 0;
+    } else { /* psd.rs:42-55: (PI / N as f32 * i as f32).sin().powi(2) */
+        const float pi = 3.14159265358979323846f;
+        float df = pi / (float)n;
+        for (int i = 0; i < n; i++) {
+            float s = sinf(df * (float)i);
+            win[i] = s * s;
+        }
+        *power = 0.25f;
+        *nenbw = 1.5f;
+        *overlap = (size_t)n / 2;
+    }
+}
+
+/* Detrend::apply (psd.rs:75-113) */
+int orc_detrend_apply(int detrend, const float *x, const float *win, int n, float *c)
+{
+    switch (detrend) {
+    case ORC_DETREND_NONE: /* psd.rs:81-86 */
+        for (int i = 0; i < n; i++) {
+            c[2 * i] = x[i] * win[i];
+            c[2 * i + 1] = 0.0f;
+        }
+        return 0;
+    case ORC_DETREND_MIDPOINT: { /* psd.rs:87-93 */
+        float offset = x[n / 2];
+        for (int i = 0; i < n; i++) {
+            c[2 * i] = (x[i] - offset) * win[i];
+            c[2 * i + 1] = 0.0f;
+        }
+        return 0;
+    }
+    case ORC_DETREND_SPAN: { /* psd.rs:94-102: offset accumulated sequentially */
+        float offset = x[0];
+        float slope = (x[n - 1] - x[0]) / (float)(n - 1);
+        for (int i = 0; i < n; i++) {
+            c[2 * i] = (x[i] - offset) * win[i];
+            c[2 * i + 1] = 0.0f;
+            offset += slope;
+        }
+        return 0;
+    }
+    case ORC_DETREND_MEAN: { /* psd.rs:103-109: sequential f32 sum */
+        float sum = 0.0f;
+        for (int i = 0; i < n; i++)
+            sum += x[i];
+        float offset = sum / (float)n;
+        for (int i = 0; i < n; i++) {
+            c[2 * i] = (x[i] - offset) * win[i];
+            c[2 * i + 1] = 0.0f;
+        }
+        return 0;
+    }
+    default: /* psd.rs:110 unimplemented!() */
+        return -1;
+    }
+}
+
+/* ------------------------------------------------------------------------------------------
+ * Psd<N> (psd.rs:123-288)
+ * ------------------------------------------------------------------------------------------ */
+struct orc_stage {
+    int n;
+    int window;
+    int hbf_preset;
+    orc_hbf8 *hbf;
+    float *buf;
+    size_t idx;
+    float *spectrum;
+    uint32_t count;
+    size_t drain;
+    float *win;
+    float power, nenbw;
+    size_t overlap;
+    int detrend;
+    uint32_t avg;
+    float *c; /* scratch: N complex */
+};
+
+orc_stage *orc_stage_new(int n, int window, int hbf_preset)
+{
+    /* psd.rs:137-152; as_chunks::<8> remainder assert psd.rs:246-247 */
+    if (n < 16 || (n & (n - 1)) != 0 || hbf_preset < 0 || hbf_preset >= ORC_HBF_NPRESET)
+        return NULL;
+    orc_stage *s = (orc_stage *)calloc(1, sizeof(*s));
+    s->n = n;
+    s->window = window;
+    s->hbf_preset = hbf_preset;
+    s->hbf = orc_hbf8_new(hbf_preset);
+    s->buf = (float *)calloc((size_t)n, sizeof(float));
+    s->spectrum = (float *)calloc((size_t)n, sizeof(float));
+    s->win = (float *)calloc((size_t)n, sizeof(float));
+    s->c = (float *)calloc(2 * (size_t)n, sizeof(float));
+    orc_window(n, window, s->win, &s->power, &s->nenbw, &s->overlap);
+    s->count = 0;
+    s->idx = 0;
+    s->drain = (size_t)orc_hbf_response_length(hbf_preset); /* psd.rs:149 */
+    s->detrend = ORC_DETREND_NONE;
+    s->avg = UINT32_MAX; /* psd.rs:150 */
+    return s;
+}
+
+orc_stage *orc_stage_clone(const orc_stage *o)
+{
+    orc_stage *s = orc_stage_new(o->n, o->window, o->hbf_preset);
+    orc_hbf8_free(s->hbf);
+    s->hbf = hbf8_clone(o->hbf);
+    memcpy(s->buf, o->buf, sizeof(float) * (size_t)o->n);
+    memcpy(s->spectrum, o->spectrum, sizeof(float) * (size_t)o->n);
+    s->idx = o->idx;
+    s->count = o->count;
+    s->drain = o->drain;
+    s->detrend = o->detrend;
+    s->avg = o->avg;
+    return s;
+}
+
+void orc_stage_free(orc_stage *s)
+{
+    if (!s)
+        return;
+    orc_hbf8_free(s->hbf);
+    free(s->buf);
+    free(s->spectrum);
+    free(s->win);
+    free(s->c);
+    free(s);
+}
+
+void orc_stage_set_avg(orc_stage *s, uint32_t avg) { s->avg = avg; }       /* psd.rs:154-156 */
+void orc_stage_set_detrend(orc_stage *s, int d) { s->detrend = d; }        /* psd.rs:158-160 */
+
+size_t orc_stage_process(orc_stage *s, const float *x, size_t nx, float *y)
+{
+    const size_t N = (size_t)s->n;
+    size_t n = 0;
+    while (nx > 0) { /* psd.rs:199 */
+        /* load, psd.rs:201-208 */
+        size_t take = nx < N - s->idx ? nx : N - s->idx;
+        memcpy(s->buf + s->idx, x, take * sizeof(float));
+        x += take;
+        nx -= take;
+        s->idx += take;
+        if (s->idx < N)
+            break;
+
+        /* detrend and window, psd.rs:211; fft in place, psd.rs:213 */
+        if (orc_detrend_apply(s->detrend, s->buf, s->win, s->n, s->c) != 0)
+            abort(); /* Detrend::Linear panics in the reference */
+        orc_fft_forward(s->c, s->n);
+
+        int is_first = s->count == 0; /* psd.rs:215 */
+
+        /* normalize and keep for EWMA, psd.rs:218-225 */
+        float g;
+        if (s->count > s->avg) {
+            g = (float)s->avg / (float)s->count;
+            s->count = s->avg;
+        } else {
+            g = 1.0f;
+        }
+        s->count += 1;
+
+        /* power accumulate, psd.rs:228-233 (norm_sqr = re*re + im*im, unfused) */
+        for (size_t k = 0; k <= N / 2; k++) {
+            float re = s->c[2 * k], im = s->c[2 * k + 1];
+            s->spectrum[k] = g * s->spectrum[k] + (re * re + im * im);
+        }
+
+        size_t start; /* psd.rs:235-243 */
+        if (is_first) {
+            start = 0;
+        } else {
+            memmove(s->buf, s->buf + (N - s->overlap), s->overlap * sizeof(float));
+            start = s->overlap;
+        }
+
+        /* decimate, psd.rs:246-253 */
+        assert((N - start) % 8 == 0);
+        size_t chunks = (N - start) / 8;
+        orc_hbf8_block(s->hbf, s->buf + start, chunks, y + n);
+        /* drain, psd.rs:255-260 */
+        size_t skip = s->drain < chunks ? s->drain : chunks;
+        if (skip > 0) {
+            s->drain -= skip;
+            memmove(y + n, y + n + skip, (chunks - skip) * sizeof(float));
+        }
+        n += chunks - skip;
+
+        if (is_first) /* psd.rs:262-265 */
+            memmove(s->buf, s->buf + (N - s->overlap), s->overlap * sizeof(float));
+        s->idx = s->overlap; /* psd.rs:266 */
+    }
+    return n;
+}
+
+const float *orc_stage_spectrum(const orc_stage *s) { return s->spectrum; } /* psd.rs:271 */
+uint32_t orc_stage_count(const orc_stage *s) { return s->count; }           /* psd.rs:275 */
+
+float orc_stage_gain(const orc_stage *s)
+{
+    /* psd.rs:279-283: (N as u32 / 2 * count) as f32 * nenbw * power.
+     * The reference multiplies in u32 (overflows for count > 2^32/(N/2)); the oracle
+     * multiplies in u64 -- identical whenever the reference does not overflow. */
+    uint64_t nc = (uint64_t)((uint32_t)s->n / 2) * (uint64_t)s->count;
+    return (float)nc * s->nenbw * s->power;
+}
+
+size_t orc_stage_buf(const orc_stage *s, float *out)
+{
+    if (out)
+        memcpy(out, s->buf, s->idx * sizeof(float));
+    return s->idx;
+}
+
+/* ------------------------------------------------------------------------------------------
+ * PsdCascade<N> (psd.rs:399-544)
+ * ------------------------------------------------------------------------------------------ */
+#define ORC_MAX_STAGES 24
+struct orc_cascade {
+    int n;
+    int hbf_preset;
+    orc_stage *stages[ORC_MAX_STAGES];
+    size_t n_stages;
+    int detrend;
+    uint32_t avg_limit, avg_count;
+    float *a0, *a1;
+};
+
+orc_cascade *orc_cascade_new(int n, int hbf_preset)
+{
+    orc_stage *probe = orc_stage_new(n, ORC_WINDOW_HANN, hbf_preset);
+    if (!probe)
+        return NULL;
+    orc_stage_free(probe);
+    orc_cascade *c = (orc_cascade *)calloc(1, sizeof(*c));
+    c->n = n;
+    c->hbf_preset = hbf_preset;
+    c->detrend = ORC_DETREND_NONE;              /* psd.rs:418 */
+    c->avg_limit = UINT32_MAX;                  /* psd.rs:369-376 */
+    c->avg_count = UINT32_MAX;
+    c->a0 = (float *)calloc((size_t)n, sizeof(float));
+    c->a1 = (float *)calloc((size_t)n, sizeof(float));
+    return c;
+}
+
+orc_cascade *orc_cascade_clone(const orc_cascade *o)
+{
+    orc_cascade *c = orc_cascade_new(o->n, o->hbf_preset);
+    c->detrend = o->detrend;
+    c->avg_limit = o->avg_limit;
+    c->avg_count = o->avg_count;
+    c->n_stages = o->n_stages;
+    for (size_t i = 0; i < o->n_stages; i++)
+        c->stages[i] = orc_stage_clone(o->stages[i]);
+    return c;
+}
+
+void orc_cascade_free(orc_cascade *c)
+{
+    if (!c)
+        return;
+    for (size_t i = 0; i < c->n_stages; i++)
+        orc_stage_free(c->stages[i]);
+    free(c->a0);
+    free(c->a1);
+    free(c);
+}
+
+float orc_cascade_rbw(const orc_cascade *c)
+{
+    /* psd.rs:427-429 */
+    return (float)(1 << ORC_DEPTH) / ((float)c->n * orc_hbf_passband());
+}
+
+static uint32_t stage_avg(const orc_cascade *c, size_t i)
+{
+    /* (avg.count >> (DEPTH * i)).min(avg.limit), psd.rs:434,449.  A shift >= 32 panics in a debug
+     * build of the reference and is masked in release; stages that deep are unreachable. */
+    unsigned sh = (unsigned)(ORC_DEPTH * i);
+    uint32_t v = sh >= 32 ? 0u : (c->avg_count >> sh);
+    return v < c->avg_limit ? v : c->avg_limit;
+}
+
+void orc_cascade_set_avg(orc_cascade *c, uint32_t limit, uint32_t count)
+{
+    c->avg_limit = limit; /* psd.rs:431-436 */
+    c->avg_count = count;
+    for (size_t i = 0; i < c->n_stages; i++)
+        orc_stage_set_avg(c->stages[i], stage_avg(c, i));
+}
+
+void orc_cascade_set_detrend(orc_cascade *c, int d)
+{
+    c->detrend = d; /* psd.rs:438-443 */
+    for (size_t i = 0; i < c->n_stages; i++)
+        orc_stage_set_detrend(c->stages[i], d);
+}
+
+static orc_stage *get_or_add(orc_cascade *c, size_t i)
+{
+    while (i >= c->n_stages) { /* psd.rs:445-453 */
+        assert(c->n_stages < ORC_MAX_STAGES);
+        orc_stage *s = orc_stage_new(c->n, ORC_WINDOW_HANN, c->hbf_preset);
+        orc_stage_set_detrend(s, c->detrend);
+        orc_stage_set_avg(s, stage_avg(c, c->n_stages));
+        c->stages[c->n_stages++] = s;
+    }
+    return c->stages[i];
+}
+
+void orc_cascade_process(orc_cascade *c, const float *x, size_t n)
+{
+    /* psd.rs:456-468 */
+    const size_t chunk = (size_t)c->n << ORC_DEPTH;
+    float *y = c->a0, *z = c->a1;
+    for (size_t off = 0; off < n; off += chunk) {
+        const float *xp = x + off;
+        size_t len = n - off < chunk ? n - off : chunk;
+        size_t i = 0;
+        while (len > 0) {
+            size_t m = orc_stage_process(get_or_add(c, i), xp, len, y);
+            float *t = z;
+            z = y;
+            y = t;
+            xp = z;
+            len = m;
+            i++;
+        }
+    }
+}
+
+size_t orc_cascade_num_stages(const orc_cascade *c) { return c->n_stages; }
+const orc_stage *orc_cascade_stage(const orc_cascade *c, size_t i) { return c->stages[i]; }
+
+size_t orc_cascade_psd(const orc_cascade *c, int keep_overlap, uint32_t min_count,
+                       int keep_transition_band, float *p, orc_break *b, size_t *nb)
+{
+    /* psd.rs:479-543 */
+    const size_t N = (size_t)c->n;
+    size_t plen = 0, blen = 0;
+    uint64_t decimation = (uint64_t)1 << (ORC_DEPTH * c->n_stages);
+    size_t end = 0;
+    for (size_t r = c->n_stages; r-- > 0;) {
+        const orc_stage *st = c->stages[r];
+        decimation >>= ORC_DEPTH;
+        size_t start = !keep_overlap ? (end + (1u << ORC_DEPTH) - 1) >> ORC_DEPTH : 0;
+        end = (decimation > 1 && !keep_transition_band) ? 2 * N / 5 : N / 2 + 1;
+        int include = st->count >= min_count;
+        orc_break *bk = &b[blen++];
+        memset(bk, 0, sizeof(*bk));
+        bk->start = plen;
+        bk->count = st->count;
+        bk->include = (uint32_t)include;
+        bk->avg = st->avg;
+        bk->bins_start = start;
+        bk->bins_end = end;
+        bk->fft_size = N;
+        bk->decimation = decimation;
+        uint32_t cm1 = st->count > 0 ? st->count - 1 : 0; /* saturating_sub(1) */
+        bk->processed = (uint64_t)N * st->count - (uint64_t)st->overlap * cm1;
+        bk->pending = st->idx;
+        if (include) {
+            float g = 1.0f / (orc_stage_gain(st) * (float)decimation);
+            for (size_t k = start; k < end; k++)
+                p[plen++] = st->spectrum[k] * g;
+        } else {
+            end = start;
+        }
+    }
+    *nb = blen;
+    return plen;
+}
+
+size_t orc_break_frequencies(const orc_break *b, size_t nb, float *f)
+{
+    /* psd.rs:315-327, rbw psd.rs:334-336 */
+    size_t n = 0;
+    for (size_t i = 0; i < nb; i++) {
+        if (!b[i].include)
+            continue;
+        float rbw = 1.0f / (float)(b[i].fft_size * b[i].decimation);
+        for (uint64_t k = b[i].bins_start; k < b[i].bins_end; k++)
+            f[n++] = (float)k * rbw;
+    }
+    return n;
+}
+
+/* ------------------------------------------------------------------------------------------
+ * Frame decode (de/frame.rs:25-60, de/data.rs) and loss (loss.rs)
+ * ------------------------------------------------------------------------------------------ */
+static inline int16_t rd_i16(const uint8_t *p) { return (int16_t)((uint16_t)p[0] | ((uint16_t)p[1] << 8)); }
+static inline int32_t rd_i32(const uint8_t *p)
+{
+    return (int32_t)((uint32_t)p[0] | ((uint32_t)p[1] << 8) | ((uint32_t)p[2] << 16) | ((uint32_t)p[3] << 24));
+}
+static inline int64_t rd_i64(const uint8_t *p)
+{
+    uint64_t lo = (uint32_t)rd_i32(p), hi = (uint32_t)rd_i32(p + 4);
+    return (int64_t)(lo | (hi << 32));
+}
+static inline float rd_f32(const uint8_t *p)
+{
+    int32_t v = rd_i32(p);
+    float f;
+    memcpy(&f, &v, 4);
+    return f;
+}
+
+int orc_frame_decode(const uint8_t *buf, size_t len, orc_header *hdr, float *const *traces,
+                     size_t *samples_per_trace, int *n_traces)
+{
+    if (len < 8)
+        return ORC_ESHORT; /* frame.rs:50 slice index panics */
+    /* Header::parse, frame.rs:25-38 */
+    if (buf[0] != 0x7b || buf[1] != 0x05)
+        return ORC_EHEADER;
+    uint8_t format = buf[2];
+    if (format < 1 || format > 4)
+        return ORC_EFORMAT; /* mod.rs:12-17 */
+    hdr->format = format;
+    hdr->batches = buf[3];
+    hdr->seq = (uint32_t)rd_i32(buf + 4);
+    const uint8_t *d = buf + 8;
+    size_t dl = len - 8;
+    const size_t batches = hdr->batches;
+    static const size_t bsize[5] = {0, 64, 56, 80, 24};
+    if (dl % bsize[format] != 0)
+        return ORC_ESIZE; /* bytemuck::try_cast_slice -> PodCastError, data.rs:23,91,149,173 */
+    if (dl / bsize[format] != batches)
+        return ORC_EBATCHES; /* assert_eq!, data.rs:24,93,150,174 */
+
+    switch (format) {
+    case 1: { /* AdcDac::traces, data.rs:28-82 */
+        const float volt_per_lsb = 4.096f * 2.5f / 32768.0f; /* data.rs:31 */
+        for (size_t b = 0; b < batches; b++) {
+            const uint8_t *bp = d + 64 * b;
+            for (int i = 0; i < 8; i++) {
+                traces[0][8 * b + i] = (float)rd_i16(bp + 2 * i) * volt_per_lsb;
+                traces[1][8 * b + i] = (float)rd_i16(bp + 16 + 2 * i) * volt_per_lsb;
+                /* wrapping_add(i16::MIN): offset binary -> two's complement, data.rs:64,75 */
+                traces[2][8 * b + i] =
+                    (float)(int16_t)((uint16_t)rd_i16(bp + 32 + 2 * i) ^ 0x8000u) * volt_per_lsb;
+                traces[3][8 * b + i] =
+                    (float)(int16_t)((uint16_t)rd_i16(bp + 48 + 2 * i) ^ 0x8000u) * volt_per_lsb;
+            }
+        }
+        *n_traces = 4;
+        *samples_per_trace = 8 * batches;
+        return ORC_OK;
+    }
+    case 2: { /* Fls::traces, data.rs:97-139; batch = [[i32;7];2] */
+        const float i32max = (float)INT32_MAX; /* 2^31 after rounding */
+        const float tau = 6.28318530717958647692f;
+        for (size_t b = 0; b < batches; b++) {
+            const uint8_t *bp = d + 56 * b;
+            float re = (float)rd_i32(bp), im = (float)rd_i32(bp + 4);
+            traces[0][b] = sqrtf(re * re + im * im) * (1.0f / i32max);
+            traces[1][b] = (float)rd_i64(bp + 8) * (tau / 65536.0f);
+            traces[2][b] = (float)rd_i32(bp + 28) / i32max;
+            traces[3][b] = (float)rd_i32(bp + 32) / i32max;
+        }
+        *n_traces = 4;
+        *samples_per_trace = batches;
+        return ORC_OK;
+    }
+    case 3: { /* ThermostatEem::traces, data.rs:154-163; f32 words 0, 8, 13, 16 of 20 */
+        static const int idx[4] = {0, 8, 13, 16};
+        for (size_t b = 0; b < batches; b++)
+            for (int t = 0; t < 4; t++)
+                traces[t][b] = rd_f32(d + 80 * b + 4 * idx[t]);
+        *n_traces = 4;
+        *samples_per_trace = batches;
+        return ORC_OK;
+    }
+    default: { /* Mpll::traces, data.rs:178-211 */
+        const float tau = 6.28318530717958647692f;
+        const float two32 = 4294967296.0f;
+        const float k_phase = tau / two32;
+        const float k_freq = 1.0f / 1.28e-3f / two32;
+        const float k_amp = 10.24f / 10.0f * 2.0f * 2.0f / two32;
+        for (size_t b = 0; b < batches; b++) {
+            const uint8_t *bp = d + 24 * b;
+            traces[0][b] = (float)rd_i32(bp + 16) * k_phase;
+            traces[1][b] = (float)rd_i32(bp + 20) * k_freq;
+            float re = (float)rd_i32(bp), im = (float)rd_i32(bp + 4);
+            traces[2][b] = sqrtf(re * re + im * im) * k_amp;
+        }
+        *n_traces = 3;
+        *samples_per_trace = batches;
+        return ORC_OK;
+    }
+    }
+}
+
+void orc_loss_update(orc_loss *l, uint32_t seq, uint8_t batches)
+{
+    /* loss.rs:11-26 */
+    l->received += batches;
+    if (l->has_seq) {
+        uint64_t missing = (uint32_t)(seq - l->seq);
+        l->dropped += missing;
+    }
+    l->seq = seq + batches;
+    l->has_seq = 1;
+}
+
+float orc_loss_ratio(const orc_loss *l)
+{
+    /* loss.rs:29-30 */
+    return (float)l->dropped / (float)(l->received + l->dropped);
+}
+
+/* ------------------------------------------------------------------------------------------
+ * Var::eval (var.rs:26-45)
+ * ------------------------------------------------------------------------------------------ */
+static float powi_f32(float x, int e)
+{
+    /* f32::powi: repeated multiplication (llvm.powi), negative exponent -> reciprocal */
+    int n = e < 0 ? -e : e;
+    float r = 1.0f, b = x;
+    while (n) {
+        if (n & 1)
+            r *= b;
+        b *= b;
+        n >>= 1;
+    }
+    return e < 0 ? 1.0f / r : r;
+}
+
+float orc_var_eval(int x_exp, int sinx_exp, float clip, size_t dc_cut, const float *phase_psd,
+                   const float *frequencies, size_t n, float tau)
+{
+    const float pi = 3.14159265358979323846f;
+    float accu = 0.0f, a0 = 0.0f, f0 = 0.0f;
+    for (size_t i = dc_cut; i < n; i++) {
+        float sp = phase_psd[i], f = frequencies[i];
+        if (!(f <= clip / tau))
+            break; /* take_while */
+        float sy = sp * f * f;
+        float pft = pi * (f * tau);
+        float hahd = powi_f32(sinf(pft), sinx_exp) * powi_f32(pft, x_exp);
+        float a = sy * hahd;
+        accu = accu + (a + a0) * (f - f0);
+        a0 = a;
+        f0 = f;
+    }
+    return accu;
+}
