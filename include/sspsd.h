@@ -1,0 +1,258 @@
+/* sspsd.h -- C ABI of the B200-native cascaded power-spectral-density library.
+ *
+ * Drop-in boundary for the hot path of quartiq/stabilizer-stream: every entry point replaces one
+ * item of the reference's Rust API (file:line cited per function, relative to the reference
+ * repository).  The reference has no FFI of its own; this is the interface its `gpu` module would
+ * bind (see INTEGRATION.md for the Rust `extern "C"` block, build.rs and safe wrappers).
+ *
+ * Conventions
+ *   - every function returns an int32 status (SSPSD_OK == 0); nothing unwinds or aborts across the
+ *     boundary; sspsd_last_error() gives a thread-local human-readable message for the last failure;
+ *   - all pointers are borrowed for the duration of the call only; the caller owns output buffers;
+ *     variable-length outputs use "capacity in / length out" size_t* parameters and return
+ *     SSPSD_ESHORT (with the needed length written) when the capacity is too small;
+ *   - `mem` says where a buffer lives: SSPSD_MEM_HOST (pageable or pinned host memory) or
+ *     SSPSD_MEM_DEVICE (memory of the handle's CUDA device);
+ *   - a handle is not thread-safe but may be moved between threads (`Send`, like the reference's
+ *     PsdCascade, src/bin/psd.rs:170-176); distinct handles are independent;
+ *   - all device work of a handle is ordered on one CUDA stream; calls that return data to the
+ *     host synchronise that stream, process() on device memory does not;
+ *   - there is no CPU fallback: if no CUDA device is usable every create call fails with
+ *     SSPSD_ECUDA.
+ */
+#ifndef SSPSD_H
+#define SSPSD_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SSPSD_VERSION 1
+
+/* status codes */
+enum {
+    SSPSD_OK = 0,
+    SSPSD_EINVAL = 1,         /* bad argument (NULL handle, unsupported N, ...) */
+    SSPSD_EUNIMPLEMENTED = 2, /* Detrend::Linear: `unimplemented!()` in the reference, src/psd.rs:110 */
+    SSPSD_ECUDA = 3,          /* CUDA runtime error / no device */
+    SSPSD_ENOMEM = 4,
+    SSPSD_EHEADER = 5,        /* de::Error::InvalidHeader, src/de/mod.rs:21-22 */
+    SSPSD_EFORMAT = 6,        /* de::Error::UnknownFormat, src/de/mod.rs:23-24 */
+    SSPSD_ESIZE = 7,          /* de::Error::PayloadSize,   src/de/mod.rs:25-26 */
+    SSPSD_EBATCHES = 8,       /* header batch count != payload batches: assert_eq! panic, src/de/data.rs:24,93,150,174 */
+    SSPSD_ESHORT = 9,         /* output capacity too small, or frame shorter than its header (src/de/frame.rs:50 panics) */
+    SSPSD_ENCCL = 10          /* reserved for collective failures */
+};
+
+enum { SSPSD_MEM_HOST = 0, SSPSD_MEM_DEVICE = 1 };
+
+/* Window<N>::rectangular / ::hann, src/psd.rs:24-55 */
+enum { SSPSD_WINDOW_RECT = 0, SSPSD_WINDOW_HANN = 1 };
+
+/* enum Detrend, src/psd.rs:59-72 */
+enum {
+    SSPSD_DETREND_NONE = 0,
+    SSPSD_DETREND_MIDPOINT = 1,
+    SSPSD_DETREND_SPAN = 2,
+    SSPSD_DETREND_MEAN = 3,
+    SSPSD_DETREND_LINEAR = 4 /* rejected with SSPSD_EUNIMPLEMENTED */
+};
+
+/* Half-band decimator tap family restating idsp::hbf (src/psd.rs:2,124,246-253).
+ * 140 = idsp HBF_TAPS ("140 dB"), 98 = idsp HBF_TAPS_98.  See DESIGN.md "parity unpinned". */
+enum { SSPSD_HBF_98 = 0, SSPSD_HBF_140 = 1 };
+
+/* const DEPTH, src/psd.rs:117: every stage decimates by 1 << 3 */
+#define SSPSD_DEPTH 3
+#define SSPSD_MAX_STAGES 16
+
+typedef struct {
+    uint32_t n_fft;      /* const generic N of Psd<N>/PsdCascade<N>; power of two, 64..8192 */
+    int32_t window;      /* SSPSD_WINDOW_*; PsdCascade::default() uses Hann, src/psd.rs:419 */
+    int32_t hbf;         /* SSPSD_HBF_* */
+    int32_t device;      /* CUDA device ordinal */
+    void *stream;        /* cudaStream_t to order all work on, or NULL for a private stream */
+    uint64_t max_batch;  /* largest number of samples handed to one kernel batch (0 = default 1<<26) */
+    uint64_t host_stage; /* host-pointer process() calls are staged in pinned memory and launched once
+                            this many samples are pending (0 = default 1<<22); psd()/set_*()/flush() launch
+                            whatever is staged */
+} sspsd_config;
+
+/* AvgOpts, src/psd.rs:360-376 */
+typedef struct {
+    uint32_t limit;
+    uint32_t count;
+} sspsd_avg_opts;
+
+/* MergeOpts, src/psd.rs:339-358 */
+typedef struct {
+    uint32_t keep_overlap;
+    uint32_t min_count;
+    uint32_t keep_transition_band;
+} sspsd_merge_opts;
+
+/* struct Break, src/psd.rs:290-311 (`bins: Range<usize>` is bins_start..bins_end) */
+typedef struct {
+    uint64_t start;
+    uint32_t include;
+    uint32_t count;
+    uint32_t avg;
+    uint32_t _pad;
+    uint64_t bins_start;
+    uint64_t bins_end;
+    uint64_t fft_size;
+    uint64_t decimation;
+    uint64_t pending;
+    uint64_t processed;
+} sspsd_break;
+
+const char *sspsd_last_error(void);
+/* fills cfg with PsdCascade::default() (src/psd.rs:408-423): Hann, HBF_140, device 0 */
+int32_t sspsd_config_default(uint32_t n_fft, sspsd_config *cfg);
+
+/* ---------------------------------------------------------------------------------------------
+ * PsdCascade<N>, src/psd.rs:399-544
+ * --------------------------------------------------------------------------------------------- */
+typedef struct sspsd_cascade sspsd_cascade;
+
+/* PsdCascade::default(), src/psd.rs:408-423 */
+int32_t sspsd_cascade_create(const sspsd_config *cfg, sspsd_cascade **out);
+/* Drop */
+void sspsd_cascade_destroy(sspsd_cascade *h);
+/* #[derive(Clone)], src/psd.rs:399: deep copy of all per-stage state on the same device */
+int32_t sspsd_cascade_clone(sspsd_cascade *h, sspsd_cascade **out);
+/* `dec.clear()` + fresh default (Cmd::Reset, src/bin/psd.rs:190): forget all stages, keep options */
+int32_t sspsd_cascade_reset(sspsd_cascade *h);
+/* PsdCascade::process(&mut self, x: &[f32]), src/psd.rs:455-468.  Any n including 0.  Results do not
+ * depend on how the stream is split over calls. */
+int32_t sspsd_cascade_process_f32(sspsd_cascade *h, const float *x, size_t n, int32_t mem);
+/* PsdCascade::set_avg(AvgOpts), src/psd.rs:431-436; applies to segments completed after the call */
+int32_t sspsd_cascade_set_avg(sspsd_cascade *h, sspsd_avg_opts avg);
+/* PsdCascade::set_detrend(Detrend), src/psd.rs:438-443 */
+int32_t sspsd_cascade_set_detrend(sspsd_cascade *h, int32_t detrend);
+/* PsdCascade::rbw(), src/psd.rs:427-429 */
+int32_t sspsd_cascade_rbw(const sspsd_cascade *h, float *rbw);
+/* PsdCascade::psd(&MergeOpts) -> (Vec<f32>, Vec<Break>), src/psd.rs:479-543.
+ * p_len / b_len: capacity in, length out.  p needs at most stages*(N/2+1) floats. */
+int32_t sspsd_cascade_psd(sspsd_cascade *h, const sspsd_merge_opts *opts, float *p, size_t *p_len,
+                          sspsd_break *b, size_t *b_len);
+/* number of stages currently alive (self.stages.len()) */
+int32_t sspsd_cascade_num_stages(sspsd_cascade *h, uint32_t *n);
+/* launch everything staged from host-pointer process() calls */
+int32_t sspsd_cascade_flush(sspsd_cascade *h);
+/* flush + wait for the handle's stream */
+int32_t sspsd_cascade_sync(sspsd_cascade *h);
+
+/* Break::frequencies(&[Break]) -> Vec<f32>, src/psd.rs:315-327 (pure host helper) */
+int32_t sspsd_break_frequencies(const sspsd_break *b, size_t n_breaks, float *f, size_t *f_len);
+
+/* ---- partial-accumulator access for multi-GPU readout (north_star item 5; no reference analogue:
+ * the reference is single threaded, src/bin/psd.rs:170-183) ----
+ * The per-stage |X|^2 accumulators of a cascade live in ONE device array
+ * acc[SSPSD_MAX_STAGES][acc_stride] so that a single collective (NCCL sum over NVLink) can combine
+ * the partial sums of several GPUs that processed disjoint segment ranges of the same stream. */
+typedef struct {
+    float *acc;          /* device pointer, SSPSD_MAX_STAGES * acc_stride floats */
+    uint64_t acc_stride; /* floats per stage (>= N/2+1) */
+    uint32_t n_stages;
+    uint32_t _pad;
+    uint64_t count_raw[SSPSD_MAX_STAGES]; /* segments accumulated per stage */
+} sspsd_partials;
+int32_t sspsd_cascade_partials(sspsd_cascade *h, sspsd_partials *out);
+/* overwrite the per-stage segment counts after an external reduction of `acc` (boxcar averaging only) */
+int32_t sspsd_cascade_set_counts(sspsd_cascade *h, const uint64_t *count_raw, uint32_t n_stages);
+
+/* ---------------------------------------------------------------------------------------------
+ * Psd<N> + trait PsdStage, src/psd.rs:119-288 (a single stage with its decimated output exposed)
+ * --------------------------------------------------------------------------------------------- */
+typedef struct sspsd_stage sspsd_stage;
+
+/* Psd::new(fft, win), src/psd.rs:137-152 (the FFT plan is internal) */
+int32_t sspsd_stage_create(const sspsd_config *cfg, sspsd_stage **out);
+void sspsd_stage_destroy(sspsd_stage *h);
+/* Psd::set_avg / set_detrend, src/psd.rs:154-160 */
+int32_t sspsd_stage_set_avg(sspsd_stage *h, uint32_t avg);
+int32_t sspsd_stage_set_detrend(sspsd_stage *h, int32_t detrend);
+/* PsdStage::process(x, y) -> &mut y[..n], src/psd.rs:196-269.  y_len: capacity in, length out */
+int32_t sspsd_stage_process_f32(sspsd_stage *h, const float *x, size_t n, int32_t x_mem, float *y,
+                                size_t *y_len, int32_t y_mem);
+/* PsdStage::spectrum(): N/2+1 accumulated powers, src/psd.rs:271-273 */
+int32_t sspsd_stage_spectrum(sspsd_stage *h, float *out, size_t *len, int32_t mem);
+/* PsdStage::count(), src/psd.rs:275-277 */
+int32_t sspsd_stage_count(sspsd_stage *h, uint32_t *count);
+/* PsdStage::gain(), src/psd.rs:279-283 (the N/2*count product is formed in 64 bits) */
+int32_t sspsd_stage_gain(sspsd_stage *h, float *gain);
+/* PsdStage::buf(): currently buffered input items incl. overlap, src/psd.rs:285-287 */
+int32_t sspsd_stage_buf(sspsd_stage *h, float *out, size_t *len, int32_t mem);
+
+/* ---------------------------------------------------------------------------------------------
+ * Frame decode + loss accounting, src/de/{frame,data}.rs, src/loss.rs
+ * --------------------------------------------------------------------------------------------- */
+/* enum Format, src/de/mod.rs:9-17 */
+enum { SSPSD_FORMAT_ADCDAC = 1, SSPSD_FORMAT_FLS = 2, SSPSD_FORMAT_THERMOSTAT_EEM = 3, SSPSD_FORMAT_MPLL = 4 };
+#define SSPSD_MAX_TRACES 4
+#define SSPSD_HEADER_SIZE 8 /* src/de/frame.rs:8 */
+
+/* struct Loss, src/loss.rs:4-8 (`seq: Option<u32>` is has_seq + seq) */
+typedef struct {
+    uint64_t received;
+    uint64_t dropped;
+    uint32_t seq;
+    uint32_t has_seq;
+} sspsd_loss;
+
+typedef struct sspsd_decoder sspsd_decoder;
+int32_t sspsd_decoder_create(int32_t device, void *stream, sspsd_decoder **out);
+void sspsd_decoder_destroy(sspsd_decoder *d);
+
+typedef struct {
+    uint32_t format;            /* Header.format of the batch (all frames of a call share it) */
+    uint32_t n_traces;          /* 4 (AdcDac, Fls, ThermostatEem) or 3 (Mpll) */
+    uint64_t samples_per_trace; /* f32 items written to each trace */
+    uint64_t frames_ok;         /* frames decoded before the first error (== n_frames on success) */
+} sspsd_decode_info;
+
+/* Batched Frame::from_bytes (src/de/frame.rs:49-60) + Loss::update (src/loss.rs:11-26) +
+ * payload.traces() (src/de/data.rs:28-82, 97-139, 154-163, 178-211) over n_frames equally sized
+ * frames (`frame_len` bytes each, `frame_stride` bytes apart -- the file source's fixed
+ * --frame-size, src/source.rs:29-31,135-148).  Traces are concatenated in frame order (lost frames
+ * are not gap filled, like the reference).  `traces[t]` must hold `trace_cap` floats each, in
+ * `traces_mem`.  On a malformed frame the call returns that frame's error code; `loss` and the
+ * traces then cover exactly the frames before it (info->frames_ok), like a caller looping over
+ * Frame::from_bytes would have seen. */
+int32_t sspsd_decode_frames(sspsd_decoder *d, const uint8_t *frames, size_t n_frames, size_t frame_len,
+                            size_t frame_stride, int32_t frames_mem, sspsd_loss *loss, float *const *traces,
+                            size_t trace_cap, int32_t traces_mem, sspsd_decode_info *info);
+
+/* Fused decode -> cascades: trace t of every frame is fed to cascades[t] (one PsdCascade per trace,
+ * src/bin/psd.rs:174-182) without the f32 traces ever leaving the device.  cascades[t] may be NULL
+ * to drop a trace. */
+int32_t sspsd_cascade_process_frames(sspsd_decoder *d, sspsd_cascade *const *cascades, uint32_t n_cascades,
+                                     const uint8_t *frames, size_t n_frames, size_t frame_len,
+                                     size_t frame_stride, int32_t frames_mem, sspsd_loss *loss,
+                                     sspsd_decode_info *info);
+
+/* Loss::update on one header (host helper, bit-exact u64/u32 wrapping arithmetic), src/loss.rs:11-26 */
+void sspsd_loss_update(sspsd_loss *loss, uint32_t seq, uint8_t batches);
+/* the ratio logged by Loss::analyze, src/loss.rs:28-30 */
+float sspsd_loss_ratio(const sspsd_loss *loss);
+
+/* ---------------------------------------------------------------------------------------------
+ * Var::eval (AVAR/MVAR/FVAR from a phase PSD), src/var.rs:26-45 -- host helper on psd() output
+ * --------------------------------------------------------------------------------------------- */
+typedef struct {
+    int32_t x_exp;    /* default -2 */
+    int32_t sinx_exp; /* default 4 */
+    float clip;       /* default f32::MAX */
+    uint32_t _pad;
+    uint64_t dc_cut;  /* default 2 */
+} sspsd_var;
+float sspsd_var_eval(const sspsd_var *v, const float *phase_psd, const float *frequencies, size_t n, float tau);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SSPSD_H */

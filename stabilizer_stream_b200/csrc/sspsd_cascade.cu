@@ -1,0 +1,968 @@
+// sspsd_cascade.cu -- host-side state machine + kernel launches of the device cascade.
+// See sspsd_cascade.cuh for the bookkeeping model and include/sspsd.h for the reference citations.
+#include "sspsd_cascade.cuh"
+
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+
+#include "sspsd_decim_kernel.cuh"
+#include "sspsd_stage_kernel.cuh"
+
+namespace sspsd {
+
+static thread_local std::string g_err;
+void set_error(const std::string& msg) { g_err = msg; }
+const char* last_error() { return g_err.c_str(); }
+
+bool cuda_ok(cudaError_t e, const char* what)
+{
+    if (e == cudaSuccess)
+        return true;
+    set_error(std::string(what) + ": " + cudaGetErrorString(e));
+    return false;
+}
+
+namespace {
+
+struct DeviceGuard {
+    int prev = -1;
+    bool ok = true;
+    explicit DeviceGuard(int dev)
+    {
+        if (cudaGetDevice(&prev) != cudaSuccess)
+            prev = -1;
+        ok = cuda_ok(cudaSetDevice(dev), "cudaSetDevice");
+    }
+    ~DeviceGuard()
+    {
+        if (prev >= 0)
+            cudaSetDevice(prev);
+    }
+};
+
+inline long long roundup4(long long v) { return (v + 3) & ~3ll; }
+
+// ---- kernel dispatch over the FFT size ----
+template <int LOG2N>
+int launch_stage_t(const StageParams& p, int grid, cudaStream_t s)
+{
+    size_t smem = stage_smem_bytes<LOG2N>(p.T, p.hop);
+    psd_stage_kernel<LOG2N><<<grid, Plan<LOG2N>::NT, smem, s>>>(p);
+    return cuda_ok(cudaGetLastError(), "psd_stage_kernel launch") ? SSPSD_OK : SSPSD_ECUDA;
+}
+
+template <int LOG2N>
+int prepare_stage_t(int hop, int budget_bytes, int* tmax)
+{
+    using PL = Plan<LOG2N>;
+    int t = 64;
+    while (t > 1 && (long long)stage_smem_bytes<LOG2N>(t, hop) > budget_bytes)
+        --t;
+    if ((long long)stage_smem_bytes<LOG2N>(t, hop) > budget_bytes) {
+        set_error("FFT size does not fit in shared memory");
+        return SSPSD_EINVAL;
+    }
+    *tmax = t;
+    (void)PL::N;
+    if (!cuda_ok(cudaFuncSetAttribute(psd_stage_kernel<LOG2N>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      (int)stage_smem_bytes<LOG2N>(t, hop)),
+                 "cudaFuncSetAttribute(psd_stage_kernel)"))
+        return SSPSD_ECUDA;
+    return SSPSD_OK;
+}
+
+#define SSPSD_FOR_SIZES(X) X(6) X(7) X(8) X(9) X(10) X(11) X(12) X(13)
+
+int launch_stage(int log2n, const StageParams& p, int grid, cudaStream_t s)
+{
+    switch (log2n) {
+#define X(L) \
+    case L:  \
+        return launch_stage_t<L>(p, grid, s);
+        SSPSD_FOR_SIZES(X)
+#undef X
+    default:
+        return SSPSD_EINVAL;
+    }
+}
+
+int prepare_stage(int log2n, int hop, int* tmax, int* nt)
+{
+    switch (log2n) {
+#define X(L)                                                                   \
+    case L:                                                                    \
+        *nt = Plan<L>::NT;                                                     \
+        return prepare_stage_t<L>(hop, Plan<L>::NT <= 256 ? 100 * 1024 : 200 * 1024, tmax);
+        SSPSD_FOR_SIZES(X)
+#undef X
+    default:
+        set_error("n_fft must be a power of two in 64..8192");
+        return SSPSD_EINVAL;
+    }
+}
+
+template <int MA, int MB, int MC>
+int launch_decim_t(const DecimParams& p, int grid, cudaStream_t s)
+{
+    using GE = DecGeom<MA, MB, MC>;
+    decim8_kernel<MA, MB, MC><<<grid, DEC_NT, GE::SMEM_FLOATS * sizeof(float), s>>>(p);
+    return cuda_ok(cudaGetLastError(), "decim8_kernel launch") ? SSPSD_OK : SSPSD_ECUDA;
+}
+
+int decim_halo(int preset)
+{
+    return preset == SSPSD_HBF_98 ? DecGeom<3, 6, 15>::HALO : DecGeom<5, 10, 23>::HALO;
+}
+
+int upload_taps_once(int device)
+{
+    static bool done[64] = {false};
+    if (device < 64 && done[device])
+        return SSPSD_OK;
+    static_assert(sizeof(sspsd_hbf_taps) == sizeof(float) * SSPSD_HBF_NPRESET * 3 * SSPSD_HBF_MAXTAPS, "tap table");
+    SSPSD_CUDA(cudaMemcpyToSymbol(c_hbf_taps, sspsd_hbf_taps, sizeof(sspsd_hbf_taps)));
+    SSPSD_CUDA(cudaFuncSetAttribute(decim8_kernel<5, 10, 23>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    (int)(DecGeom<5, 10, 23>::SMEM_FLOATS * sizeof(float))));
+    SSPSD_CUDA(cudaFuncSetAttribute(decim8_kernel<3, 6, 15>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    (int)(DecGeom<3, 6, 15>::SMEM_FLOATS * sizeof(float))));
+    if (device < 64)
+        done[device] = true;
+    return SSPSD_OK;
+}
+
+__global__ void set_small_kernel(float* dst, int n, float v0, float v1, float v2)
+{
+    if (threadIdx.x == 0) {
+        if (n > 0) dst[0] = v0;
+        if (n > 1) dst[1] = v1;
+        if (n > 2) dst[2] = v2;
+    }
+}
+
+// EWMA bookkeeping for a batch of S segments, psd.rs:215-225
+struct EwmaPlan {
+    int jb;         // first segment of the batch whose factor differs from 1 (>= S: pure boxcar)
+    float g_first;  // factor applied at segment jb
+    float g_s;      // factor applied at every later segment: avg / (avg + 1)
+    float total;    // product of all factors (scales the running sum before the batch)
+    uint32_t count_after;
+};
+
+EwmaPlan ewma_plan(uint32_t count, uint32_t avg, uint64_t S)
+{
+    EwmaPlan e{};
+    uint32_t steady = avg + 1u;  // count in the steady state (wraps only for avg == u32::MAX, unused then)
+    e.g_s = (float)avg / (float)steady;
+    uint64_t jb;
+    if (count > avg) {
+        jb = 0;
+        e.g_first = (float)avg / (float)count;
+    } else {
+        jb = (uint64_t)avg - count + 1;
+        e.g_first = e.g_s;
+    }
+    if (jb >= S) {
+        e.jb = (int)S;
+        e.total = 1.0f;
+        e.count_after = (uint32_t)(count + S);
+    } else {
+        e.jb = (int)jb;
+        double t = (double)e.g_first;
+        uint64_t n_s = S - 1 - jb;
+        if (n_s > 0)
+            t *= std::pow((double)e.g_s, (double)n_s);
+        e.total = (float)t;
+        e.count_after = steady;
+    }
+    return e;
+}
+
+}  // namespace
+
+// =============================================================================================
+Cascade::~Cascade()
+{
+    if (n_ == 0)
+        return;
+    DeviceGuard g(cfg_.device);
+    if (stream_)
+        cudaStreamSynchronize(stream_);
+    for (auto& st : stages_) {
+        cudaFree(st.carry[0]);
+        cudaFree(st.carry[1]);
+        cudaFree(st.fresh);
+    }
+    cudaFree(d_win_);
+    cudaFree(d_twM_);
+    cudaFree(d_twN_);
+    cudaFree(d_acc_);
+    cudaFree(d_in_[0]);
+    cudaFree(d_in_[1]);
+    cudaFree(d_sink_);
+    if (h_stage_[0]) cudaFreeHost(h_stage_[0]);
+    if (h_stage_[1]) cudaFreeHost(h_stage_[1]);
+    if (h_acc_) cudaFreeHost(h_acc_);
+    for (int i = 0; i < 2; ++i) {
+        if (ev_copied_[i]) cudaEventDestroy(ev_copied_[i]);
+        if (ev_free_[i]) cudaEventDestroy(ev_free_[i]);
+        if (ev_stage_[i]) cudaEventDestroy(ev_stage_[i]);
+    }
+    if (copy_stream_) cudaStreamDestroy(copy_stream_);
+    if (own_stream_ && stream_) cudaStreamDestroy(stream_);
+}
+
+int Cascade::init(const sspsd_config& cfg, uint32_t max_stages)
+{
+    cfg_ = cfg;
+    uint32_t n = cfg.n_fft;
+    if (n < 64 || n > 8192 || (n & (n - 1))) {
+        set_error("n_fft must be a power of two in 64..8192");
+        return SSPSD_EINVAL;
+    }
+    if (cfg.window != SSPSD_WINDOW_RECT && cfg.window != SSPSD_WINDOW_HANN) {
+        set_error("unknown window");
+        return SSPSD_EINVAL;
+    }
+    if (cfg.hbf != SSPSD_HBF_98 && cfg.hbf != SSPSD_HBF_140) {
+        set_error("unknown half-band preset");
+        return SSPSD_EINVAL;
+    }
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+        set_error("no CUDA device: this library has no CPU fallback");
+        return SSPSD_ECUDA;
+    }
+    if (cfg.device < 0 || cfg.device >= ndev) {
+        set_error("bad device ordinal");
+        return SSPSD_EINVAL;
+    }
+    DeviceGuard g(cfg.device);
+    if (!g.ok)
+        return SSPSD_ECUDA;
+    uint32_t l2 = 0;
+    while ((1u << l2) < n) ++l2;
+    log2n_ = l2;
+    max_stages_ = std::min<uint32_t>(max_stages, SSPSD_MAX_STAGES);
+    if (cfg_.max_batch == 0) cfg_.max_batch = 1ull << 26;
+    if (cfg_.host_stage == 0) cfg_.host_stage = 1ull << 22;
+    cfg_.max_batch = std::max<uint64_t>(cfg_.max_batch, 16ull * n);
+    cfg_.max_batch = std::min<uint64_t>(cfg_.max_batch, 1ull << 30);
+
+    // Window::rectangular / ::hann, psd.rs:24-55 (same f32 expression as the reference)
+    std::vector<float> win(n);
+    if (cfg.window == SSPSD_WINDOW_RECT) {
+        std::fill(win.begin(), win.end(), 1.0f);
+        win_ = {1.0f, 1.0f, 0};
+    } else {
+        const float pi = 3.14159265358979323846f;
+        float df = pi / (float)n;
+        for (uint32_t i = 0; i < n; ++i) {
+            float s = sinf(df * (float)i);
+            win[i] = s * s;
+        }
+        win_ = {0.25f, 1.5f, n / 2};
+    }
+    hop_ = n - win_.overlap;
+    drain_ = sspsd_hbf_drain[cfg.hbf];
+    int halo = decim_halo(cfg.hbf);
+    hb_ = std::max<int>((int)win_.overlap, halo);
+    hb_ = (hb_ + 7) & ~7;
+
+    SSPSD_CUDA(cudaDeviceGetAttribute(&num_sms_, cudaDevAttrMultiProcessorCount, cfg.device));
+    if (cfg.stream) {
+        stream_ = (cudaStream_t)cfg.stream;
+    } else {
+        SSPSD_CUDA(cudaStreamCreateWithFlags(&stream_, cudaStreamNonBlocking));
+        own_stream_ = true;
+    }
+    SSPSD_CUDA(cudaStreamCreateWithFlags(&copy_stream_, cudaStreamNonBlocking));
+    for (int i = 0; i < 2; ++i) {
+        SSPSD_CUDA(cudaEventCreateWithFlags(&ev_copied_[i], cudaEventDisableTiming));
+        SSPSD_CUDA(cudaEventCreateWithFlags(&ev_free_[i], cudaEventDisableTiming));
+        SSPSD_CUDA(cudaEventCreateWithFlags(&ev_stage_[i], cudaEventDisableTiming));
+    }
+    int rc = upload_taps_once(cfg.device);
+    if (rc) return rc;
+    rc = prepare_stage((int)log2n_, (int)hop_, &tmax_, &nt_);
+    if (rc) return rc;
+
+    const uint32_t m = n / 2;
+    std::vector<float2> twM(m), twN(m);
+    for (uint32_t k = 0; k < m; ++k) {
+        double a = -2.0 * M_PI * (double)k / (double)m;
+        twM[k] = make_float2((float)std::cos(a), (float)std::sin(a));
+        double b = -2.0 * M_PI * (double)k / (double)n;
+        twN[k] = make_float2((float)std::cos(b), (float)std::sin(b));
+    }
+    acc_stride_ = (m + 1 + 63) & ~63u;
+    SSPSD_CUDA(cudaMalloc(&d_win_, n * sizeof(float)));
+    SSPSD_CUDA(cudaMalloc(&d_twM_, m * sizeof(float2)));
+    SSPSD_CUDA(cudaMalloc(&d_twN_, m * sizeof(float2)));
+    SSPSD_CUDA(cudaMalloc(&d_acc_, (size_t)SSPSD_MAX_STAGES * acc_stride_ * sizeof(float)));
+    SSPSD_CUDA(cudaMemcpyAsync(d_win_, win.data(), n * sizeof(float), cudaMemcpyHostToDevice, stream_));
+    SSPSD_CUDA(cudaMemcpyAsync(d_twM_, twM.data(), m * sizeof(float2), cudaMemcpyHostToDevice, stream_));
+    SSPSD_CUDA(cudaMemcpyAsync(d_twN_, twN.data(), m * sizeof(float2), cudaMemcpyHostToDevice, stream_));
+    SSPSD_CUDA(cudaMemsetAsync(d_acc_, 0, (size_t)SSPSD_MAX_STAGES * acc_stride_ * sizeof(float), stream_));
+    SSPSD_CUDA(cudaMallocHost(&h_acc_, (size_t)SSPSD_MAX_STAGES * acc_stride_ * sizeof(float)));
+    SSPSD_CUDA(cudaStreamSynchronize(stream_));  // the host vectors above go out of scope
+    stages_.reserve(SSPSD_MAX_STAGES);
+    n_ = n;
+    return SSPSD_OK;
+}
+
+uint32_t Cascade::stage_avg(size_t i) const
+{
+    // (avg.count >> (DEPTH * i)).min(avg.limit), psd.rs:434,449
+    unsigned sh = (unsigned)(SSPSD_DEPTH * i);
+    uint32_t v = sh >= 32 ? 0u : (avg_.count >> sh);
+    return std::min(v, avg_.limit);
+}
+
+int Cascade::add_stage()
+{
+    // get_or_add, psd.rs:445-453 + Psd::new, psd.rs:137-152
+    if (stages_.size() >= SSPSD_MAX_STAGES) {
+        set_error("too many stages");
+        return SSPSD_EINVAL;
+    }
+    StageState st;
+    st.avg = single_stage_avg_set_ ? single_stage_avg_ : stage_avg(stages_.size());
+    const size_t cap = (size_t)hb_ + n_ + 16;
+    SSPSD_CUDA(cudaMalloc(&st.carry[0], cap * sizeof(float)));
+    SSPSD_CUDA(cudaMalloc(&st.carry[1], cap * sizeof(float)));
+    // zero history for g < 0: the decimator starts from HbfDec8::default() (psd.rs:141)
+    SSPSD_CUDA(cudaMemsetAsync(st.carry[0], 0, cap * sizeof(float), stream_));
+    SSPSD_CUDA(cudaMemsetAsync(st.carry[1], 0, cap * sizeof(float), stream_));
+    st.carry_start = -(long long)hb_;
+    SSPSD_CUDA(cudaMemsetAsync(d_acc_ + stages_.size() * acc_stride_, 0, acc_stride_ * sizeof(float), stream_));
+    stages_.push_back(st);
+    return SSPSD_OK;
+}
+
+int Cascade::ensure_fresh(StageState& st, size_t need)
+{
+    if (need <= st.fresh_cap)
+        return SSPSD_OK;
+    // earlier batches may still be reading the old buffer on the stream
+    if (st.fresh) {
+        SSPSD_CUDA(cudaStreamSynchronize(stream_));
+        SSPSD_CUDA(cudaFree(st.fresh));
+        st.fresh = nullptr;
+    }
+    size_t cap = std::max(need + 64, st.fresh_cap * 2);
+    SSPSD_CUDA(cudaMalloc(&st.fresh, cap * sizeof(float)));
+    st.fresh_cap = cap;
+    return SSPSD_OK;
+}
+
+int Cascade::launch_psd(size_t i, const StreamSrc& src, uint64_t k0, uint64_t nseg, int jb, float g_first, float g_s)
+{
+    StageParams p{};
+    p.src = src;
+    p.k0 = (long long)k0;
+    p.nseg = (int)nseg;
+    long long t = ((long long)nseg + 2ll * num_sms_ - 1) / (2ll * num_sms_);
+    p.T = (int)std::max<long long>(1, std::min<long long>(t, tmax_));
+    p.hop = (int)hop_;
+    p.detrend = detrend_;
+    p.tile_cap = (p.T - 1) * (int)hop_ + (int)n_;
+    p.win = d_win_;
+    p.twM = d_twM_;
+    p.twN = d_twN_;
+    p.acc = d_acc_ + i * acc_stride_;
+    p.jb = jb;
+    p.g_first = g_first;
+    p.g_s = g_s;
+    int grid = (int)((nseg + p.T - 1) / p.T);
+    return launch_stage((int)log2n_, p, grid, stream_);
+}
+
+int Cascade::launch_decim(size_t, const StreamSrc& src, uint64_t m0, uint64_t m1, float* out_fresh,
+                          long long out_split, float* out_carry, long long out_carry_start)
+{
+    DecimParams p{};
+    p.src = src;
+    p.m0 = (long long)m0;
+    p.m1 = (long long)m1;
+    p.drain = drain_;
+    p.out_fresh = out_fresh;
+    p.out_split = out_split;
+    p.out_carry = out_carry;
+    p.out_carry_start = out_carry_start;
+    p.preset = cfg_.hbf;
+    long long lo = std::max<long long>(p.m0, p.drain);
+    if (p.m1 <= lo)
+        return SSPSD_OK;
+    int grid = (int)((p.m1 - lo + DEC_OB - 1) / DEC_OB);
+    if (cfg_.hbf == SSPSD_HBF_98)
+        return launch_decim_t<3, 6, 15>(p, grid, stream_);
+    return launch_decim_t<5, 10, 23>(p, grid, stream_);
+}
+
+// One batch of one stage: n_new samples have been appended to the stage's stream (in `fresh` for
+// g >= split, in the carry sliver for L <= g < split).
+int Cascade::run_stage(size_t i, const float* fresh, long long split, uint64_t n_new)
+{
+    StageState& st = stages_[i];
+    const uint64_t L1 = st.L + n_new;
+    const uint64_t craw0 = st.craw;
+    const uint64_t craw1 = L1 < n_ ? 0 : 1 + (L1 - n_) / hop_;
+    const StreamSrc src{st.carry[st.cur], fresh, st.carry_start, split};
+    int rc;
+
+    if (craw1 > craw0) {
+        const uint64_t S = craw1 - craw0;
+        EwmaPlan e = ewma_plan(st.count, st.avg, S);
+        if (e.total != 1.0f) {
+            int nb = (int)(n_ / 2 + 1);
+            scale_kernel<<<(nb + 255) / 256, 256, 0, stream_>>>(d_acc_ + i * acc_stride_, nb, e.total);
+            SSPSD_CUDA(cudaGetLastError());
+        }
+        rc = launch_psd(i, src, craw0, S, e.jb, e.g_first, e.g_s);
+        if (rc) return rc;
+        st.count = e.count_after;
+    }
+
+    const uint64_t D0 = decimated(st);
+    st.craw = craw1;
+    const uint64_t D1 = decimated(st);
+    uint64_t n_next = 0;
+    long long nsplit = 0;
+    if (D1 > D0) {
+        const uint64_t m0 = D0 / 8, m1 = D1 / 8;
+        const uint64_t em1 = m1 > (uint64_t)drain_ ? m1 - drain_ : 0;
+        n_next = em1 - st.emitted;
+        if (n_next > 0) {
+            if (i + 1 >= max_stages_) {
+                // single-stage API: the decimated items of this call are collected in the sink
+                if (sink_len_ + n_next > sink_cap_) {
+                    set_error("internal: sink overflow");
+                    return SSPSD_EINVAL;
+                }
+                rc = launch_decim(i, src, m0, m1, d_sink_ + sink_len_, (long long)st.emitted, nullptr, 0);
+                if (rc) return rc;
+                sink_len_ += n_next;
+                n_next = 0;
+            } else {
+                if (i + 1 >= stages_.size()) {
+                    rc = add_stage();
+                    if (rc) return rc;
+                }
+                StageState& nx = stages_[i + 1];
+                nsplit = roundup4((long long)nx.L);
+                if ((long long)em1 > nsplit) {
+                    rc = ensure_fresh(nx, (size_t)((long long)em1 - nsplit));
+                    if (rc) return rc;
+                }
+                rc = launch_decim(i, src, m0, m1, nx.fresh, nsplit, nx.carry[nx.cur], nx.carry_start);
+                if (rc) return rc;
+            }
+            stages_[i].emitted = em1;
+        }
+    }
+
+    // next batch's carry: history for the decimator + pending samples, [D1 - hb, L1)
+    {
+        StageState& s2 = stages_[i];
+        const long long cs = (long long)D1 - hb_;
+        const int n = (int)((long long)L1 - cs);
+        carry_copy_kernel<<<std::max(1, std::min(64, (n + 255) / 256)), 256, 0, stream_>>>(src, cs, n, s2.carry[s2.cur ^ 1]);
+        SSPSD_CUDA(cudaGetLastError());
+        s2.cur ^= 1;
+        s2.carry_start = cs;
+        s2.L = L1;
+    }
+    if (n_next > 0)
+        return run_stage(i + 1, stages_[i + 1].fresh, nsplit, n_next);
+    return SSPSD_OK;
+}
+
+// x: device memory, valid in stream order
+int Cascade::feed_device_chunk(const float* x, size_t n)
+{
+    if (n == 0)
+        return SSPSD_OK;
+    int rc;
+    if (stages_.empty()) {
+        rc = add_stage();
+        if (rc) return rc;
+    }
+    StageState& st = stages_[0];
+    const long long split = roundup4((long long)st.L);
+    const size_t sliver = std::min<size_t>((size_t)(split - (long long)st.L), n);
+    if (sliver)
+        SSPSD_CUDA(cudaMemcpyAsync(st.carry[st.cur] + ((long long)st.L - st.carry_start), x, sliver * sizeof(float),
+                                   cudaMemcpyDeviceToDevice, stream_));
+    const float* fresh = x + sliver;
+    const size_t rest = n - sliver;
+    if (rest && (reinterpret_cast<uintptr_t>(fresh) & 15u)) {
+        // unaligned device input: realign through the staging buffer (one extra device copy)
+        rc = ensure_in_buffers(rest);
+        if (rc) return rc;
+        SSPSD_CUDA(cudaMemcpyAsync(d_in_[in_buf_], fresh, rest * sizeof(float), cudaMemcpyDeviceToDevice, stream_));
+        fresh = d_in_[in_buf_];
+        in_buf_ ^= 1;
+    }
+    return run_stage(0, fresh, split, n);
+}
+
+int Cascade::process_device(const float* x, size_t n)
+{
+    size_t pos = 0;
+    while (pos < n) {
+        size_t c = std::min<size_t>(n - pos, cfg_.max_batch);
+        int rc = feed_device_chunk(x + pos, c);
+        if (rc) return rc;
+        pos += c;
+    }
+    return SSPSD_OK;
+}
+
+int Cascade::ensure_in_buffers(size_t need)
+{
+    if (need <= d_in_cap_)
+        return SSPSD_OK;
+    SSPSD_CUDA(cudaStreamSynchronize(stream_));
+    SSPSD_CUDA(cudaStreamSynchronize(copy_stream_));
+    for (int i = 0; i < 2; ++i) {
+        if (d_in_[i]) SSPSD_CUDA(cudaFree(d_in_[i]));
+        d_in_[i] = nullptr;
+    }
+    size_t cap = need + 64;
+    for (int i = 0; i < 2; ++i)
+        SSPSD_CUDA(cudaMalloc(&d_in_[i], cap * sizeof(float)));
+    d_in_cap_ = cap;
+    return SSPSD_OK;
+}
+
+// One chunk of host samples: H2D on the copy stream (double buffered against the compute stream)
+int Cascade::feed_host_chunk(const float* xh, size_t n)
+{
+    if (n == 0)
+        return SSPSD_OK;
+    int rc;
+    if (stages_.empty()) {
+        rc = add_stage();
+        if (rc) return rc;
+    }
+    rc = ensure_in_buffers(std::min<uint64_t>(std::max<uint64_t>(n, host_chunk()), cfg_.max_batch));
+    if (rc) return rc;
+    StageState& st = stages_[0];
+    const long long split = roundup4((long long)st.L);
+    const size_t sliver = std::min<size_t>((size_t)(split - (long long)st.L), n);
+    if (sliver) {
+        // <= 3 samples complete the carry's last float4 group; passed by value, no host lifetime issue
+        float v[3] = {0.f, 0.f, 0.f};
+        for (size_t q = 0; q < sliver; ++q) v[q] = xh[q];
+        set_small_kernel<<<1, 32, 0, stream_>>>(st.carry[st.cur] + ((long long)st.L - st.carry_start), (int)sliver,
+                                                v[0], v[1], v[2]);
+        SSPSD_CUDA(cudaGetLastError());
+    }
+    const size_t rest = n - sliver;
+    const int b = in_buf_;
+    if (rest) {
+        SSPSD_CUDA(cudaStreamWaitEvent(copy_stream_, ev_free_[b], 0));
+        SSPSD_CUDA(cudaMemcpyAsync(d_in_[b], xh + sliver, rest * sizeof(float), cudaMemcpyHostToDevice, copy_stream_));
+        SSPSD_CUDA(cudaEventRecord(ev_copied_[b], copy_stream_));
+        SSPSD_CUDA(cudaStreamWaitEvent(stream_, ev_copied_[b], 0));
+        last_copy_ = b;
+    }
+    rc = run_stage(0, d_in_[b], split, n);
+    if (rc) return rc;
+    if (rest) {
+        SSPSD_CUDA(cudaEventRecord(ev_free_[b], stream_));
+        in_buf_ ^= 1;
+    }
+    return SSPSD_OK;
+}
+
+int Cascade::flush_staged()
+{
+    if (staged_ == 0)
+        return SSPSD_OK;
+    const int hb = stage_buf_;
+    int rc = feed_host_chunk(h_stage_[hb], staged_);
+    if (rc) return rc;
+    // the pinned buffer may be refilled only after this H2D copy has completed
+    SSPSD_CUDA(cudaEventRecord(ev_stage_[hb], copy_stream_));
+    stage_pending_[hb] = true;
+    staged_ = 0;
+    stage_buf_ ^= 1;
+    if (stage_pending_[stage_buf_]) {
+        SSPSD_CUDA(cudaEventSynchronize(ev_stage_[stage_buf_]));
+        stage_pending_[stage_buf_] = false;
+    }
+    return SSPSD_OK;
+}
+
+int Cascade::process_host(const float* x, size_t n)
+{
+    if (n == 0)
+        return SSPSD_OK;
+    int rc;
+    if (n < cfg_.host_stage) {
+        // small call (the reference's callers hand over 176..4096 items, src/source.rs:116-157):
+        // collect in pinned memory, launch once enough is pending
+        if (!h_stage_[0]) {
+            SSPSD_CUDA(cudaMallocHost(&h_stage_[0], cfg_.host_stage * sizeof(float)));
+            SSPSD_CUDA(cudaMallocHost(&h_stage_[1], cfg_.host_stage * sizeof(float)));
+        }
+        while (n) {
+            size_t take = std::min<size_t>(n, cfg_.host_stage - staged_);
+            std::memcpy(h_stage_[stage_buf_] + staged_, x, take * sizeof(float));
+            staged_ += take;
+            x += take;
+            n -= take;
+            if (staged_ == cfg_.host_stage) {
+                rc = flush_staged();
+                if (rc) return rc;
+            }
+        }
+        return SSPSD_OK;
+    }
+    rc = flush_staged();
+    if (rc) return rc;
+    const size_t chunk = (size_t)std::min<uint64_t>(host_chunk(), cfg_.max_batch);
+    size_t pos = 0;
+    last_copy_ = -1;
+    while (pos < n) {
+        size_t c = std::min(n - pos, chunk);
+        rc = feed_host_chunk(x + pos, c);
+        if (rc) return rc;
+        pos += c;
+    }
+    // the caller's buffer is borrowed for the call only: wait for the last H2D copy (not the compute)
+    if (last_copy_ >= 0)
+        SSPSD_CUDA(cudaEventSynchronize(ev_copied_[last_copy_]));
+    return SSPSD_OK;
+}
+
+int Cascade::process(const float* x, size_t n, int mem)
+{
+    if (n == 0)
+        return SSPSD_OK;  // psd.rs:459: no chunk, no stage
+    if (!x) {
+        set_error("null input");
+        return SSPSD_EINVAL;
+    }
+    DeviceGuard g(cfg_.device);
+    if (!g.ok) return SSPSD_ECUDA;
+    sink_len_ = 0;
+    if (max_stages_ == 1) {
+        // PsdStage::process returns at most n/8 + N/8 decimated items
+        size_t need = n / 8 + n_ / 8 + 16 + staged_ / 8;
+        if (need > sink_cap_) {
+            SSPSD_CUDA(cudaStreamSynchronize(stream_));
+            if (d_sink_) SSPSD_CUDA(cudaFree(d_sink_));
+            d_sink_ = nullptr;
+            SSPSD_CUDA(cudaMalloc(&d_sink_, need * sizeof(float)));
+            sink_cap_ = need;
+        }
+    }
+    if (mem == SSPSD_MEM_DEVICE) {
+        int rc = flush_staged();
+        if (rc) return rc;
+        return process_device(x, n);
+    }
+    if (mem != SSPSD_MEM_HOST) {
+        set_error("bad mem kind");
+        return SSPSD_EINVAL;
+    }
+    if (max_stages_ == 1) {
+        // the single-stage API returns its decimated output synchronously: no deferred staging
+        size_t pos = 0;
+        const size_t chunk = (size_t)std::min<uint64_t>(host_chunk(), cfg_.max_batch);
+        last_copy_ = -1;
+        while (pos < n) {
+            size_t c = std::min(n - pos, chunk);
+            int rc = feed_host_chunk(x + pos, c);
+            if (rc) return rc;
+            pos += c;
+        }
+        if (last_copy_ >= 0)
+            SSPSD_CUDA(cudaEventSynchronize(ev_copied_[last_copy_]));
+        return SSPSD_OK;
+    }
+    return process_host(x, n);
+}
+
+int Cascade::flush()
+{
+    DeviceGuard g(cfg_.device);
+    if (!g.ok) return SSPSD_ECUDA;
+    return flush_staged();
+}
+
+int Cascade::sync()
+{
+    DeviceGuard g(cfg_.device);
+    if (!g.ok) return SSPSD_ECUDA;
+    int rc = flush_staged();
+    if (rc) return rc;
+    SSPSD_CUDA(cudaStreamSynchronize(stream_));
+    return SSPSD_OK;
+}
+
+int Cascade::set_avg(sspsd_avg_opts a)
+{
+    // options apply to segments completed after the call: launch what is staged first
+    int rc = flush();
+    if (rc) return rc;
+    avg_ = a;  // psd.rs:431-436
+    for (size_t i = 0; i < stages_.size(); ++i)
+        stages_[i].avg = stage_avg(i);
+    return SSPSD_OK;
+}
+
+int Cascade::set_stage_avg(uint32_t avg)
+{
+    int rc = flush();
+    if (rc) return rc;
+    single_stage_avg_set_ = true;
+    single_stage_avg_ = avg;
+    if (!stages_.empty())
+        stages_[0].avg = avg;
+    return SSPSD_OK;
+}
+
+int Cascade::set_detrend(int d)
+{
+    if (d == SSPSD_DETREND_LINEAR) {
+        set_error("Detrend::Linear is unimplemented!() in the reference (src/psd.rs:110)");
+        return SSPSD_EUNIMPLEMENTED;
+    }
+    if (d < 0 || d > SSPSD_DETREND_LINEAR) {
+        set_error("unknown detrend");
+        return SSPSD_EINVAL;
+    }
+    int rc = flush();
+    if (rc) return rc;
+    detrend_ = d;  // psd.rs:438-443 (all stages share the option)
+    return SSPSD_OK;
+}
+
+int Cascade::reset()
+{
+    DeviceGuard g(cfg_.device);
+    if (!g.ok) return SSPSD_ECUDA;
+    SSPSD_CUDA(cudaStreamSynchronize(stream_));
+    SSPSD_CUDA(cudaStreamSynchronize(copy_stream_));
+    for (auto& st : stages_) {
+        cudaFree(st.carry[0]);
+        cudaFree(st.carry[1]);
+        cudaFree(st.fresh);
+    }
+    stages_.clear();
+    staged_ = 0;
+    sink_len_ = 0;
+    SSPSD_CUDA(cudaMemsetAsync(d_acc_, 0, (size_t)SSPSD_MAX_STAGES * acc_stride_ * sizeof(float), stream_));
+    return SSPSD_OK;
+}
+
+int Cascade::clone_from(Cascade& o)
+{
+    int rc = o.sync();
+    if (rc) return rc;
+    rc = init(o.cfg_, o.max_stages_);
+    if (rc) return rc;
+    DeviceGuard g(cfg_.device);
+    if (!g.ok) return SSPSD_ECUDA;
+    detrend_ = o.detrend_;
+    avg_ = o.avg_;
+    single_stage_avg_set_ = o.single_stage_avg_set_;
+    single_stage_avg_ = o.single_stage_avg_;
+    for (size_t i = 0; i < o.stages_.size(); ++i) {
+        rc = add_stage();
+        if (rc) return rc;
+        StageState& d = stages_[i];
+        const StageState& s = o.stages_[i];
+        d.L = s.L;
+        d.craw = s.craw;
+        d.count = s.count;
+        d.avg = s.avg;
+        d.emitted = s.emitted;
+        d.carry_start = s.carry_start;
+        d.cur = 0;
+        const size_t cap = (size_t)hb_ + n_ + 16;
+        SSPSD_CUDA(cudaMemcpyAsync(d.carry[0], s.carry[s.cur], cap * sizeof(float), cudaMemcpyDeviceToDevice, stream_));
+    }
+    SSPSD_CUDA(cudaMemcpyAsync(d_acc_, o.d_acc_, (size_t)SSPSD_MAX_STAGES * acc_stride_ * sizeof(float),
+                               cudaMemcpyDeviceToDevice, stream_));
+    SSPSD_CUDA(cudaStreamSynchronize(stream_));
+    return SSPSD_OK;
+}
+
+float Cascade::gain_of(uint32_t count) const
+{
+    // PsdStage::gain, psd.rs:279-283; N/2*count formed in 64 bits (the reference wraps in u32 for
+    // count > 2^32/(N/2))
+    uint64_t nc = (uint64_t)(n_ / 2) * (uint64_t)count;
+    return (float)nc * win_.nenbw * win_.power;
+}
+
+float Cascade::stage_gain() const { return gain_of(stages_.empty() ? 0 : stages_[0].count); }
+
+int Cascade::psd(const sspsd_merge_opts& o, float* p, size_t* p_len, sspsd_break* b, size_t* b_len)
+{
+    if (!p_len || !b_len) {
+        set_error("null length pointer");
+        return SSPSD_EINVAL;
+    }
+    int rc = sync();
+    if (rc) return rc;
+    DeviceGuard g(cfg_.device);
+    if (!g.ok) return SSPSD_ECUDA;
+    const size_t ns = stages_.size();
+    const size_t N = n_;
+    // first pass: sizes (PsdCascade::psd, psd.rs:479-543)
+    size_t plen = 0;
+    {
+        size_t end = 0;
+        uint64_t dec = 1ull << (SSPSD_DEPTH * ns);
+        for (size_t r = ns; r-- > 0;) {
+            dec >>= SSPSD_DEPTH;
+            size_t start = !o.keep_overlap ? (end + 7) >> 3 : 0;
+            end = (dec > 1 && !o.keep_transition_band) ? 2 * N / 5 : N / 2 + 1;
+            if (stages_[r].count >= o.min_count)
+                plen += end - start;
+            else
+                end = start;
+        }
+    }
+    const bool fits = (plen <= *p_len) && (ns <= *b_len) && (plen == 0 || p) && (ns == 0 || b);
+    *p_len = plen;
+    *b_len = ns;
+    if (!fits) {
+        set_error("output capacity too small");
+        return SSPSD_ESHORT;
+    }
+    if (ns == 0)
+        return SSPSD_OK;
+    SSPSD_CUDA(cudaMemcpyAsync(h_acc_, d_acc_, ns * acc_stride_ * sizeof(float), cudaMemcpyDeviceToHost, stream_));
+    SSPSD_CUDA(cudaStreamSynchronize(stream_));
+    size_t pl = 0, bl = 0, end = 0;
+    uint64_t dec = 1ull << (SSPSD_DEPTH * ns);
+    for (size_t r = ns; r-- > 0;) {
+        const StageState& st = stages_[r];
+        dec >>= SSPSD_DEPTH;
+        size_t start = !o.keep_overlap ? (end + 7) >> 3 : 0;
+        end = (dec > 1 && !o.keep_transition_band) ? 2 * N / 5 : N / 2 + 1;
+        bool include = st.count >= o.min_count;
+        sspsd_break& bk = b[bl++];
+        std::memset(&bk, 0, sizeof(bk));
+        bk.start = pl;
+        bk.include = include;
+        bk.count = st.count;
+        bk.avg = st.avg;
+        bk.bins_start = start;
+        bk.bins_end = end;
+        bk.fft_size = N;
+        bk.decimation = dec;
+        uint32_t cm1 = st.count > 0 ? st.count - 1 : 0;
+        bk.processed = (uint64_t)N * st.count - (uint64_t)win_.overlap * cm1;
+        bk.pending = st.craw ? st.L - st.craw * (uint64_t)hop_ : st.L;
+        if (include) {
+            float gg = 1.0f / (gain_of(st.count) * (float)dec);
+            const float* sp = h_acc_ + r * acc_stride_;
+            for (size_t k = start; k < end; ++k)
+                p[pl++] = sp[k] * gg;
+        } else {
+            end = start;
+        }
+    }
+    return SSPSD_OK;
+}
+
+int Cascade::partials(sspsd_partials* out)
+{
+    if (!out) return SSPSD_EINVAL;
+    int rc = flush();
+    if (rc) return rc;
+    std::memset(out, 0, sizeof(*out));
+    out->acc = d_acc_;
+    out->acc_stride = acc_stride_;
+    out->n_stages = (uint32_t)stages_.size();
+    for (size_t i = 0; i < stages_.size(); ++i)
+        out->count_raw[i] = stages_[i].craw;
+    return SSPSD_OK;
+}
+
+int Cascade::set_counts(const uint64_t* craw, uint32_t n)
+{
+    if (!craw || n > SSPSD_MAX_STAGES) return SSPSD_EINVAL;
+    DeviceGuard g(cfg_.device);
+    if (!g.ok) return SSPSD_ECUDA;
+    while (stages_.size() < n) {
+        int rc = add_stage();
+        if (rc) return rc;
+    }
+    for (uint32_t i = 0; i < n; ++i)
+        stages_[i].count = (uint32_t)std::min<uint64_t>(craw[i], 0xffffffffull);
+    return SSPSD_OK;
+}
+
+static int copy_out(float* dst, const float* src_dev, size_t n, int mem, cudaStream_t s)
+{
+    if (n == 0) return SSPSD_OK;
+    SSPSD_CUDA(cudaMemcpyAsync(dst, src_dev, n * sizeof(float),
+                               mem == SSPSD_MEM_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, s));
+    if (mem != SSPSD_MEM_DEVICE) SSPSD_CUDA(cudaStreamSynchronize(s));
+    return SSPSD_OK;
+}
+
+int Cascade::stage_spectrum(float* out, size_t* len, int mem)
+{
+    if (!len) return SSPSD_EINVAL;
+    const size_t need = n_ / 2 + 1;
+    if (*len < need || !out) {
+        *len = need;
+        set_error("output capacity too small");
+        return SSPSD_ESHORT;
+    }
+    *len = need;
+    int rc = flush();
+    if (rc) return rc;
+    DeviceGuard g(cfg_.device);
+    if (!g.ok) return SSPSD_ECUDA;
+    return copy_out(out, d_acc_, need, mem, stream_);
+}
+
+int Cascade::stage_buf(float* out, size_t* len, int mem)
+{
+    if (!len) return SSPSD_EINVAL;
+    int rc = flush();
+    if (rc) return rc;
+    size_t pending = 0;
+    if (!stages_.empty()) {
+        const StageState& st = stages_[0];
+        pending = (size_t)(st.craw ? st.L - st.craw * (uint64_t)hop_ : st.L);
+    }
+    if (*len < pending || (pending && !out)) {
+        *len = pending;
+        set_error("output capacity too small");
+        return SSPSD_ESHORT;
+    }
+    *len = pending;
+    if (!pending) return SSPSD_OK;
+    DeviceGuard g(cfg_.device);
+    if (!g.ok) return SSPSD_ECUDA;
+    const StageState& st = stages_[0];
+    return copy_out(out, st.carry[st.cur] + ((long long)(st.L - pending) - st.carry_start), pending, mem, stream_);
+}
+
+int Cascade::take_sink(float* y, size_t* y_len, int mem)
+{
+    if (!y_len) return SSPSD_EINVAL;
+    if (*y_len < sink_len_ || (sink_len_ && !y)) {
+        *y_len = sink_len_;
+        set_error("output capacity too small");
+        return SSPSD_ESHORT;
+    }
+    *y_len = sink_len_;
+    DeviceGuard g(cfg_.device);
+    if (!g.ok) return SSPSD_ECUDA;
+    return copy_out(y, d_sink_, sink_len_, mem, stream_);
+}
+
+}  // namespace sspsd

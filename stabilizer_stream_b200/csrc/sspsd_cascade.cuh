@@ -1,0 +1,135 @@
+// sspsd_cascade.cuh -- host-side state machine of the device cascade (internal C++).
+//
+// Mirrors the streaming semantics of the reference's Psd<N>::process / PsdCascade<N>::process
+// (src/psd.rs:196-269, 445-468) in closed form: after L samples a stage has
+// completed  craw = L < N ? 0 : 1 + (L-N)/hop  segments, has decimated its first
+// D = craw ? N + (craw-1)*hop : 0  samples, and has handed  max(D/8 - R, 0)  samples to the next
+// stage.  All integer bookkeeping lives on the host; the device only sees batches.
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstdint>
+#include <string>
+#include <vector>
+
+#include "../../include/sspsd.h"
+#include "sspsd_device.cuh"
+
+namespace sspsd {
+
+void set_error(const std::string& msg);
+const char* last_error();
+bool cuda_ok(cudaError_t e, const char* what);
+#define SSPSD_CUDA(call)                     \
+    do {                                     \
+        if (!::sspsd::cuda_ok((call), #call)) return SSPSD_ECUDA; \
+    } while (0)
+
+struct WindowInfo {
+    float power, nenbw;
+    uint32_t overlap;
+};
+
+struct StageState {
+    uint64_t L = 0;       // samples received so far
+    uint64_t craw = 0;    // segments completed so far
+    uint32_t count = 0;   // effective averaging count (Psd::count, psd.rs:128)
+    uint32_t avg = 0xffffffffu;
+    uint64_t emitted = 0; // samples handed to the next stage
+    // device stream storage: carry[cur] holds [carry_start, split) with split = roundup4(L)
+    float* carry[2] = {nullptr, nullptr};
+    int cur = 0;
+    long long carry_start = 0;
+    float* fresh = nullptr; // written by the previous stage's decimator (stages >= 1)
+    size_t fresh_cap = 0;
+};
+
+class Cascade {
+public:
+    Cascade() = default;
+    ~Cascade();
+    int init(const sspsd_config& cfg, uint32_t max_stages);
+    int clone_from(Cascade& o);
+    int reset();
+
+    int process(const float* x, size_t n, int mem);
+    int set_avg(sspsd_avg_opts a);
+    int set_stage_avg(uint32_t avg);  // Psd::set_avg on stage 0 (single-stage API)
+    int set_detrend(int d);
+    int flush();
+    int sync();
+    int psd(const sspsd_merge_opts& o, float* p, size_t* p_len, sspsd_break* b, size_t* b_len);
+    int partials(sspsd_partials* out);
+    int set_counts(const uint64_t* craw, uint32_t n);
+
+    // single-stage helpers (PsdStage trait)
+    int stage_spectrum(float* out, size_t* len, int mem);
+    int stage_buf(float* out, size_t* len, int mem);
+    int take_sink(float* y, size_t* y_len, int mem);  // decimated output of the last process()
+    float stage_gain() const;
+    uint32_t stage_count() const { return stages_.empty() ? 0 : stages_[0].count; }
+
+    uint32_t n_stages() const { return (uint32_t)stages_.size(); }
+    uint32_t n_fft() const { return n_; }
+    float rbw() const { return 8.0f / ((float)n_ * 0.4f); }  // psd.rs:427-429
+    cudaStream_t stream() const { return stream_; }
+    int device() const { return cfg_.device; }
+    // device-side entry used by the fused decode path: x is device memory valid in stream order
+    int process_device(const float* x, size_t n);
+
+private:
+    int add_stage();
+    int run_stage(size_t i, const float* fresh, long long split, uint64_t n_new);
+    int launch_psd(size_t i, const StreamSrc& src, uint64_t k0, uint64_t nseg, int jb, float g_first, float g_s);
+    int launch_decim(size_t i, const StreamSrc& src, uint64_t m0, uint64_t m1, float* out_fresh,
+                     long long out_split, float* out_carry, long long out_carry_start);
+    int ensure_fresh(StageState& st, size_t need);
+    int ensure_in_buffers(size_t need);
+    int process_host(const float* x, size_t n);
+    int flush_staged();
+    int feed_device_chunk(const float* x, size_t n);
+    int feed_host_chunk(const float* xh, size_t n);
+    static uint64_t host_chunk() { return 1ull << 23; }  // samples per pipelined H2D copy
+    float gain_of(uint32_t count) const;
+    uint32_t stage_avg(size_t i) const;
+    uint64_t decimated(const StageState& st) const { return st.craw ? n_ + (st.craw - 1) * (uint64_t)hop_ : 0; }
+
+    sspsd_config cfg_{};
+    uint32_t n_ = 0, log2n_ = 0, hop_ = 0, max_stages_ = SSPSD_MAX_STAGES;
+    WindowInfo win_{};
+    int detrend_ = 0;
+    sspsd_avg_opts avg_{0xffffffffu, 0xffffffffu};
+    int hb_ = 0;       // history kept in the carry: max(overlap, decimator halo), multiple of 8
+    int drain_ = 0;    // hbf_dec_response_length(3)
+    int num_sms_ = 148;
+    int tmax_ = 1, nt_ = 256;  // largest tile (segments per CTA) and CTA size of the stage kernel
+    bool single_stage_avg_set_ = false;
+    uint32_t single_stage_avg_ = 0xffffffffu;
+    cudaStream_t stream_ = nullptr;
+    bool own_stream_ = false;
+    cudaStream_t copy_stream_ = nullptr;
+    cudaEvent_t ev_copied_[2] = {nullptr, nullptr}, ev_free_[2] = {nullptr, nullptr};
+    cudaEvent_t ev_stage_[2] = {nullptr, nullptr};
+    int last_copy_ = -1;
+    std::vector<StageState> stages_;
+    // device tables + accumulators
+    float* d_win_ = nullptr;
+    float2* d_twM_ = nullptr;
+    float2* d_twN_ = nullptr;
+    float* d_acc_ = nullptr;  // [SSPSD_MAX_STAGES][acc_stride_]
+    uint32_t acc_stride_ = 0;
+    // host-input staging
+    float* h_stage_[2] = {nullptr, nullptr};  // pinned, cfg_.host_stage floats each
+    int stage_buf_ = 0;
+    bool stage_pending_[2] = {false, false};
+    size_t staged_ = 0;
+    float* d_in_[2] = {nullptr, nullptr};
+    size_t d_in_cap_ = 0;
+    int in_buf_ = 0;
+    float* h_acc_ = nullptr;  // pinned readback buffer
+    // sink of the single-stage API
+    float* d_sink_ = nullptr;
+    size_t sink_cap_ = 0, sink_len_ = 0;
+};
+
+}  // namespace sspsd

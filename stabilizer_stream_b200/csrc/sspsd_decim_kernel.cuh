@@ -1,0 +1,166 @@
+// sspsd_decim_kernel.cuh -- K3: decimate-by-8 half-band cascade between PSD stages.
+//
+// Replaces `HBF_DEC_CASCADE.inner.1.inner.1.block(&mut self.hbf, xb, y)` (reference
+// src/psd.rs:246-253, idsp::hbf::HbfDec8) and the once-per-stage drain of the first
+// hbf_dec_response_length(3) outputs (psd.rs:149, 254-260).  The three half-band FIRs are finite
+// impulse responses, so the persistent filter state of the reference is exactly "the last H-1
+// input samples": the host keeps them in the stage's carry buffer (StreamSrc) and every CTA
+// recomputes its own warm-up from that halo (overlap-save), which makes CTAs independent.
+//
+// Per CTA: OB final outputs.  The x tile is de-interleaved into even/odd planes in shared memory
+// (a half-band FIR only touches the odd phase plus one even centre tap), each thread computes 4
+// consecutive outputs from a sliding register window, planes are padded 1 float per 32 so the
+// lane stride of 4 is bank-conflict free.
+#pragma once
+#include "sspsd_device.cuh"
+#include "sspsd_hbf_taps.h"
+
+namespace sspsd {
+
+__constant__ float c_hbf_taps[SSPSD_HBF_NPRESET][3][SSPSD_HBF_MAXTAPS];
+
+constexpr int DEC_OB = 512;  // outputs per CTA
+constexpr int DEC_NT = 256;
+
+constexpr int roundup(int v, int m) { return (v + m - 1) / m * m; }
+
+// Tap counts: MA = highest-rate stage (tap set 2), MB = set 1, MC = lowest-rate stage (set 0)
+template <int MA, int MB, int MC>
+struct DecGeom {
+    static constexpr int NB = roundup(2 * DEC_OB + 4 * MC - 2, 4);  // stage-B outputs computed per CTA
+    static constexpr int NA = roundup(2 * NB + 4 * MB - 2, 4);      // stage-A outputs
+    static constexpr int NX = roundup(2 * NA + 4 * MA - 2, 8);      // input samples loaded
+    static constexpr int HALO = NX - 8 * DEC_OB;                    // history needed before the block
+    static constexpr int PX = NX / 2 + NX / 64 + 4;                 // padded plane sizes
+    static constexpr int PA = NA / 2 + NA / 64 + 4;
+    static constexpr int PB = NB / 2 + NB / 64 + 4;
+    static constexpr int SMEM_FLOATS = 2 * (PX + PA + PB);
+};
+
+__device__ __forceinline__ int pad32(int i) { return i + (i >> 5); }
+
+// One half-band stage over de-interleaved, padded planes.
+//   ine/ino : input planes; plane index r <-> input sample in_base + 2r (+1 for the odd plane)
+//   outputs j = out_base + 4w + q (q < 4), for work items w < n_out/4, where
+//   y[j] = 0.5*(e[r-M+1] + sum_i t[i]*(o[r-2M+1+i] + o[r-i])),  r = j - in_base/2
+// rel0 = out_base - in_base/2 (relative index of the first output).
+// If FINAL, outputs go to `gout` (global, scalar) through the (m0, m1, drain) window; otherwise to
+// the padded planes oute/outo with plane index (j - out_base)/2.
+struct DecimParams {
+    StreamSrc src;
+    long long m0, m1;  // outputs m in [m0, m1) are produced by this launch (m = chunk index of 8 inputs)
+    long long drain;   // outputs m < drain are discarded (psd.rs:254-260)
+    // output m is sample g = m - drain of the next stage's stream: it goes to out_fresh[g - out_split]
+    // for g >= out_split, else to the tail of the next stage's carry, out_carry[g - out_carry_start]
+    float* out_fresh;
+    long long out_split;
+    float* out_carry;
+    long long out_carry_start;
+    int preset;
+};
+
+template <int M, bool FINAL>
+__device__ __forceinline__ void hbf_stage(const float* __restrict__ ine, const float* __restrict__ ino, int rel0,
+                                          int n_out, const float* __restrict__ taps, float* __restrict__ oute,
+                                          float* __restrict__ outo, const DecimParams& p, long long out_base,
+                                          long long m0, long long m1)
+{
+    for (int w = threadIdx.x; w < n_out / 4; w += DEC_NT) {
+        const int r0 = rel0 + 4 * w;
+        float win[2 * M + 3];
+#pragma unroll
+        for (int i = 0; i < 2 * M + 3; ++i)
+            win[i] = ino[pad32(r0 - 2 * M + 1 + i)];
+        float y[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            float acc = 0.f;
+#pragma unroll
+            for (int i = 0; i < M; ++i)
+                acc = fmaf(win[q + i] + win[q + 2 * M - 1 - i], taps[i], acc);
+            y[q] = 0.5f * (ine[pad32(r0 + q - M + 1)] + acc);
+        }
+        if constexpr (FINAL) {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                long long m = out_base + 4 * w + q;
+                if (m >= m0 && m < m1) {
+                    long long g = m - p.drain;
+                    if (g >= p.out_split)
+                        p.out_fresh[g - p.out_split] = y[q];
+                    else
+                        p.out_carry[g - p.out_carry_start] = y[q];
+                }
+            }
+        } else {
+            // out_base is even and 4w is a multiple of 4: q = 0,2 -> even plane, q = 1,3 -> odd plane
+            const int pe = 2 * w;
+            oute[pad32(pe)] = y[0];
+            outo[pad32(pe)] = y[1];
+            oute[pad32(pe + 1)] = y[2];
+            outo[pad32(pe + 1)] = y[3];
+        }
+    }
+}
+
+template <int MA, int MB, int MC>
+__global__ void __launch_bounds__(DEC_NT) decim8_kernel(const DecimParams p)
+{
+    using GE = DecGeom<MA, MB, MC>;
+    extern __shared__ __align__(16) float smem[];
+    float* xe = smem;
+    float* xo = xe + GE::PX;
+    float* ae = xo + GE::PX;
+    float* ao = ae + GE::PA;
+    float* be = ao + GE::PA;
+    float* bo = be + GE::PB;
+
+    // blocks are counted down from the top of the range so that every block is full size and only
+    // the lowest one is clipped (by the m >= m0 store guard)
+    const long long mhi = p.m1 - (long long)blockIdx.x * DEC_OB;
+    const long long x_base = 8 * mhi - GE::NX;          // multiple of 8
+    const long long a_base = 4 * mhi - GE::NA;          // first stage-A output index (even)
+    const long long b_base = 2 * mhi - GE::NB;          // first stage-B output index (even)
+    const long long c_base = mhi - DEC_OB;
+
+    // ---- load + de-interleave ----
+    for (int v = threadIdx.x; v < GE::NX / 4; v += DEC_NT) {
+        float4 f = ld_stream4(p.src, x_base + 4ll * v);
+        int r = 2 * v;
+        xe[pad32(r)] = f.x;
+        xo[pad32(r)] = f.y;
+        xe[pad32(r + 1)] = f.z;
+        xo[pad32(r + 1)] = f.w;
+    }
+    __syncthreads();
+    const float* tA = c_hbf_taps[p.preset][2];
+    const float* tB = c_hbf_taps[p.preset][1];
+    const float* tC = c_hbf_taps[p.preset][0];
+    // relative index of the first output of each stage: out_base - in_base/2
+    hbf_stage<MA, false>(xe, xo, (int)(a_base - x_base / 2), GE::NA, tA, ae, ao, p, a_base, 0, 0);
+    __syncthreads();
+    hbf_stage<MB, false>(ae, ao, (int)(b_base - a_base / 2), GE::NB, tB, be, bo, p, b_base, 0, 0);
+    __syncthreads();
+    const long long lo = p.m0 > p.drain ? p.m0 : p.drain;
+    hbf_stage<MC, true>(be, bo, (int)(c_base - b_base / 2), DEC_OB, tC, nullptr, nullptr, p, c_base, lo, mhi);
+}
+
+// ---------------------------------------------------------------------------------------------
+// small helpers
+// ---------------------------------------------------------------------------------------------
+// dst[i] = stream[g0 + i], i < n  (builds the next batch's carry buffer)
+__global__ void carry_copy_kernel(StreamSrc src, long long g0, int n, float* __restrict__ dst)
+{
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+        dst[i] = ld_stream1(src, g0 + i);
+}
+
+// acc[i] *= s (EWMA rescale of the running average before a batch, psd.rs:218-232)
+__global__ void scale_kernel(float* __restrict__ acc, int n, float s)
+{
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n)
+        acc[i] *= s;
+}
+
+}  // namespace sspsd

@@ -1,0 +1,380 @@
+"""Host-side mirror of the reference's PSD API (quartiq/stabilizer-stream src/psd.rs, src/de,
+src/loss.rs, src/var.rs) on top of the C ABI of libsspsd.so.  Same names, same argument meaning,
+same error behaviour; all arithmetic happens in the CUDA library (there is no CPU path here).
+
+    PsdCascade(n).process(x); p, breaks = cascade.psd(MergeOpts()); f = Break.frequencies(breaks)
+
+`x` may be a numpy float32 array (host memory) or a CUDA torch tensor (device memory, consumed in
+stream order on the cascade's stream).
+"""
+import ctypes as C
+import enum
+from dataclasses import dataclass
+
+import numpy as np
+
+from . import _lib as L
+
+DEPTH = 3  # src/psd.rs:117
+HBF_PASSBAND = 0.4  # idsp::hbf::HBF_PASSBAND, src/psd.rs:601
+
+
+class Detrend(enum.IntEnum):
+    """enum Detrend, src/psd.rs:59-72"""
+    NONE = 0
+    MIDPOINT = 1
+    SPAN = 2
+    MEAN = 3
+    LINEAR = 4
+
+
+class Window(enum.IntEnum):
+    """Window::rectangular / Window::hann, src/psd.rs:24-55"""
+    RECTANGULAR = 0
+    HANN = 1
+
+
+class Hbf(enum.IntEnum):
+    TAPS_98 = 0
+    TAPS_140 = 1
+
+
+@dataclass
+class AvgOpts:
+    """src/psd.rs:360-376"""
+    limit: int = 0xFFFFFFFF
+    count: int = 0xFFFFFFFF
+
+
+@dataclass
+class MergeOpts:
+    """src/psd.rs:339-358"""
+    keep_overlap: bool = False
+    min_count: int = 1
+    keep_transition_band: bool = False
+
+
+@dataclass
+class Break:
+    """src/psd.rs:290-337"""
+    start: int
+    include: bool
+    count: int
+    avg: int
+    bins: range
+    fft_size: int
+    decimation: int
+    pending: int
+    processed: int
+
+    def effective_fft_size(self):
+        return self.fft_size * self.decimation
+
+    def rbw(self):
+        return np.float32(1.0) / np.float32(self.effective_fft_size())
+
+    @staticmethod
+    def frequencies(breaks):
+        """Break::frequencies, src/psd.rs:315-327 (computed by the library)."""
+        arr = (L.BreakC * max(len(breaks), 1))()
+        for i, b in enumerate(breaks):
+            arr[i] = b._c()
+        n = C.c_size_t(0)
+        st = L.lib().sspsd_break_frequencies(arr, len(breaks), None, C.byref(n))
+        if st not in (L.OK, L.ESHORT):
+            L.check(st)
+        f = np.zeros(max(n.value, 1), np.float32)
+        n = C.c_size_t(f.size)
+        L.check(L.lib().sspsd_break_frequencies(arr, len(breaks), f.ctypes.data, C.byref(n)))
+        return f[:n.value]
+
+    def _c(self):
+        return L.BreakC(self.start, int(self.include), self.count, self.avg, 0, self.bins.start, self.bins.stop,
+                        self.fft_size, self.decimation, self.pending, self.processed)
+
+    @staticmethod
+    def _from_c(b):
+        return Break(b.start, bool(b.include), b.count, b.avg, range(b.bins_start, b.bins_end), b.fft_size,
+                     b.decimation, b.pending, b.processed)
+
+
+def _as_buffer(x):
+    """-> (pointer, n, mem, keepalive)"""
+    if isinstance(x, np.ndarray) or not hasattr(x, "data_ptr"):
+        a = np.ascontiguousarray(x, dtype=np.float32)
+        return a.ctypes.data, a.size, L.MEM_HOST, a
+    import torch
+    if x.dtype != torch.float32:
+        raise TypeError("expected float32 samples")
+    t = x.contiguous()
+    mem = L.MEM_DEVICE if t.is_cuda else L.MEM_HOST
+    return t.data_ptr(), t.numel(), mem, t
+
+
+def _config(n, window, hbf, device, stream, max_batch, host_stage):
+    cfg = L.Config()
+    L.check(L.lib().sspsd_config_default(n, C.byref(cfg)))
+    cfg.window = int(window)
+    cfg.hbf = int(hbf)
+    cfg.device = int(device)
+    cfg.stream = stream
+    cfg.max_batch = max_batch
+    cfg.host_stage = host_stage
+    return cfg
+
+
+class PsdCascade:
+    """PsdCascade<N>, src/psd.rs:399-544.  `PsdCascade(n)` is `PsdCascade::<N>::default()`."""
+
+    def __init__(self, n=512, device=0, hbf=Hbf.TAPS_140, stream=None, max_batch=0, host_stage=0, _handle=None):
+        self.n = n
+        if _handle is not None:
+            self._h = _handle
+            return
+        cfg = _config(n, Window.HANN, hbf, device, stream, max_batch, host_stage)
+        h = C.c_void_p()
+        L.check(L.lib().sspsd_cascade_create(C.byref(cfg), C.byref(h)))
+        self._h = h
+
+    def clone(self):
+        h = C.c_void_p()
+        L.check(L.lib().sspsd_cascade_clone(self._h, C.byref(h)))
+        return PsdCascade(self.n, _handle=h)
+
+    def reset(self):
+        L.check(L.lib().sspsd_cascade_reset(self._h))
+
+    def rbw(self):
+        r = C.c_float()
+        L.check(L.lib().sspsd_cascade_rbw(self._h, C.byref(r)))
+        return r.value
+
+    def set_avg(self, avg: AvgOpts):
+        L.check(L.lib().sspsd_cascade_set_avg(self._h, L.AvgOptsC(avg.limit, avg.count)))
+
+    def set_detrend(self, d: Detrend):
+        L.check(L.lib().sspsd_cascade_set_detrend(self._h, int(d)))
+
+    def process(self, x):
+        ptr, n, mem, keep = _as_buffer(x)
+        L.check(L.lib().sspsd_cascade_process_f32(self._h, ptr, n, mem))
+        del keep
+
+    def process_raw(self, ptr, n, mem):
+        L.check(L.lib().sspsd_cascade_process_f32(self._h, ptr, n, mem))
+
+    def flush(self):
+        L.check(L.lib().sspsd_cascade_flush(self._h))
+
+    def sync(self):
+        L.check(L.lib().sspsd_cascade_sync(self._h))
+
+    def num_stages(self):
+        n = C.c_uint32()
+        L.check(L.lib().sspsd_cascade_num_stages(self._h, C.byref(n)))
+        return n.value
+
+    def psd(self, opts: MergeOpts = None):
+        opts = opts or MergeOpts()
+        o = L.MergeOptsC(int(opts.keep_overlap), opts.min_count, int(opts.keep_transition_band))
+        p = np.zeros(L.MAX_STAGES * (self.n // 2 + 1), np.float32)
+        b = (L.BreakC * L.MAX_STAGES)()
+        pl, bl = C.c_size_t(p.size), C.c_size_t(L.MAX_STAGES)
+        L.check(L.lib().sspsd_cascade_psd(self._h, C.byref(o), p.ctypes.data, C.byref(pl), b, C.byref(bl)))
+        return p[:pl.value].copy(), [Break._from_c(b[i]) for i in range(bl.value)]
+
+    def partials(self):
+        out = L.PartialsC()
+        L.check(L.lib().sspsd_cascade_partials(self._h, C.byref(out)))
+        return out
+
+    def set_counts(self, counts):
+        arr = (C.c_uint64 * len(counts))(*counts)
+        L.check(L.lib().sspsd_cascade_set_counts(self._h, arr, len(counts)))
+
+    def __del__(self):
+        h = getattr(self, "_h", None)
+        if h:
+            L.lib().sspsd_cascade_destroy(h)
+            self._h = None
+
+
+class Psd:
+    """Psd<N> + trait PsdStage, src/psd.rs:119-288 (one stage, decimated output exposed)."""
+
+    def __init__(self, n=512, window=Window.HANN, device=0, hbf=Hbf.TAPS_140, stream=None):
+        self.n = n
+        cfg = _config(n, window, hbf, device, stream, 0, 0)
+        h = C.c_void_p()
+        L.check(L.lib().sspsd_stage_create(C.byref(cfg), C.byref(h)))
+        self._h = h
+
+    def set_avg(self, avg: int):
+        L.check(L.lib().sspsd_stage_set_avg(self._h, avg))
+
+    def set_detrend(self, d: Detrend):
+        L.check(L.lib().sspsd_stage_set_detrend(self._h, int(d)))
+
+    def process(self, x):
+        """PsdStage::process(x, y) -> y[..n] (returned as a numpy array)."""
+        ptr, n, mem, keep = _as_buffer(x)
+        y = np.zeros(n // 8 + self.n // 8 + 16, np.float32)
+        yl = C.c_size_t(y.size)
+        L.check(L.lib().sspsd_stage_process_f32(self._h, ptr, n, mem, y.ctypes.data, C.byref(yl), L.MEM_HOST))
+        del keep
+        return y[:yl.value]
+
+    def spectrum(self):
+        out = np.zeros(self.n // 2 + 1, np.float32)
+        ln = C.c_size_t(out.size)
+        L.check(L.lib().sspsd_stage_spectrum(self._h, out.ctypes.data, C.byref(ln), L.MEM_HOST))
+        return out
+
+    def count(self):
+        c = C.c_uint32()
+        L.check(L.lib().sspsd_stage_count(self._h, C.byref(c)))
+        return c.value
+
+    def gain(self):
+        g = C.c_float()
+        L.check(L.lib().sspsd_stage_gain(self._h, C.byref(g)))
+        return g.value
+
+    def buf(self):
+        out = np.zeros(self.n, np.float32)
+        ln = C.c_size_t(out.size)
+        L.check(L.lib().sspsd_stage_buf(self._h, out.ctypes.data, C.byref(ln), L.MEM_HOST))
+        return out[:ln.value]
+
+    def __del__(self):
+        h = getattr(self, "_h", None)
+        if h:
+            L.lib().sspsd_stage_destroy(h)
+            self._h = None
+
+
+class Format(enum.IntEnum):
+    """enum Format, src/de/mod.rs:9-17"""
+    AdcDac = 1
+    Fls = 2
+    ThermostatEem = 3
+    Mpll = 4
+
+
+TRACE_NAMES = {  # src/de/data.rs:37,48,59,70 / 100,111,124,131 / 155 / 181,190,199
+    Format.AdcDac: ("ADC0", "ADC1", "DAC0", "DAC1"),
+    Format.Fls: ("AR", "AP", "BI", "BQ"),
+    Format.ThermostatEem: ("T00", "T20", "I0", "I1"),
+    Format.Mpll: ("phase (rad)", "frequency (kHz)", "amplitude (V/G10)"),
+}
+
+
+class DecodeError(Exception):
+    """de::Error (src/de/mod.rs:19-27) plus the reference's panics, by status code."""
+
+    def __init__(self, status, frames_ok):
+        super().__init__("%s at frame %d" % (L.STATUS_NAMES.get(status, status), frames_ok))
+        self.status = status
+        self.frames_ok = frames_ok
+
+
+class Loss:
+    """struct Loss, src/loss.rs:4-38"""
+
+    def __init__(self):
+        self.c = L.LossC()
+
+    received = property(lambda self: self.c.received)
+    dropped = property(lambda self: self.c.dropped)
+    seq = property(lambda self: self.c.seq if self.c.has_seq else None)
+
+    def update(self, seq, batches):
+        L.lib().sspsd_loss_update(C.byref(self.c), seq, batches)
+
+    def ratio(self):
+        return L.lib().sspsd_loss_ratio(C.byref(self.c))
+
+
+class FrameDecoder:
+    """Batched Frame::from_bytes + Loss::update + Payload::traces (src/de/frame.rs:49-60,
+    src/loss.rs:11-26, src/de/data.rs)."""
+
+    def __init__(self, device=0, stream=None):
+        h = C.c_void_p()
+        L.check(L.lib().sspsd_decoder_create(device, stream, C.byref(h)))
+        self._h = h
+
+    @staticmethod
+    def _frames(frames, frame_len, frame_stride):
+        if hasattr(frames, "data_ptr"):
+            t = frames.contiguous()
+            return t.data_ptr(), t.numel(), (L.MEM_DEVICE if t.is_cuda else L.MEM_HOST), t
+        a = np.frombuffer(frames, dtype=np.uint8) if not isinstance(frames, np.ndarray) else np.ascontiguousarray(frames, np.uint8)
+        return a.ctypes.data, a.size, L.MEM_HOST, a
+
+    def decode(self, frames, frame_len, loss: Loss = None, frame_stride=None, n_frames=None):
+        """-> (format, [(name, np.ndarray)], frames_ok).  Raises DecodeError on a malformed frame after
+        having accounted (in `loss`) for the frames before it."""
+        frame_stride = frame_stride or frame_len
+        ptr, nbytes, mem, keep = self._frames(frames, frame_len, frame_stride)
+        if n_frames is None:
+            n_frames = 0 if nbytes < frame_len else 1 + (nbytes - frame_len) // frame_stride
+        payload = max(frame_len - 8, 0)
+        cap = max(n_frames * max(payload // 64 * 8, payload // 24), 1)
+        tr = [np.zeros(cap, np.float32) for _ in range(L.MAX_TRACES)]
+        ptrs = (C.c_void_p * L.MAX_TRACES)(*[t.ctypes.data for t in tr])
+        info = L.DecodeInfoC()
+        st = L.lib().sspsd_decode_frames(self._h, ptr, n_frames, frame_len, frame_stride, mem,
+                                         C.byref(loss.c) if loss is not None else None, ptrs, cap, L.MEM_HOST,
+                                         C.byref(info))
+        del keep
+        traces = []
+        if info.frames_ok:
+            names = TRACE_NAMES[Format(info.format)]
+            traces = [(names[t], tr[t][:info.samples_per_trace]) for t in range(info.n_traces)]
+        if st in (L.EHEADER, L.EFORMAT, L.ESIZE, L.EBATCHES, L.ESHORT) and info.frames_ok < n_frames:
+            err = DecodeError(st, info.frames_ok)
+            err.traces = traces
+            err.format = info.format
+            raise err
+        L.check(st)
+        return (Format(info.format) if info.frames_ok else None), traces, info.frames_ok
+
+    def process_frames(self, cascades, frames, frame_len, loss: Loss = None, frame_stride=None, n_frames=None):
+        """Fused decode -> one PsdCascade per trace (src/bin/psd.rs:174-182)."""
+        frame_stride = frame_stride or frame_len
+        ptr, nbytes, mem, keep = self._frames(frames, frame_len, frame_stride)
+        if n_frames is None:
+            n_frames = 0 if nbytes < frame_len else 1 + (nbytes - frame_len) // frame_stride
+        hs = (C.c_void_p * len(cascades))(*[(c._h if c is not None else None) for c in cascades])
+        info = L.DecodeInfoC()
+        st = L.lib().sspsd_cascade_process_frames(self._h, hs, len(cascades), ptr, n_frames, frame_len,
+                                                  frame_stride, mem, C.byref(loss.c) if loss is not None else None,
+                                                  C.byref(info))
+        del keep
+        if st in (L.EHEADER, L.EFORMAT, L.ESIZE, L.EBATCHES, L.ESHORT) and info.frames_ok < n_frames:
+            raise DecodeError(st, info.frames_ok)
+        L.check(st)
+        return info
+
+    def __del__(self):
+        h = getattr(self, "_h", None)
+        if h:
+            L.lib().sspsd_decoder_destroy(h)
+            self._h = None
+
+
+@dataclass
+class Var:
+    """struct Var / VarBuilder defaults, src/var.rs:4-19"""
+    x_exp: int = -2
+    sinx_exp: int = 4
+    clip: float = 3.4028234663852886e38
+    dc_cut: int = 2
+
+    def eval(self, phase_psd, frequencies, tau):
+        """Var::eval, src/var.rs:26-45"""
+        p = np.ascontiguousarray(phase_psd, np.float32)
+        f = np.ascontiguousarray(frequencies, np.float32)
+        v = L.VarC(self.x_exp, self.sinx_exp, self.clip, 0, self.dc_cut)
+        return L.lib().sspsd_var_eval(C.byref(v), p.ctypes.data, f.ctypes.data, min(p.size, f.size), tau)

@@ -1,0 +1,209 @@
+"""Parity of the CUDA cascade (through the C ABI) against the CPU oracle.  Needs a B200."""
+import numpy as np
+import pytest
+
+from conftest import uniform_noise
+
+pytestmark = pytest.mark.gpu
+
+RTOL = 1e-4   # north_star: "within a stated relative tolerance per PSD bin (1e-4 in f32)"
+AFLOOR = 1e-5  # absolute floor, as a fraction of the stage's median bin power: only matters for
+#                bins that are accidentally ~0 in a stage with a single segment
+
+
+@pytest.fixture(scope="module")
+def sp():
+    import torch
+    assert torch.cuda.is_available()
+    import stabilizer_stream_b200 as m
+    return m
+
+
+def assert_bins_close(got, want, what=""):
+    got = np.asarray(got, np.float64)
+    want = np.asarray(want, np.float64)
+    assert got.shape == want.shape, what
+    if want.size == 0:
+        return
+    floor = AFLOOR * np.median(np.abs(want))
+    err = np.abs(got - want) - floor
+    rel = np.max(err / np.maximum(np.abs(want), 1e-300))
+    assert rel <= RTOL, "%s: max rel err %.3g" % (what, rel)
+
+
+def breaks_tuple(b):
+    return (b.start, b.include, b.count, b.avg, b.bins.start, b.bins.stop, b.fft_size, b.decimation, b.pending,
+            b.processed)
+
+
+@pytest.mark.parametrize("n", [64, 128, 256, 512, 1024, 2048, 4096, 8192])
+@pytest.mark.parametrize("window", [0, 1])
+def test_single_stage_all_sizes(sp, oracle, n, window):
+    x = uniform_noise(40 * n + 13, n + window) + np.float32(0.1)
+    g = sp.Psd(n, sp.Window(window))
+    o = oracle.Stage(n, window)
+    yg = g.process(x)
+    yo = o.process(x)
+    assert g.count() == o.count() and g.gain() == o.gain()
+    assert_bins_close(g.spectrum(), o.spectrum(), "stage n=%d" % n)
+    assert yg.shape == yo.shape
+    np.testing.assert_allclose(yg, yo, atol=3e-6)
+    np.testing.assert_array_equal(g.buf(), o.buf())
+
+
+@pytest.mark.parametrize("n", [512, 4096])
+@pytest.mark.parametrize("det", [0, 1, 2, 3])
+def test_detrend_modes(sp, oracle, n, det):
+    x = uniform_noise(64 * n, 17 * det + n) + np.float32(0.5)
+    g = sp.Psd(n)
+    g.set_detrend(sp.Detrend(det))
+    o = oracle.Stage(n)
+    o.set_detrend(det)
+    g.process(x)
+    o.process(x)
+    assert_bins_close(g.spectrum(), o.spectrum(), "detrend %d" % det)
+
+
+def test_detrend_linear_is_unimplemented(sp):
+    # reference: Detrend::Linear => unimplemented!() (src/psd.rs:110)
+    from stabilizer_stream_b200 import _lib
+    g = sp.PsdCascade(512)
+    with pytest.raises(_lib.SspsdError) as e:
+        g.set_detrend(sp.Detrend.LINEAR)
+    assert e.value.status == _lib.EUNIMPLEMENTED
+
+
+@pytest.mark.parametrize("n", [512, 4096])
+def test_known_answer_hann_ones(sp, n):
+    # reference src/psd.rs:562-597 generalised: x = ones -> [4N/3, N/3, 0, ...]
+    g = sp.Psd(n)
+    g.process(np.ones(n, np.float32))
+    p = g.spectrum() / g.gain()
+    assert g.count() == 1
+    assert abs(p[0] - 4 * n / 3) < 1e-5 * n and abs(p[1] - n / 3) < 1e-5 * n
+    assert np.all(np.abs(p[2:]) < 1e-6 * n)
+
+
+def test_reference_statistical_test(sp):
+    """The reference's own live test (src/psd.rs:599-644), seeded, on the device path."""
+    x = uniform_noise(1 << 16, 0x7654321)
+    n = 512
+    s = sp.Psd(n)
+    y = s.process(x)
+    assert y.size == (x.size >> 3) - 115
+    p = s.spectrum() / s.gain()
+    assert s.count() == 255
+    assert np.all(np.abs(p * 0.5 - 1.0) < 10.0 / np.sqrt(s.count()))
+    d = sp.PsdCascade(n)
+    d.process(x)
+    p, b = d.psd()
+    for bi in b:
+        seg = p[bi.start:bi.start + len(bi.bins)]
+        if bi.include and bi.count:
+            assert np.all(np.abs(seg * 0.5 - 1.0) < 10.0 / np.sqrt(bi.count))
+    f = sp.Break.frequencies(b)
+    assert f.size == p.size and f[0] == 0.0 and f[-1] == 0.5
+
+
+@pytest.mark.parametrize("n,det,hbf", [(512, 0, 1), (512, 3, 0), (4096, 1, 1), (4096, 0, 0), (64, 2, 1), (1024, 3, 1)])
+def test_cascade_matches_oracle_ragged_host_and_device(sp, oracle, n, det, hbf):
+    import torch
+    x = uniform_noise(700 * n + 77, 3 + n) + np.float32(0.25)
+    g = sp.PsdCascade(n, hbf=sp.Hbf(hbf), host_stage=1 << 14)
+    g.set_detrend(sp.Detrend(det))
+    o = oracle.Cascade(n, hbf)
+    o.set_detrend(det)
+    o.process(x)
+    rng = np.random.default_rng(1)
+    xd = torch.from_numpy(x).cuda()
+    pos = 0
+    while pos < x.size:
+        k = int(rng.integers(0, 40 * n))
+        if rng.random() < 0.5:
+            g.process(x[pos:pos + k])          # host pointer (small calls are staged)
+        else:
+            g.process(xd[pos:pos + k])         # device pointer, arbitrary alignment
+        pos += k
+    p, b = g.psd()
+    po, bo = o.psd()
+    assert [breaks_tuple(k) for k in b] == [k.as_tuple() for k in bo]
+    assert_bins_close(p, po, "cascade n=%d" % n)
+    np.testing.assert_array_equal(sp.Break.frequencies(b), oracle.break_frequencies(bo))
+    # every stage on its own, all bins, all merge options
+    pk, bk = g.psd(sp.MergeOpts(keep_overlap=True, min_count=0, keep_transition_band=True))
+    pok, bok = o.psd(True, 0, True)
+    assert [breaks_tuple(k) for k in bk] == [k.as_tuple() for k in bok]
+    for bi in bk:
+        if bi.count:
+            sl = slice(bi.start, bi.start + len(bi.bins))
+            assert_bins_close(pk[sl], pok[sl], "stage dec=%d" % bi.decimation)
+
+
+def test_cascade_ewma_and_option_changes(sp, oracle):
+    n = 512
+    x = uniform_noise(3000 * n, 9)
+    g = sp.PsdCascade(n)
+    o = oracle.Cascade(n, 1)
+    # the psd binary's defaults: limit = avg_max - 1 = 999, count = avg - 1 (src/bin/psd.rs:73-78)
+    g.set_avg(sp.AvgOpts(limit=999, count=2 ** 32 - 2))
+    o.set_avg(999, 2 ** 32 - 2)
+    third = x.size // 3
+    g.process(x[:third]); o.process(x[:third])
+    g.set_detrend(sp.Detrend.MEAN); o.set_detrend(3)
+    g.process(x[third:2 * third]); o.process(x[third:2 * third])
+    g.set_avg(sp.AvgOpts(limit=50, count=400)); o.set_avg(50, 400)   # lowering avg mid-stream
+    g.process(x[2 * third:]); o.process(x[2 * third:])
+    p, b = g.psd()
+    po, bo = o.psd()
+    assert [breaks_tuple(k) for k in b] == [k.as_tuple() for k in bo]
+    assert_bins_close(p, po, "ewma")
+
+
+def test_clone_reset_and_empty(sp, oracle):
+    n = 512
+    x = uniform_noise(100 * n, 21)
+    g = sp.PsdCascade(n)
+    assert g.psd()[0].size == 0 and g.num_stages() == 0
+    g.process(np.zeros(0, np.float32))
+    assert g.num_stages() == 0
+    g.process(x[:100])
+    p, b = g.psd()
+    assert p.size == 0 and len(b) == 1 and b[0].pending == 100 and not b[0].include
+    g.process(x[100:50 * n])
+    c = g.clone()
+    g.process(x[50 * n:])
+    c.process(x[50 * n:])
+    p1, b1 = g.psd()
+    p2, b2 = c.psd()
+    assert [breaks_tuple(k) for k in b1] == [breaks_tuple(k) for k in b2]
+    np.testing.assert_allclose(p1, p2, rtol=1e-5)
+    o = oracle.Cascade(n, 1)
+    o.process(x)
+    assert_bins_close(p2, o.psd()[0], "clone")
+    g.reset()
+    assert g.num_stages() == 0 and g.psd()[0].size == 0
+    g.process(x)
+    assert_bins_close(g.psd()[0], o.psd()[0], "after reset")
+
+
+def test_large_batch_properties(sp):
+    """BASELINE config 2 size (200e6 samples, N=4096): closed-form stage counts and flat PSD."""
+    import torch
+    n = 4096
+    total = 200_000_000
+    g = sp.PsdCascade(n)
+    gen = torch.Generator(device="cuda").manual_seed(5)
+    x = (torch.rand(total, device="cuda", generator=gen) - 0.5) * (12 ** 0.5)
+    g.process(x)
+    p, b = g.psd()
+    counts = [k.count for k in reversed(b)]
+    assert counts == [97655, 12205, 1524, 189, 22, 1, 0]   # SURVEY.md 8(a9), drain-independent
+    for k in b:
+        if k.count >= 20:
+            seg = p[k.start:k.start + len(k.bins)]
+            assert np.all(np.abs(seg * 0.5 - 1.0) < 10.0 / np.sqrt(k.count))
+    # linearity: scaling the input by 2 scales every bin by 4 (same segmentation)
+    g2 = sp.PsdCascade(n)
+    g2.process(x * 2.0)
+    p2, _ = g2.psd()
+    np.testing.assert_allclose(p2, 4.0 * p, rtol=1e-5)
