@@ -1,0 +1,288 @@
+#!/usr/bin/env python3
+"""Benchmark of the cascaded-PSD hot path (BASELINE.json metric: sustained MS/s through the full
+PSD cascade; % of HBM roofline).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+Workload (config.workload): BASELINE.json configs[1] -- default PsdCascade (N=4096 Hann, 50 % overlap,
+divide-by-8 half-band cascade per stage) over one second of a 200 MS/s synthetic raw f32 stream.
+A step = one pass of the whole cascade over 200e6 samples + the psd() readout.  With N GPUs every
+rank runs its own channel of the same shape (channels are independent cascades, reference
+src/bin/psd.rs:174-182): weak scaling, no data-path collective, one NCCL gather of the merged
+spectra at readout.
+
+`value` is measured with the input resident in HBM (800 MB per step, far larger than the 126 MB L2,
+so nothing is served from cache between steps); `e2e` is the same metric through the same C-ABI
+call with the samples in pinned HOST memory (H2D inside the timed region) and the spectra read back.
+`--impl reference` times the CPU restatement of the reference (oracle/, kind "port": the Rust
+reference cannot be built offline) on the box's host cores.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+N_FFT = 4096
+SAMPLES_PER_STEP = 200_000_000
+BYTES_PER_SAMPLE = 4.0  # algorithmic: every raw f32 sample must cross HBM once
+WORKLOAD = "PsdCascade N=4096 Hann 50% overlap, div-8 half-band per stage, 200e6-sample f32 stream per channel"
+
+
+def peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured"
+    except Exception:
+        return 6650.0, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index = index
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        self.p = None
+
+    def start(self):
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                       "--format=csv,noheader,nounits", "-lms", "100"],
+                                      stdout=self.f, stderr=subprocess.DEVNULL)
+        except OSError:
+            self.p = None
+
+    def stop(self):
+        if self.p is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.12)
+        self.p.terminate()
+        self.p.wait()
+        self.f.flush()
+        self.f.seek(0)
+        sm, mx, reasons = [], [], set()
+        for line in self.f.read().splitlines():
+            c = [v.strip() for v in line.split(",")]
+            if len(c) < 9:
+                continue
+            try:
+                sm.append(float(c[1]))
+                mx.append(float(c[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), c[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        os.unlink(self.f.name)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def cpu_baseline(seconds_target=12.0, threads=1, n_fft=N_FFT):
+    """Time the CPU restatement (oracle) on this host: `threads` independent channels, one per thread."""
+    import numpy as np
+    from oracle import binding as orc
+    orc.lib()
+    rng = np.random.default_rng(0x7654321)
+    block = ((rng.random(1 << 22, dtype=np.float32) - np.float32(0.5)) * np.float32(12 ** 0.5)).astype(np.float32)
+    cas = [orc.Cascade(n_fft, orc.HBF_140) for _ in range(threads)]
+    for c in cas:
+        c.process(block[:1 << 20])
+    # calibrate, then run a bounded sample
+    t0 = time.perf_counter()
+    cas[0].process(block)
+    per_block = time.perf_counter() - t0
+    reps = max(1, int(seconds_target / max(per_block, 1e-3)))
+    done = [0] * threads
+
+    def work(i):
+        for _ in range(reps):
+            cas[i].process(block)  # ctypes releases the GIL for the duration of the call
+            done[i] += block.size
+
+    ths = [threading.Thread(target=work, args=(i,)) for i in range(threads)]
+    t0 = time.perf_counter()
+    for t in ths:
+        t.start()
+    for t in ths:
+        t.join()
+    dt = time.perf_counter() - t0
+    total = sum(done)
+    return {"value": total / dt / 1e6, "unit": "MS/s", "cores": threads, "kind": "port",
+            "sample": "%d channel(s) x %d samples (N=%d cascade, CPU restatement of src/psd.rs, gcc -O3 -march=native; "
+                      "the Rust reference cannot be built offline; it publishes >200 MS/s/core at N=512)"
+                      % (threads, total // threads, n_fft), "seconds": dt}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    n = max(1, args.gpus)
+    # the reference runs one cascade per trace on one receiver thread; with N channels it can use N threads
+    threads = min(n, os.cpu_count() or 1)
+    vals = []
+    for _ in range(args.warmup):
+        cpu_baseline(1.0, threads)
+    t_all = time.perf_counter()
+    for _ in range(args.steps):
+        vals.append(cpu_baseline(max(2.0, 20.0 / args.steps), threads))
+    wall = time.perf_counter() - t_all
+    v = sum(x["value"] for x in vals) / len(vals)
+    cb = dict(vals[-1])
+    cb["value"] = v
+    out = {"impl": "reference", "metric": "sustained MS/s through full PSD cascade", "value": v, "unit": "MS/s",
+           "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+           "ms_per_step": wall / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+           "dtype": "f32", "data": "synthetic", "config": {"workload": WORKLOAD, "channels": n},
+           "cpu_baseline": cb,
+           "e2e": {"value": v, "unit": "MS/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(out))
+
+
+def run_ours(args):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    from stabilizer_stream_b200 import MergeOpts, PsdCascade
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    stream = torch.cuda.current_stream(dev)
+
+    gen = torch.Generator(device=dev).manual_seed(0x7654321 + rank)
+    x = (torch.rand(SAMPLES_PER_STEP, device=dev, generator=gen) - 0.5) * (12 ** 0.5)
+    xh = torch.empty(SAMPLES_PER_STEP, dtype=torch.float32, pin_memory=True)
+    xh.copy_(x)
+    torch.cuda.synchronize(dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    def gather_readout(p):
+        """readout collective: one NCCL gather of every channel's merged spectrum to rank 0"""
+        if world == 1:
+            return
+        t = torch.zeros(16 * (N_FFT // 2 + 1), device=dev)
+        t[:p.size] = torch.from_numpy(p).to(dev, non_blocking=True)
+        out = [torch.empty_like(t) for _ in range(world)] if rank == 0 else None
+        dist.gather(t, out, dst=0)
+
+    def timed(cascade, src, steps, warmup):
+        for _ in range(warmup):
+            cascade.process(src)
+            gather_readout(cascade.psd(MergeOpts())[0])
+        cascade.profile_read()
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for _ in range(steps):
+            cascade.process(src)
+            p, b = cascade.psd(MergeOpts())
+            gather_readout(p)
+        e1.record(stream)
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item()), p, b
+
+    # ---- device-resident run (value) with per-kernel event timing and clock sampling ----
+    c = PsdCascade(N_FFT, device=local, stream=stream.cuda_stream)
+    c.profile_enable(True)
+    sampler = ClockSampler(local)
+    for _ in range(args.warmup):
+        c.process(x)
+        gather_readout(c.psd(MergeOpts())[0])
+    c.profile_read()
+    barrier()
+    sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for _ in range(args.steps):
+        c.process(x)
+        p, b = c.psd(MergeOpts())
+        gather_readout(p)
+    e1.record(stream)
+    barrier()
+    clocks = sampler.stop()
+    ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    ms = float(ms.item())
+    prof, launches = c.profile_read()
+    value = world * SAMPLES_PER_STEP * args.steps / (ms * 1e-3) / 1e6
+
+    # ---- end-to-end run: host pinned input, H2D inside the timed region, spectra read back ----
+    c2 = PsdCascade(N_FFT, device=local, stream=stream.cuda_stream)
+    e2e_steps = max(1, min(args.steps, 5))
+    ms2, p2, b2 = timed(c2, xh, e2e_steps, min(args.warmup, 2))
+    e2e_value = world * SAMPLES_PER_STEP * e2e_steps / (ms2 * 1e-3) / 1e6
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    peak, peak_kind = peaks()
+    k_ms, k_launches, k_units = prof["psd_stage0"]
+    achieved = (BYTES_PER_SAMPLE * k_units / (k_ms * 1e-3) / 1e9) if k_ms > 0 else 0.0
+    roof = {"bound": "hbm", "kernel": "psd_stage_kernel<12> (stage 0)", "achieved": achieved, "peak": peak,
+            "peak_kind": peak_kind, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+            "launches": int(k_launches), "avg_launch_ms": (k_ms / k_launches) if k_launches else None,
+            "algorithmic_bytes_per_launch": BYTES_PER_SAMPLE * k_units / max(k_launches, 1),
+            "share_of_step": k_ms / ms,
+            "other_kernels_ms": {k: v[0] for k, v in prof.items() if k != "psd_stage0"},
+            "whole_step_frac": BYTES_PER_SAMPLE * SAMPLES_PER_STEP * args.steps / (ms * 1e-3) / 1e9 / peak}
+    cb = cpu_baseline(12.0, 1) if world == 1 else None
+    d2h = sum(len(k.bins) for k in b if k.include) * 4
+    out = {"metric": "sustained MS/s through full PSD cascade", "value": value, "unit": "MS/s", "n_gpus": world,
+           "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
+           "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+           "config": {"workload": WORKLOAD, "channels": world, "samples_per_step_per_gpu": SAMPLES_PER_STEP,
+                      "stage_counts_per_step": [k.count for k in reversed(b)][:8],
+                      "cache": "inputs (800 MB per step) larger than the 126 MB L2"},
+           "roofline": roof, "clocks": clocks, "gpu_launches": int(launches),
+           "e2e": {"value": e2e_value, "unit": "MS/s", "h2d_bytes_per_step": SAMPLES_PER_STEP * 4 * world,
+                   "d2h_bytes_per_step": d2h * world, "steps": e2e_steps, "ms_per_step": ms2 / e2e_steps}}
+    if cb is not None:
+        out["cpu_baseline"] = cb
+    print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -165,6 +165,28 @@ int32_t sspsd_cascade_partials(sspsd_cascade *h, sspsd_partials *out);
 /* overwrite the per-stage segment counts after an external reduction of `acc` (boxcar averaging only) */
 int32_t sspsd_cascade_set_counts(sspsd_cascade *h, const uint64_t *count_raw, uint32_t n_stages);
 
+/* ---- measurement hooks (no reference analogue) ----
+ * With profiling enabled every kernel launch of the handle is bracketed by CUDA events on the
+ * handle's stream; sspsd_cascade_profile_read() synchronises, sums the event times per kernel class
+ * and clears the log.  `launches` counts kernel launches since creation / the last read, whether
+ * profiling is enabled or not. */
+enum {
+    SSPSD_PROF_PSD_STAGE0 = 0, /* psd_stage_kernel on stage 0 (units: input samples) */
+    SSPSD_PROF_PSD_DEEP = 1,   /* psd_stage_kernel on stages >= 1 */
+    SSPSD_PROF_DECIM_STAGE0 = 2,
+    SSPSD_PROF_DECIM_DEEP = 3,
+    SSPSD_PROF_OTHER = 4,      /* carry copies, EWMA rescale */
+    SSPSD_PROF_NCLASS = 5
+};
+typedef struct {
+    double ms[SSPSD_PROF_NCLASS];       /* summed device time per class */
+    uint64_t launches[SSPSD_PROF_NCLASS];
+    uint64_t units[SSPSD_PROF_NCLASS];  /* input samples consumed by those launches */
+    uint64_t launches_total;
+} sspsd_profile;
+int32_t sspsd_cascade_profile_enable(sspsd_cascade *h, int32_t on);
+int32_t sspsd_cascade_profile_read(sspsd_cascade *h, sspsd_profile *out);
+
 /* ---------------------------------------------------------------------------------------------
  * Psd<N> + trait PsdStage, src/psd.rs:119-288 (a single stage with its decimated output exposed)
  * --------------------------------------------------------------------------------------------- */

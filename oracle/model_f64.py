@@ -41,11 +41,11 @@ def hbf_impulse(t):
     m = len(t)
     h = np.zeros(4 * m - 1)
     c = 2 * m - 1
-    h[c] = 0.5
+    h[c] = 1.0  # taps are 2*remez(...): DC gain 2 per half-band stage (see sspsd_oracle.c)
     for i, tk in enumerate(t):
         k = m - 1 - i
-        h[c - (2 * k + 1)] = 0.5 * tk
-        h[c + (2 * k + 1)] = 0.5 * tk
+        h[c - (2 * k + 1)] = tk
+        h[c + (2 * k + 1)] = tk
     return h
 
 

@@ -21,9 +21,13 @@
 /* ------------------------------------------------------------------------------------------
  * idsp::hbf restatement
  * One half-band decimate-by-2 stage with M unique taps is the causal linear-phase FIR
- *   y[j] = 0.5 * ( x[c] + sum_{i=0}^{M-1} t[i] * (x[c-(2k+1)] + x[c+(2k+1)]) ),
+ *   y[j] = x[c] + sum_{i=0}^{M-1} t[i] * (x[c-(2k+1)] + x[c+(2k+1)]),
  *   k = M-1-i,  c = 2*j - 2*M + 2,   newest input used: x[2*j+1]
- * with zero initial state.  HbfDec8 chains three of them, highest rate first, using tap sets
+ * with zero initial state.  The taps are 2*remez(...) (centre tap 1.0, sum of t = 0.5), so every
+ * stage has DC gain 2 and the divide-by-8 cascade has amplitude gain 8.  That gain is what makes
+ * the reference's stage normalisation 1/(gain * decimation) (psd.rs:516) continuous across stage
+ * breaks for noise: power gain 64, bandwidth 1/8 => net 8 = decimation per stage (this is what the
+ * reference test psd.rs:634-643 asserts: 0.5*p ~ 1 in every break).  HbfDec8 chains three of them, highest rate first, using tap sets
  * 2, 1, 0 (the lowest-rate stage has the longest filter).  psd.rs:246-253 feeds it chunks of
  * 8 items and gets one item per chunk.
  * ------------------------------------------------------------------------------------------ */
@@ -74,20 +78,37 @@ void orc_hbf8_free(orc_hbf8 *h)
     free(h);
 }
 
-/* e = hist ++ x (2k new inputs) -> y (k outputs); hist <- last 4m-2 of e */
+/* e = hist ++ x (2k new inputs) -> y (k outputs); hist <- last 4m-2 of e.
+ * Per output the taps are accumulated in the same order as a scalar loop would (outermost first);
+ * the loops are merely arranged tap-outer / output-inner over de-interleaved even/odd planes so
+ * that the compiler vectorises across outputs. */
+#define HBF_BLK 512
 static void hbf2_block(hbf2 *f, float *e, size_t k, float *y)
 {
     const int m = f->m;
     const int hl = 4 * m - 2;
     const float *t = f->t;
-    for (size_t j = 0; j < k; j++) {
-        const float *c = e + 2 * m + 2 * j; /* centre tap */
-        float acc = 0.0f;
-        for (int i = 0; i < m; i++) {
-            int d = 2 * (m - 1 - i) + 1;
-            acc += (c[-d] + c[d]) * t[i];
+    float od[HBF_BLK + 2 * ORC_HBF_MAXTAPS + 8], ev[HBF_BLK], acc[HBF_BLK];
+    for (size_t j0 = 0; j0 < k; j0 += HBF_BLK) {
+        const size_t nb = k - j0 < HBF_BLK ? k - j0 : HBF_BLK;
+        /* output j: centre e[2m + 2j]; odd taps e[2m + 2j +- (2q+1)], q < m
+         * od[i] = e[2*j0 + 1 + 2i] covers i in [0, nb + 2m - 1) */
+        const float *base = e + 2 * j0;
+        for (size_t i = 0; i < nb + 2 * (size_t)m - 1; i++)
+            od[i] = base[1 + 2 * i];
+        for (size_t j = 0; j < nb; j++) {
+            ev[j] = base[2 * m + 2 * j];
+            acc[j] = 0.0f;
         }
-        y[j] = (c[0] + acc) * 0.5f;
+        for (int i = 0; i < m; i++) {
+            /* tap i pairs od[j + i] (below the centre) with od[j + 2m - 1 - i] (above) */
+            const float ti = t[i];
+            const float *lo = od + i, *hi = od + (2 * m - 1 - i);
+            for (size_t j = 0; j < nb; j++)
+                acc[j] += (lo[j] + hi[j]) * ti;
+        }
+        for (size_t j = 0; j < nb; j++)
+            y[j0 + j] = ev[j] + acc[j];
     }
     memmove(f->hist, e + 2 * k, (size_t)hl * sizeof(float));
 }
@@ -128,113 +149,220 @@ float orc_hbf_passband(void)
 
 /* ------------------------------------------------------------------------------------------
  * rustfft restatement: forward, unnormalised, X[k] = sum_n x[n] e^{-2 pi i nk/N}.
- * Stockham autosort, radix 4 with one radix-2 pass when log2(N) is odd.  Twiddles from f64.
+ * Four-step FFT over split re/im planes; the sub-transforms are Stockham autosort radix-4 (+ one
+ * radix-2) passes over interleaved batches, so every inner loop is long and contiguous and gcc
+ * vectorises it (the reference's rustfft picks an AVX kernel at run time; this keeps the CPU
+ * baseline within a small factor of it).  Twiddles from f64.
  * ------------------------------------------------------------------------------------------ */
 typedef struct {
-    int n;
-    float *tw; /* interleaved cos, -sin of 2 pi k / n, k < n */
-    float *tmp;
+    int n, n1, n2;
+    float *w1r, *w1i; /* W_n1^k */
+    float *w2r, *w2i; /* W_n2^k */
+    float *tr, *ti;   /* W_n^(k1*c), [n1][n2] */
+    float *ar, *ai, *br, *bi; /* work planes, n floats each */
 } fft_plan;
 
 static fft_plan g_plans[32];
+
+/* Planes are placed at distinct offsets modulo 4 KiB: the radix-4 passes stream 16 arrays whose
+ * mutual distances are powers of two, which would otherwise all map to the same L1 sets. */
+static float *alloc_plane(size_t n, size_t skew_bytes)
+{
+    void *p = NULL;
+    if (posix_memalign(&p, 4096, n * sizeof(float) + 4096) != 0)
+        abort();
+    return (float *)((char *)p + skew_bytes);
+}
+
+static void make_roots(int n, float **wr, float **wi)
+{
+    *wr = (float *)malloc(sizeof(float) * (size_t)n);
+    *wi = (float *)malloc(sizeof(float) * (size_t)n);
+    for (int k = 0; k < n; k++) {
+        double a = -2.0 * M_PI * (double)k / (double)n;
+        (*wr)[k] = (float)cos(a);
+        (*wi)[k] = (float)sin(a);
+    }
+}
 
 static fft_plan *fft_get_plan(int n)
 {
     int l = 0;
     while ((1 << l) < n)
         l++;
-    assert((1 << l) == n && l < 32);
+    assert((1 << l) == n && l < 32 && l >= 2);
     fft_plan *p = &g_plans[l];
     if (p->n != n) {
         p->n = n;
-        p->tw = (float *)malloc(sizeof(float) * 2 * (size_t)n);
-        p->tmp = (float *)malloc(sizeof(float) * 2 * (size_t)n);
-        for (int k = 0; k < n; k++) {
-            double a = -2.0 * M_PI * (double)k / (double)n;
-            p->tw[2 * k] = (float)cos(a);
-            p->tw[2 * k + 1] = (float)sin(a);
-        }
+        p->n1 = 1 << ((l + 1) / 2);
+        p->n2 = n / p->n1;
+        make_roots(p->n1, &p->w1r, &p->w1i);
+        make_roots(p->n2, &p->w2r, &p->w2i);
+        p->tr = (float *)malloc(sizeof(float) * (size_t)n);
+        p->ti = (float *)malloc(sizeof(float) * (size_t)n);
+        for (int k1 = 0; k1 < p->n1; k1++)
+            for (int c = 0; c < p->n2; c++) {
+                double a = -2.0 * M_PI * (double)k1 * (double)c / (double)n;
+                p->tr[k1 * p->n2 + c] = (float)cos(a);
+                p->ti[k1 * p->n2 + c] = (float)sin(a);
+            }
+        p->ar = alloc_plane((size_t)n, 2048);
+        p->ai = alloc_plane((size_t)n, 3072);
+        p->br = alloc_plane((size_t)n, 512);
+        p->bi = alloc_plane((size_t)n, 1536);
     }
     return p;
+}
+
+static inline void r4_inner(const float *restrict ar, const float *restrict ai, const float *restrict br,
+                            const float *restrict bi, const float *restrict cr, const float *restrict ci,
+                            const float *restrict dr, const float *restrict di, float *restrict y0r,
+                            float *restrict y0i, float *restrict y1r, float *restrict y1i, float *restrict y2r,
+                            float *restrict y2i, float *restrict y3r, float *restrict y3i, size_t n, float w1r,
+                            float w1i, float w2r, float w2i, float w3r, float w3i)
+{
+    for (size_t q = 0; q < n; q++) {
+        float apcr = ar[q] + cr[q], apci = ai[q] + ci[q];
+        float amcr = ar[q] - cr[q], amci = ai[q] - ci[q];
+        float bpdr = br[q] + dr[q], bpdi = bi[q] + di[q];
+        float jr = bi[q] - di[q], ji = -(br[q] - dr[q]); /* -i (b - d) */
+        y0r[q] = apcr + bpdr;
+        y0i[q] = apci + bpdi;
+        float t1r = amcr + jr, t1i = amci + ji;
+        y1r[q] = t1r * w1r - t1i * w1i;
+        y1i[q] = t1r * w1i + t1i * w1r;
+        float t2r = apcr - bpdr, t2i = apci - bpdi;
+        y2r[q] = t2r * w2r - t2i * w2i;
+        y2i[q] = t2r * w2i + t2i * w2r;
+        float t3r = amcr - jr, t3i = amci - ji;
+        y3r[q] = t3r * w3r - t3i * w3i;
+        y3i[q] = t3r * w3i + t3i * w3r;
+    }
+}
+
+static inline void r2_inner(const float *restrict ar, const float *restrict ai, const float *restrict br,
+                            const float *restrict bi, float *restrict y0r, float *restrict y0i,
+                            float *restrict y1r, float *restrict y1i, size_t n, float w1r, float w1i)
+{
+    for (size_t q = 0; q < n; q++) {
+        y0r[q] = ar[q] + br[q];
+        y0i[q] = ai[q] + bi[q];
+        float tr = ar[q] - br[q], ti = ai[q] - bi[q];
+        y1r[q] = tr * w1r - ti * w1i;
+        y1i[q] = tr * w1i + ti * w1r;
+    }
+}
+
+/* B interleaved length-n transforms (element idx of transform b at [idx*B + b]), Stockham autosort,
+ * radix 4 (+ one radix 2).  Result ends up in (xr, xi) or (yr, yi); returns 1 if in y. */
+static int fft_batch(float *xr, float *xi, float *yr, float *yi, int n, int B, const float *wr, const float *wi)
+{
+    int len = n, s = 1, flip = 0;
+    while (len > 1) {
+        const size_t sb = (size_t)s * B;
+        if (len % 4 == 0) {
+            const int m = len / 4, tws = n / len;
+            for (int p = 0; p < m; p++) {
+                float *y0r = yr + sb * (4 * p), *y0i = yi + sb * (4 * p);
+                r4_inner(xr + sb * p, xi + sb * p, xr + sb * (p + m), xi + sb * (p + m), xr + sb * (p + 2 * m),
+                         xi + sb * (p + 2 * m), xr + sb * (p + 3 * m), xi + sb * (p + 3 * m), y0r, y0i, y0r + sb,
+                         y0i + sb, y0r + 2 * sb, y0i + 2 * sb, y0r + 3 * sb, y0i + 3 * sb, sb, wr[p * tws],
+                         wi[p * tws], wr[2 * p * tws], wi[2 * p * tws], wr[3 * p * tws], wi[3 * p * tws]);
+            }
+            len = m;
+            s *= 4;
+        } else {
+            const int m = len / 2, tws = n / len;
+            for (int p = 0; p < m; p++) {
+                float *y0r = yr + sb * (2 * p), *y0i = yi + sb * (2 * p);
+                r2_inner(xr + sb * p, xi + sb * p, xr + sb * (p + m), xi + sb * (p + m), y0r, y0i, y0r + sb,
+                         y0i + sb, sb, wr[p * tws], wi[p * tws]);
+            }
+            len = m;
+            s *= 2;
+        }
+        float *t;
+        t = xr; xr = yr; yr = t;
+        t = xi; xi = yi; yi = t;
+        flip ^= 1;
+    }
+    return flip;
+}
+
+/* Four-step FFT on split planes: (re, im) of length n, in place.  n = n1*n2, input index r*n2 + c:
+ * n2 interleaved column transforms of length n1, twiddle W_n^(k1 c), transpose, n1 interleaved
+ * transforms of length n2; X[k1 + n1 k2] lands at k2*n1 + k1, i.e. in natural order. */
+static void fft_soa(float *re, float *im, int n)
+{
+    fft_plan *pl = fft_get_plan(n);
+    const int n1 = pl->n1, n2 = pl->n2;
+    float *xr = re, *xi = im, *yr = pl->ar, *yi = pl->ai;
+    if (fft_batch(xr, xi, yr, yi, n1, n2, pl->w1r, pl->w1i)) {
+        xr = pl->ar;
+        xi = pl->ai;
+    }
+    /* twiddle (contiguous), then blocked transpose [n1][n2] -> [n2][n1] */
+    float *tr = pl->br, *ti = pl->bi;
+    {
+        const float *restrict wr = pl->tr, *restrict wi = pl->ti;
+        float *restrict ar = xr, *restrict ai = xi;
+        for (int i = 0; i < n; i++) {
+            float vr = ar[i] * wr[i] - ai[i] * wi[i];
+            float vi = ar[i] * wi[i] + ai[i] * wr[i];
+            ar[i] = vr;
+            ai[i] = vi;
+        }
+    }
+    enum { TB = 16 };
+    for (int r0 = 0; r0 < n1; r0 += TB)
+        for (int c0 = 0; c0 < n2; c0 += TB) {
+            const int rb = n1 - r0 < TB ? n1 - r0 : TB, cb = n2 - c0 < TB ? n2 - c0 : TB;
+            for (int c = 0; c < cb; c++) {
+                float *restrict dr = tr + (size_t)(c0 + c) * n1 + r0, *restrict di = ti + (size_t)(c0 + c) * n1 + r0;
+                const float *restrict sr = xr + (size_t)r0 * n2 + c0 + c, *restrict si = xi + (size_t)r0 * n2 + c0 + c;
+                for (int r = 0; r < rb; r++) {
+                    dr[r] = sr[(size_t)r * n2];
+                    di[r] = si[(size_t)r * n2];
+                }
+            }
+        }
+    float *zr = (xr == re) ? pl->ar : re, *zi = (xr == re) ? pl->ai : im;
+    if (fft_batch(tr, ti, zr, zi, n2, n1, pl->w2r, pl->w2i)) {
+        if (zr != re) {
+            memcpy(re, zr, sizeof(float) * (size_t)n);
+            memcpy(im, zi, sizeof(float) * (size_t)n);
+        }
+    } else {
+        memcpy(re, tr, sizeof(float) * (size_t)n);
+        memcpy(im, ti, sizeof(float) * (size_t)n);
+    }
 }
 
 void orc_fft_forward(float *c, int n)
 {
     if (n <= 1)
         return;
-    fft_plan *pl = fft_get_plan(n);
-    float *x = c, *y = pl->tmp;
-    const float *tw = pl->tw;
-    int len = n, s = 1;
-    while (len > 1) {
-        if (len % 4 == 0) {
-            int m = len / 4;
-            int tws = n / len; /* twiddle stride: W_len^p = tw[p*tws] */
-            for (int p = 0; p < m; p++) {
-                float w1r = tw[2 * (p * tws)], w1i = tw[2 * (p * tws) + 1];
-                float w2r = tw[2 * (2 * p * tws)], w2i = tw[2 * (2 * p * tws) + 1];
-                float w3r = tw[2 * (3 * p * tws)], w3i = tw[2 * (3 * p * tws) + 1];
-                const float *xa = x + 2 * (size_t)(s * p);
-                const float *xb = x + 2 * (size_t)(s * (p + m));
-                const float *xc = x + 2 * (size_t)(s * (p + 2 * m));
-                const float *xd = x + 2 * (size_t)(s * (p + 3 * m));
-                float *y0 = y + 2 * (size_t)(s * (4 * p));
-                float *y1 = y + 2 * (size_t)(s * (4 * p + 1));
-                float *y2 = y + 2 * (size_t)(s * (4 * p + 2));
-                float *y3 = y + 2 * (size_t)(s * (4 * p + 3));
-                for (int q = 0; q < s; q++) {
-                    float ar = xa[2 * q], ai = xa[2 * q + 1];
-                    float br = xb[2 * q], bi = xb[2 * q + 1];
-                    float cr = xc[2 * q], ci = xc[2 * q + 1];
-                    float dr = xd[2 * q], di = xd[2 * q + 1];
-                    float apcr = ar + cr, apci = ai + ci;
-                    float amcr = ar - cr, amci = ai - ci;
-                    float bpdr = br + dr, bpdi = bi + di;
-                    /* -i * (b - d) */
-                    float jr = bi - di, ji = -(br - dr);
-                    y0[2 * q] = apcr + bpdr;
-                    y0[2 * q + 1] = apci + bpdi;
-                    float t1r = amcr + jr, t1i = amci + ji;
-                    y1[2 * q] = t1r * w1r - t1i * w1i;
-                    y1[2 * q + 1] = t1r * w1i + t1i * w1r;
-                    float t2r = apcr - bpdr, t2i = apci - bpdi;
-                    y2[2 * q] = t2r * w2r - t2i * w2i;
-                    y2[2 * q + 1] = t2r * w2i + t2i * w2r;
-                    float t3r = amcr - jr, t3i = amci - ji;
-                    y3[2 * q] = t3r * w3r - t3i * w3i;
-                    y3[2 * q + 1] = t3r * w3i + t3i * w3r;
-                }
-            }
-            len = m;
-            s *= 4;
-        } else {
-            int m = len / 2;
-            int tws = n / len;
-            for (int p = 0; p < m; p++) {
-                float wr = tw[2 * (p * tws)], wi = tw[2 * (p * tws) + 1];
-                const float *xa = x + 2 * (size_t)(s * p);
-                const float *xb = x + 2 * (size_t)(s * (p + m));
-                float *y0 = y + 2 * (size_t)(s * (2 * p));
-                float *y1 = y + 2 * (size_t)(s * (2 * p + 1));
-                for (int q = 0; q < s; q++) {
-                    float ar = xa[2 * q], ai = xa[2 * q + 1];
-                    float br = xb[2 * q], bi = xb[2 * q + 1];
-                    y0[2 * q] = ar + br;
-                    y0[2 * q + 1] = ai + bi;
-                    float tr = ar - br, ti = ai - bi;
-                    y1[2 * q] = tr * wr - ti * wi;
-                    y1[2 * q + 1] = tr * wi + ti * wr;
-                }
-            }
-            len = m;
-            s *= 2;
-        }
-        float *t = x;
-        x = y;
-        y = t;
+    if (n == 2) {
+        float ar = c[0], ai = c[1], br = c[2], bi = c[3];
+        c[0] = ar + br; c[1] = ai + bi; c[2] = ar - br; c[3] = ai - bi;
+        return;
     }
-    if (x != c)
-        memcpy(c, x, sizeof(float) * 2 * (size_t)n);
+    static float *re = NULL, *im = NULL;
+    static int cap = 0;
+    if (n > cap) { /* planes are never freed (they are skewed pointers); grow-only scratch */
+        re = alloc_plane((size_t)n, 0);
+        im = alloc_plane((size_t)n, 1024);
+        cap = n;
+    }
+    for (int i = 0; i < n; i++) {
+        re[i] = c[2 * i];
+        im[i] = c[2 * i + 1];
+    }
+    fft_soa(re, im, n);
+    for (int i = 0; i < n; i++) {
+        c[2 * i] = re[i];
+        c[2 * i + 1] = im[i];
+    }
 }
 
 /* ------------------------------------------------------------------------------------------
@@ -261,30 +389,25 @@ void orc_window(int n, int window, float *win, float *power, float *nenbw, size_
     }
 }
 
-/* Detrend::apply (psd.rs:75-113) */
-int orc_detrend_apply(int detrend, const float *x, const float *win, int n, float *c)
+/* Detrend::apply (psd.rs:75-113), real part only (the imaginary part is 0) */
+static int detrend_real(int detrend, const float *x, const float *win, int n, float *re)
 {
     switch (detrend) {
     case ORC_DETREND_NONE: /* psd.rs:81-86 */
-        for (int i = 0; i < n; i++) {
-            c[2 * i] = x[i] * win[i];
-            c[2 * i + 1] = 0.0f;
-        }
+        for (int i = 0; i < n; i++)
+            re[i] = x[i] * win[i];
         return 0;
     case ORC_DETREND_MIDPOINT: { /* psd.rs:87-93 */
         float offset = x[n / 2];
-        for (int i = 0; i < n; i++) {
-            c[2 * i] = (x[i] - offset) * win[i];
-            c[2 * i + 1] = 0.0f;
-        }
+        for (int i = 0; i < n; i++)
+            re[i] = (x[i] - offset) * win[i];
         return 0;
     }
     case ORC_DETREND_SPAN: { /* psd.rs:94-102: offset accumulated sequentially */
         float offset = x[0];
         float slope = (x[n - 1] - x[0]) / (float)(n - 1);
         for (int i = 0; i < n; i++) {
-            c[2 * i] = (x[i] - offset) * win[i];
-            c[2 * i + 1] = 0.0f;
+            re[i] = (x[i] - offset) * win[i];
             offset += slope;
         }
         return 0;
@@ -294,15 +417,26 @@ int orc_detrend_apply(int detrend, const float *x, const float *win, int n, floa
         for (int i = 0; i < n; i++)
             sum += x[i];
         float offset = sum / (float)n;
-        for (int i = 0; i < n; i++) {
-            c[2 * i] = (x[i] - offset) * win[i];
-            c[2 * i + 1] = 0.0f;
-        }
+        for (int i = 0; i < n; i++)
+            re[i] = (x[i] - offset) * win[i];
         return 0;
     }
     default: /* psd.rs:110 unimplemented!() */
         return -1;
     }
+}
+
+int orc_detrend_apply(int detrend, const float *x, const float *win, int n, float *c)
+{
+    float *re = (float *)malloc(sizeof(float) * (size_t)n);
+    int r = detrend_real(detrend, x, win, n, re);
+    if (r == 0)
+        for (int i = 0; i < n; i++) {
+            c[2 * i] = re[i];
+            c[2 * i + 1] = 0.0f;
+        }
+    free(re);
+    return r;
 }
 
 /* ------------------------------------------------------------------------------------------
@@ -323,7 +457,8 @@ struct orc_stage {
     size_t overlap;
     int detrend;
     uint32_t avg;
-    float *c; /* scratch: N complex */
+    float *c_re, *c_im; /* scratch planes, N floats each (skewed, see alloc_plane) */
+    void *c_base;
 };
 
 orc_stage *orc_stage_new(int n, int window, int hbf_preset)
@@ -339,7 +474,10 @@ orc_stage *orc_stage_new(int n, int window, int hbf_preset)
     s->buf = (float *)calloc((size_t)n, sizeof(float));
     s->spectrum = (float *)calloc((size_t)n, sizeof(float));
     s->win = (float *)calloc((size_t)n, sizeof(float));
-    s->c = (float *)calloc(2 * (size_t)n, sizeof(float));
+    if (posix_memalign(&s->c_base, 4096, 2 * (size_t)n * sizeof(float) + 8192) != 0)
+        abort();
+    s->c_re = (float *)s->c_base;
+    s->c_im = (float *)((char *)s->c_base + (((size_t)n * sizeof(float) + 4095) & ~(size_t)4095) + 1024);
     orc_window(n, window, s->win, &s->power, &s->nenbw, &s->overlap);
     s->count = 0;
     s->idx = 0;
@@ -372,7 +510,7 @@ void orc_stage_free(orc_stage *s)
     free(s->buf);
     free(s->spectrum);
     free(s->win);
-    free(s->c);
+    free(s->c_base);
     free(s);
 }
 
@@ -393,10 +531,11 @@ size_t orc_stage_process(orc_stage *s, const float *x, size_t nx, float *y)
         if (s->idx < N)
             break;
 
-        /* detrend and window, psd.rs:211; fft in place, psd.rs:213 */
-        if (orc_detrend_apply(s->detrend, s->buf, s->win, s->n, s->c) != 0)
+        /* detrend and window, psd.rs:211 (re plane; im = 0); fft in place, psd.rs:213 */
+        if (detrend_real(s->detrend, s->buf, s->win, s->n, s->c_re) != 0)
             abort(); /* Detrend::Linear panics in the reference */
-        orc_fft_forward(s->c, s->n);
+        memset(s->c_im, 0, N * sizeof(float));
+        fft_soa(s->c_re, s->c_im, s->n);
 
         int is_first = s->count == 0; /* psd.rs:215 */
 
@@ -412,7 +551,7 @@ size_t orc_stage_process(orc_stage *s, const float *x, size_t nx, float *y)
 
         /* power accumulate, psd.rs:228-233 (norm_sqr = re*re + im*im, unfused) */
         for (size_t k = 0; k <= N / 2; k++) {
-            float re = s->c[2 * k], im = s->c[2 * k + 1];
+            float re = s->c_re[k], im = s->c_im[k];
             s->spectrum[k] = g * s->spectrum[k] + (re * re + im * im);
         }
 

@@ -44,6 +44,11 @@ class PartialsC(C.Structure):
                 ("count_raw", C.c_uint64 * MAX_STAGES)]
 
 
+class ProfileC(C.Structure):
+    _fields_ = [("ms", C.c_double * 5), ("launches", C.c_uint64 * 5), ("units", C.c_uint64 * 5),
+                ("launches_total", C.c_uint64)]
+
+
 class LossC(C.Structure):
     _fields_ = [("received", C.c_uint64), ("dropped", C.c_uint64), ("seq", C.c_uint32), ("has_seq", C.c_uint32)]
 
@@ -82,6 +87,8 @@ PROTOTYPES = {
     "sspsd_break_frequencies": (_i32, [C.POINTER(BreakC), _sz, _vp, _psz]),
     "sspsd_cascade_partials": (_i32, [_vp, C.POINTER(PartialsC)]),
     "sspsd_cascade_set_counts": (_i32, [_vp, C.POINTER(C.c_uint64), C.c_uint32]),
+    "sspsd_cascade_profile_enable": (_i32, [_vp, _i32]),
+    "sspsd_cascade_profile_read": (_i32, [_vp, C.POINTER(ProfileC)]),
     "sspsd_stage_create": (_i32, [C.POINTER(Config), C.POINTER(_vp)]),
     "sspsd_stage_destroy": (None, [_vp]),
     "sspsd_stage_set_avg": (_i32, [_vp, C.c_uint32]),

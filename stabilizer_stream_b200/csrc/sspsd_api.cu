@@ -186,6 +186,18 @@ int32_t sspsd_cascade_set_counts(sspsd_cascade* h, const uint64_t* craw, uint32_
     return h ? h->c.set_counts(craw, n) : SSPSD_EINVAL;
 }
 
+int32_t sspsd_cascade_profile_enable(sspsd_cascade* h, int32_t on)
+{
+    if (!h) return SSPSD_EINVAL;
+    h->c.profile_enable(on != 0);
+    return SSPSD_OK;
+}
+
+int32_t sspsd_cascade_profile_read(sspsd_cascade* h, sspsd_profile* out)
+{
+    return h ? h->c.profile_read(out) : SSPSD_EINVAL;
+}
+
 // ---------------------------------------------------------------------------------------------
 int32_t sspsd_stage_create(const sspsd_config* cfg, sspsd_stage** out)
 {

@@ -375,10 +375,13 @@ int Cascade::launch_psd(size_t i, const StreamSrc& src, uint64_t k0, uint64_t ns
     p.g_first = g_first;
     p.g_s = g_s;
     int grid = (int)((nseg + p.T - 1) / p.T);
-    return launch_stage((int)log2n_, p, grid, stream_);
+    prof_begin(i == 0 ? SSPSD_PROF_PSD_STAGE0 : SSPSD_PROF_PSD_DEEP, nseg * (uint64_t)hop_);
+    int rc = launch_stage((int)log2n_, p, grid, stream_);
+    prof_end();
+    return rc;
 }
 
-int Cascade::launch_decim(size_t, const StreamSrc& src, uint64_t m0, uint64_t m1, float* out_fresh,
+int Cascade::launch_decim(size_t i, const StreamSrc& src, uint64_t m0, uint64_t m1, float* out_fresh,
                           long long out_split, float* out_carry, long long out_carry_start)
 {
     DecimParams p{};
@@ -395,9 +398,11 @@ int Cascade::launch_decim(size_t, const StreamSrc& src, uint64_t m0, uint64_t m1
     if (p.m1 <= lo)
         return SSPSD_OK;
     int grid = (int)((p.m1 - lo + DEC_OB - 1) / DEC_OB);
-    if (cfg_.hbf == SSPSD_HBF_98)
-        return launch_decim_t<3, 6, 15>(p, grid, stream_);
-    return launch_decim_t<5, 10, 23>(p, grid, stream_);
+    prof_begin(i == 0 ? SSPSD_PROF_DECIM_STAGE0 : SSPSD_PROF_DECIM_DEEP, (uint64_t)(p.m1 - lo) * 8);
+    int rc = cfg_.hbf == SSPSD_HBF_98 ? launch_decim_t<3, 6, 15>(p, grid, stream_)
+                                      : launch_decim_t<5, 10, 23>(p, grid, stream_);
+    prof_end();
+    return rc;
 }
 
 // One batch of one stage: n_new samples have been appended to the stage's stream (in `fresh` for
@@ -416,7 +421,9 @@ int Cascade::run_stage(size_t i, const float* fresh, long long split, uint64_t n
         EwmaPlan e = ewma_plan(st.count, st.avg, S);
         if (e.total != 1.0f) {
             int nb = (int)(n_ / 2 + 1);
+            prof_begin(SSPSD_PROF_OTHER, 0);
             scale_kernel<<<(nb + 255) / 256, 256, 0, stream_>>>(d_acc_ + i * acc_stride_, nb, e.total);
+            prof_end();
             SSPSD_CUDA(cudaGetLastError());
         }
         rc = launch_psd(i, src, craw0, S, e.jb, e.g_first, e.g_s);
@@ -467,7 +474,9 @@ int Cascade::run_stage(size_t i, const float* fresh, long long split, uint64_t n
         StageState& s2 = stages_[i];
         const long long cs = (long long)D1 - hb_;
         const int n = (int)((long long)L1 - cs);
+        prof_begin(SSPSD_PROF_OTHER, 0);
         carry_copy_kernel<<<std::max(1, std::min(64, (n + 255) / 256)), 256, 0, stream_>>>(src, cs, n, s2.carry[s2.cur ^ 1]);
+        prof_end();
         SSPSD_CUDA(cudaGetLastError());
         s2.cur ^= 1;
         s2.carry_start = cs;
@@ -555,8 +564,10 @@ int Cascade::feed_host_chunk(const float* xh, size_t n)
         // <= 3 samples complete the carry's last float4 group; passed by value, no host lifetime issue
         float v[3] = {0.f, 0.f, 0.f};
         for (size_t q = 0; q < sliver; ++q) v[q] = xh[q];
+        prof_begin(SSPSD_PROF_OTHER, 0);
         set_small_kernel<<<1, 32, 0, stream_>>>(st.carry[st.cur] + ((long long)st.L - st.carry_start), (int)sliver,
                                                 v[0], v[1], v[2]);
+        prof_end();
         SSPSD_CUDA(cudaGetLastError());
     }
     const size_t rest = n - sliver;
@@ -870,6 +881,47 @@ int Cascade::psd(const sspsd_merge_opts& o, float* p, size_t* p_len, sspsd_break
         } else {
             end = start;
         }
+    }
+    return SSPSD_OK;
+}
+
+void Cascade::prof_begin(int cls, uint64_t units)
+{
+    launches_[cls]++;
+    if (!prof_on_) return;
+    ProfRec r{cls, nullptr, nullptr, units};
+    if (cudaEventCreate(&r.a) != cudaSuccess || cudaEventCreate(&r.b) != cudaSuccess) return;
+    cudaEventRecord(r.a, stream_);
+    prof_.push_back(r);
+}
+
+void Cascade::prof_end()
+{
+    if (!prof_on_ || prof_.empty()) return;
+    cudaEventRecord(prof_.back().b, stream_);
+}
+
+int Cascade::profile_read(sspsd_profile* out)
+{
+    if (!out) return SSPSD_EINVAL;
+    DeviceGuard g(cfg_.device);
+    if (!g.ok) return SSPSD_ECUDA;
+    SSPSD_CUDA(cudaStreamSynchronize(stream_));
+    std::memset(out, 0, sizeof(*out));
+    for (auto& r : prof_) {
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, r.a, r.b) == cudaSuccess) {
+            out->ms[r.cls] += ms;
+            out->launches[r.cls]++;
+            out->units[r.cls] += r.units;
+        }
+        cudaEventDestroy(r.a);
+        cudaEventDestroy(r.b);
+    }
+    prof_.clear();
+    for (int c = 0; c < SSPSD_PROF_NCLASS; ++c) {
+        out->launches_total += launches_[c];
+        launches_[c] = 0;
     }
     return SSPSD_OK;
 }

@@ -60,6 +60,8 @@ public:
     int sync();
     int psd(const sspsd_merge_opts& o, float* p, size_t* p_len, sspsd_break* b, size_t* b_len);
     int partials(sspsd_partials* out);
+    void profile_enable(bool on) { prof_on_ = on; }
+    int profile_read(sspsd_profile* out);
     int set_counts(const uint64_t* craw, uint32_t n);
 
     // single-stage helpers (PsdStage trait)
@@ -93,6 +95,17 @@ private:
     float gain_of(uint32_t count) const;
     uint32_t stage_avg(size_t i) const;
     uint64_t decimated(const StageState& st) const { return st.craw ? n_ + (st.craw - 1) * (uint64_t)hop_ : 0; }
+
+    struct ProfRec {
+        int cls;
+        cudaEvent_t a, b;
+        uint64_t units;
+    };
+    bool prof_on_ = false;
+    std::vector<ProfRec> prof_;
+    uint64_t launches_[SSPSD_PROF_NCLASS] = {0, 0, 0, 0, 0};
+    void prof_begin(int cls, uint64_t units);
+    void prof_end();
 
     sspsd_config cfg_{};
     uint32_t n_ = 0, log2n_ = 0, hop_ = 0, max_stages_ = SSPSD_MAX_STAGES;

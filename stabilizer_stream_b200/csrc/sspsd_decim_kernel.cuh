@@ -42,9 +42,9 @@ __device__ __forceinline__ int pad32(int i) { return i + (i >> 5); }
 // One half-band stage over de-interleaved, padded planes.
 //   ine/ino : input planes; plane index r <-> input sample in_base + 2r (+1 for the odd plane)
 //   outputs j = out_base + 4w + q (q < 4), for work items w < n_out/4, where
-//   y[j] = 0.5*(e[r-M+1] + sum_i t[i]*(o[r-2M+1+i] + o[r-i])),  r = j - in_base/2
+//   y[j] = e[r-M+1] + sum_i t[i]*(o[r-2M+1+i] + o[r-i]),  r = j - in_base/2   (DC gain 2 per stage)
 // rel0 = out_base - in_base/2 (relative index of the first output).
-// If FINAL, outputs go to `gout` (global, scalar) through the (m0, m1, drain) window; otherwise to
+// If FINAL, outputs go to the next stage's stream (DecimParams) for m in [m0, m1); otherwise to
 // the padded planes oute/outo with plane index (j - out_base)/2.
 struct DecimParams {
     StreamSrc src;
@@ -78,7 +78,7 @@ __device__ __forceinline__ void hbf_stage(const float* __restrict__ ine, const f
 #pragma unroll
             for (int i = 0; i < M; ++i)
                 acc = fmaf(win[q + i] + win[q + 2 * M - 1 - i], taps[i], acc);
-            y[q] = 0.5f * (ine[pad32(r0 + q - M + 1)] + acc);
+            y[q] = ine[pad32(r0 + q - M + 1)] + acc;
         }
         if constexpr (FINAL) {
 #pragma unroll

@@ -183,6 +183,16 @@ class PsdCascade:
         L.check(L.lib().sspsd_cascade_psd(self._h, C.byref(o), p.ctypes.data, C.byref(pl), b, C.byref(bl)))
         return p[:pl.value].copy(), [Break._from_c(b[i]) for i in range(bl.value)]
 
+    def profile_enable(self, on=True):
+        L.check(L.lib().sspsd_cascade_profile_enable(self._h, int(on)))
+
+    def profile_read(self):
+        """-> dict(class -> (ms, launches, input samples)), total kernel launches since the last read"""
+        out = L.ProfileC()
+        L.check(L.lib().sspsd_cascade_profile_read(self._h, C.byref(out)))
+        names = ("psd_stage0", "psd_deep", "decim_stage0", "decim_deep", "other")
+        return {k: (out.ms[i], out.launches[i], out.units[i]) for i, k in enumerate(names)}, out.launches_total
+
     def partials(self):
         out = L.PartialsC()
         L.check(L.lib().sspsd_cascade_partials(self._h, C.byref(out)))

@@ -19,7 +19,12 @@ def sp():
     return m
 
 
-def assert_bins_close(got, want, what=""):
+DC_RTOL = 1e-2  # bins 0 and 1 under Mean/Span detrend: what is left after subtracting the offset is set by
+#                 the rounding of that offset; the oracle sums sequentially in f32 like the reference
+#                 (src/psd.rs:100,104), the GPU sums as a tree, so the two agree only to ~N*eps*DC/sigma
+
+
+def assert_bins_close(got, want, what="", loose_head=0):
     got = np.asarray(got, np.float64)
     want = np.asarray(want, np.float64)
     assert got.shape == want.shape, what
@@ -27,8 +32,11 @@ def assert_bins_close(got, want, what=""):
         return
     floor = AFLOOR * np.median(np.abs(want))
     err = np.abs(got - want) - floor
-    rel = np.max(err / np.maximum(np.abs(want), 1e-300))
-    assert rel <= RTOL, "%s: max rel err %.3g" % (what, rel)
+    rel = err / np.maximum(np.abs(want), 1e-300)
+    if loose_head:
+        assert np.max(rel[:loose_head]) <= DC_RTOL, "%s: DC bins rel err %.3g" % (what, np.max(rel[:loose_head]))
+        rel = rel[loose_head:]
+    assert rel.size == 0 or np.max(rel) <= RTOL, "%s: max rel err %.3g" % (what, np.max(rel))
 
 
 def breaks_tuple(b):
@@ -61,7 +69,7 @@ def test_detrend_modes(sp, oracle, n, det):
     o.set_detrend(det)
     g.process(x)
     o.process(x)
-    assert_bins_close(g.spectrum(), o.spectrum(), "detrend %d" % det)
+    assert_bins_close(g.spectrum(), o.spectrum(), "detrend %d" % det, loose_head=2 if det >= 2 else 0)
 
 
 def test_detrend_linear_is_unimplemented(sp):
@@ -101,6 +109,8 @@ def test_reference_statistical_test(sp):
         seg = p[bi.start:bi.start + len(bi.bins)]
         if bi.include and bi.count:
             assert np.all(np.abs(seg * 0.5 - 1.0) < 10.0 / np.sqrt(bi.count))
+            # continuity across stage breaks: the decimator's gain of 8 cancels 1/decimation (psd.rs:516)
+            assert abs(np.mean(seg) * 0.5 - 1.0) < 5.0 / np.sqrt(bi.count * seg.size)
     f = sp.Break.frequencies(b)
     assert f.size == p.size and f[0] == 0.0 and f[-1] == 0.5
 
@@ -127,7 +137,8 @@ def test_cascade_matches_oracle_ragged_host_and_device(sp, oracle, n, det, hbf):
     p, b = g.psd()
     po, bo = o.psd()
     assert [breaks_tuple(k) for k in b] == [k.as_tuple() for k in bo]
-    assert_bins_close(p, po, "cascade n=%d" % n)
+    loose = 2 if det >= 2 else 0
+    assert_bins_close(p, po, "cascade n=%d" % n, loose_head=loose)
     np.testing.assert_array_equal(sp.Break.frequencies(b), oracle.break_frequencies(bo))
     # every stage on its own, all bins, all merge options
     pk, bk = g.psd(sp.MergeOpts(keep_overlap=True, min_count=0, keep_transition_band=True))
@@ -136,7 +147,7 @@ def test_cascade_matches_oracle_ragged_host_and_device(sp, oracle, n, det, hbf):
     for bi in bk:
         if bi.count:
             sl = slice(bi.start, bi.start + len(bi.bins))
-            assert_bins_close(pk[sl], pok[sl], "stage dec=%d" % bi.decimation)
+            assert_bins_close(pk[sl], pok[sl], "stage dec=%d" % bi.decimation, loose_head=loose)
 
 
 def test_cascade_ewma_and_option_changes(sp, oracle):
@@ -156,7 +167,7 @@ def test_cascade_ewma_and_option_changes(sp, oracle):
     p, b = g.psd()
     po, bo = o.psd()
     assert [breaks_tuple(k) for k in b] == [k.as_tuple() for k in bo]
-    assert_bins_close(p, po, "ewma")
+    assert_bins_close(p, po, "ewma", loose_head=2)
 
 
 def test_clone_reset_and_empty(sp, oracle):
