@@ -1,0 +1,201 @@
+//! `stabilizer_stream::gpu` -- safe wrappers over the C ABI of libsspsd (include/sspsd.h) that
+//! re-implement the public types of `src/psd.rs` on the B200.  SOURCE ONLY: never compiled here
+//! (no Rust toolchain in the build container).  With this module the binaries keep their code:
+//! `use stabilizer_stream::gpu::PsdCascade` instead of `stabilizer_stream::PsdCascade`.
+use std::{ffi::CStr, ops::Range, os::raw::c_char, ptr};
+
+pub use crate::{AvgOpts, Break, Detrend, MergeOpts};
+
+#[repr(C)]
+struct Config {
+    n_fft: u32,
+    window: i32,
+    hbf: i32,
+    device: i32,
+    stream: *mut core::ffi::c_void,
+    max_batch: u64,
+    host_stage: u64,
+}
+#[repr(C)]
+#[derive(Clone, Copy)]
+struct CAvgOpts {
+    limit: u32,
+    count: u32,
+}
+#[repr(C)]
+struct CMergeOpts {
+    keep_overlap: u32,
+    min_count: u32,
+    keep_transition_band: u32,
+}
+#[repr(C)]
+#[derive(Clone, Copy, Default)]
+struct CBreak {
+    start: u64,
+    include: u32,
+    count: u32,
+    avg: u32,
+    _pad: u32,
+    bins_start: u64,
+    bins_end: u64,
+    fft_size: u64,
+    decimation: u64,
+    pending: u64,
+    processed: u64,
+}
+#[repr(C)]
+#[derive(Clone, Copy, Default)]
+pub struct CLoss {
+    pub received: u64,
+    pub dropped: u64,
+    pub seq: u32,
+    pub has_seq: u32,
+}
+#[repr(C)]
+#[derive(Default)]
+pub struct DecodeInfo {
+    pub format: u32,
+    pub n_traces: u32,
+    pub samples_per_trace: u64,
+    pub frames_ok: u64,
+}
+enum CCascade {}
+enum CDecoder {}
+
+extern "C" {
+    fn sspsd_last_error() -> *const c_char;
+    fn sspsd_config_default(n_fft: u32, cfg: *mut Config) -> i32;
+    fn sspsd_cascade_create(cfg: *const Config, out: *mut *mut CCascade) -> i32;
+    fn sspsd_cascade_destroy(h: *mut CCascade);
+    fn sspsd_cascade_clone(h: *mut CCascade, out: *mut *mut CCascade) -> i32;
+    fn sspsd_cascade_process_f32(h: *mut CCascade, x: *const f32, n: usize, mem: i32) -> i32;
+    fn sspsd_cascade_set_avg(h: *mut CCascade, avg: CAvgOpts) -> i32;
+    fn sspsd_cascade_set_detrend(h: *mut CCascade, detrend: i32) -> i32;
+    fn sspsd_cascade_rbw(h: *const CCascade, rbw: *mut f32) -> i32;
+    fn sspsd_cascade_psd(h: *mut CCascade, opts: *const CMergeOpts, p: *mut f32, p_len: *mut usize,
+                         b: *mut CBreak, b_len: *mut usize) -> i32;
+    fn sspsd_decoder_create(device: i32, stream: *mut core::ffi::c_void, out: *mut *mut CDecoder) -> i32;
+    fn sspsd_decoder_destroy(d: *mut CDecoder);
+    fn sspsd_cascade_process_frames(d: *mut CDecoder, cascades: *const *mut CCascade, n: u32, frames: *const u8,
+                                    n_frames: usize, frame_len: usize, frame_stride: usize, mem: i32,
+                                    loss: *mut CLoss, info: *mut DecodeInfo) -> i32;
+}
+
+fn check(status: i32) {
+    // The reference's PSD API is infallible; a CUDA failure is as fatal as an allocation failure.
+    if status != 0 {
+        let msg = unsafe { CStr::from_ptr(sspsd_last_error()) }.to_string_lossy();
+        panic!("sspsd error {status}: {msg}");
+    }
+}
+
+/// Drop-in for `stabilizer_stream::PsdCascade<N>` (src/psd.rs:399-544).
+pub struct PsdCascade<const N: usize> {
+    h: *mut CCascade,
+}
+// moved into the receiver thread by the binaries (src/bin/psd.rs:170-176)
+unsafe impl<const N: usize> Send for PsdCascade<N> {}
+
+impl<const N: usize> Default for PsdCascade<N> {
+    fn default() -> Self {
+        let mut cfg = core::mem::MaybeUninit::<Config>::uninit();
+        let mut h = ptr::null_mut();
+        unsafe {
+            check(sspsd_config_default(N as u32, cfg.as_mut_ptr()));
+            check(sspsd_cascade_create(cfg.as_ptr(), &mut h));
+        }
+        Self { h }
+    }
+}
+
+impl<const N: usize> Clone for PsdCascade<N> {
+    fn clone(&self) -> Self {
+        let mut h = ptr::null_mut();
+        unsafe { check(sspsd_cascade_clone(self.h, &mut h)) };
+        Self { h }
+    }
+}
+
+impl<const N: usize> Drop for PsdCascade<N> {
+    fn drop(&mut self) {
+        unsafe { sspsd_cascade_destroy(self.h) }
+    }
+}
+
+impl<const N: usize> PsdCascade<N> {
+    pub fn rbw(&self) -> f32 {
+        let mut r = 0.0;
+        unsafe { check(sspsd_cascade_rbw(self.h, &mut r)) };
+        r
+    }
+    pub fn set_avg(&mut self, avg: AvgOpts) {
+        unsafe { check(sspsd_cascade_set_avg(self.h, CAvgOpts { limit: avg.limit, count: avg.count })) }
+    }
+    pub fn set_detrend(&mut self, d: Detrend) {
+        // Detrend::Linear returns SSPSD_EUNIMPLEMENTED -> panics like unimplemented!() (src/psd.rs:110)
+        unsafe { check(sspsd_cascade_set_detrend(self.h, d as i32)) }
+    }
+    pub fn process(&mut self, x: &[f32]) {
+        unsafe { check(sspsd_cascade_process_f32(self.h, x.as_ptr(), x.len(), 0 /* SSPSD_MEM_HOST */)) }
+    }
+    pub fn psd(&self, opts: &MergeOpts) -> (Vec<f32>, Vec<Break>) {
+        let o = CMergeOpts {
+            keep_overlap: opts.keep_overlap as u32,
+            min_count: opts.min_count,
+            keep_transition_band: opts.keep_transition_band as u32,
+        };
+        let mut p = vec![0f32; 16 * (N / 2 + 1)];
+        let mut b = vec![CBreak::default(); 16];
+        let (mut pl, mut bl) = (p.len(), b.len());
+        unsafe { check(sspsd_cascade_psd(self.h, &o, p.as_mut_ptr(), &mut pl, b.as_mut_ptr(), &mut bl)) };
+        p.truncate(pl);
+        let b = b[..bl]
+            .iter()
+            .map(|c| Break {
+                start: c.start as usize,
+                include: c.include != 0,
+                count: c.count,
+                avg: c.avg,
+                bins: Range { start: c.bins_start as usize, end: c.bins_end as usize },
+                fft_size: c.fft_size as usize,
+                decimation: c.decimation as usize,
+                pending: c.pending as usize,
+                processed: c.processed as usize,
+            })
+            .collect();
+        (p, b)
+    }
+}
+
+/// Batched `Frame::from_bytes` + `Loss::update` + `traces()` feeding one cascade per trace
+/// (src/source.rs:135-148 + src/bin/psd.rs:174-182 in one device pass).
+pub struct FrameDecoder {
+    d: *mut CDecoder,
+}
+unsafe impl Send for FrameDecoder {}
+
+impl FrameDecoder {
+    pub fn new(device: i32) -> Self {
+        let mut d = ptr::null_mut();
+        unsafe { check(sspsd_decoder_create(device, ptr::null_mut(), &mut d)) };
+        Self { d }
+    }
+    /// `frames`: n equally sized frames back to back.  Errors map to `de::Error` by status code
+    /// (5 InvalidHeader, 6 UnknownFormat, 7 PayloadSize; 8/9 are the reference's panics).
+    pub fn process<const N: usize>(&mut self, cascades: &mut [PsdCascade<N>], frames: &[u8], frame_len: usize,
+                                   loss: &mut CLoss) -> Result<DecodeInfo, i32> {
+        let hs: Vec<*mut CCascade> = cascades.iter().map(|c| c.h).collect();
+        let mut info = DecodeInfo::default();
+        let st = unsafe {
+            sspsd_cascade_process_frames(self.d, hs.as_ptr(), hs.len() as u32, frames.as_ptr(), frames.len() / frame_len,
+                                         frame_len, frame_len, 0, loss, &mut info)
+        };
+        if st == 0 { Ok(info) } else { Err(st) }
+    }
+}
+
+impl Drop for FrameDecoder {
+    fn drop(&mut self) {
+        unsafe { sspsd_decoder_destroy(self.d) }
+    }
+}
