@@ -75,7 +75,7 @@ typedef struct {
     int32_t hbf;         /* SSPSD_HBF_* */
     int32_t device;      /* CUDA device ordinal */
     void *stream;        /* cudaStream_t to order all work on, or NULL for a private stream */
-    uint64_t max_batch;  /* largest number of samples handed to one kernel batch (0 = default 1<<26) */
+    uint64_t max_batch;  /* largest number of samples handed to one kernel batch (0 = default 1<<28) */
     uint64_t host_stage; /* host-pointer process() calls are staged in pinned memory and launched once
                             this many samples are pending (0 = default 1<<22); psd()/set_*()/flush() launch
                             whatever is staged */

@@ -244,7 +244,7 @@ int Cascade::init(const sspsd_config& cfg, uint32_t max_stages)
     while ((1u << l2) < n) ++l2;
     log2n_ = l2;
     max_stages_ = std::min<uint32_t>(max_stages, SSPSD_MAX_STAGES);
-    if (cfg_.max_batch == 0) cfg_.max_batch = 1ull << 26;
+    if (cfg_.max_batch == 0) cfg_.max_batch = 1ull << 28;
     if (cfg_.host_stage == 0) cfg_.host_stage = 1ull << 22;
     cfg_.max_batch = std::max<uint64_t>(cfg_.max_batch, 16ull * n);
     cfg_.max_batch = std::min<uint64_t>(cfg_.max_batch, 1ull << 30);

@@ -8,9 +8,12 @@
 // recomputes its own warm-up from that halo (overlap-save), which makes CTAs independent.
 //
 // Per CTA: OB final outputs.  The x tile is de-interleaved into even/odd planes in shared memory
-// (a half-band FIR only touches the odd phase plus one even centre tap), each thread computes 4
-// consecutive outputs from a sliding register window, planes are padded 1 float per 32 so the
-// lane stride of 4 is bank-conflict free.
+// (a half-band FIR only touches the odd phase plus one even centre tap) and each thread computes 4
+// consecutive outputs from a sliding register window.  Lanes therefore read plane elements
+// 4w + c for a common c: planes are stored "polyphase by 4" (element i at (i&3)*S + (i>>2)), which
+// makes every such read unit-stride across lanes for every c (the first version padded 1/32 and
+// measured 38 % conflicting wavefronts, profiles/r01_ncu_summary.md); S = 8 mod 32 keeps the two
+// phases a store instruction touches on disjoint banks.
 #pragma once
 #include "sspsd_device.cuh"
 #include "sspsd_hbf_taps.h"
@@ -31,13 +34,14 @@ struct DecGeom {
     static constexpr int NA = roundup(2 * NB + 4 * MB - 2, 4);      // stage-A outputs
     static constexpr int NX = roundup(2 * NA + 4 * MA - 2, 8);      // input samples loaded
     static constexpr int HALO = NX - 8 * DEC_OB;                    // history needed before the block
-    static constexpr int PX = NX / 2 + NX / 64 + 4;                 // padded plane sizes
-    static constexpr int PA = NA / 2 + NA / 64 + 4;
-    static constexpr int PB = NB / 2 + NB / 64 + 4;
-    static constexpr int SMEM_FLOATS = 2 * (PX + PA + PB);
+    // polyphase-by-4 plane layout: phase stride S = ceil(len/4) rounded up to 8 mod 32
+    static constexpr int phase_stride(int len) { return ((len + 3) / 4 + 23) / 32 * 32 + 8; }
+    static constexpr int SX = phase_stride(NX / 2), SA = phase_stride(NA / 2), SB = phase_stride(NB / 2);
+    static constexpr int SMEM_FLOATS = 2 * 4 * (SX + SA + SB);
 };
 
-__device__ __forceinline__ int pad32(int i) { return i + (i >> 5); }
+template <int S>
+__device__ __forceinline__ int pp4(int i) { return (i & 3) * S + (i >> 2); }
 
 // One half-band stage over de-interleaved, padded planes.
 //   ine/ino : input planes; plane index r <-> input sample in_base + 2r (+1 for the odd plane)
@@ -59,7 +63,7 @@ struct DecimParams {
     int preset;
 };
 
-template <int M, bool FINAL>
+template <int M, int SI, int SO, bool FINAL>
 __device__ __forceinline__ void hbf_stage(const float* __restrict__ ine, const float* __restrict__ ino, int rel0,
                                           int n_out, const float* __restrict__ taps, float* __restrict__ oute,
                                           float* __restrict__ outo, const DecimParams& p, long long out_base,
@@ -70,7 +74,7 @@ __device__ __forceinline__ void hbf_stage(const float* __restrict__ ine, const f
         float win[2 * M + 3];
 #pragma unroll
         for (int i = 0; i < 2 * M + 3; ++i)
-            win[i] = ino[pad32(r0 - 2 * M + 1 + i)];
+            win[i] = ino[pp4<SI>(r0 - 2 * M + 1 + i)];
         float y[4];
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
@@ -78,7 +82,7 @@ __device__ __forceinline__ void hbf_stage(const float* __restrict__ ine, const f
 #pragma unroll
             for (int i = 0; i < M; ++i)
                 acc = fmaf(win[q + i] + win[q + 2 * M - 1 - i], taps[i], acc);
-            y[q] = ine[pad32(r0 + q - M + 1)] + acc;
+            y[q] = ine[pp4<SI>(r0 + q - M + 1)] + acc;
         }
         if constexpr (FINAL) {
 #pragma unroll
@@ -95,10 +99,10 @@ __device__ __forceinline__ void hbf_stage(const float* __restrict__ ine, const f
         } else {
             // out_base is even and 4w is a multiple of 4: q = 0,2 -> even plane, q = 1,3 -> odd plane
             const int pe = 2 * w;
-            oute[pad32(pe)] = y[0];
-            outo[pad32(pe)] = y[1];
-            oute[pad32(pe + 1)] = y[2];
-            outo[pad32(pe + 1)] = y[3];
+            oute[pp4<SO>(pe)] = y[0];
+            outo[pp4<SO>(pe)] = y[1];
+            oute[pp4<SO>(pe + 1)] = y[2];
+            outo[pp4<SO>(pe + 1)] = y[3];
         }
     }
 }
@@ -109,11 +113,11 @@ __global__ void __launch_bounds__(DEC_NT) decim8_kernel(const DecimParams p)
     using GE = DecGeom<MA, MB, MC>;
     extern __shared__ __align__(16) float smem[];
     float* xe = smem;
-    float* xo = xe + GE::PX;
-    float* ae = xo + GE::PX;
-    float* ao = ae + GE::PA;
-    float* be = ao + GE::PA;
-    float* bo = be + GE::PB;
+    float* xo = xe + 4 * GE::SX;
+    float* ae = xo + 4 * GE::SX;
+    float* ao = ae + 4 * GE::SA;
+    float* be = ao + 4 * GE::SA;
+    float* bo = be + 4 * GE::SB;
 
     // blocks are counted down from the top of the range so that every block is full size and only
     // the lowest one is clipped (by the m >= m0 store guard)
@@ -127,22 +131,22 @@ __global__ void __launch_bounds__(DEC_NT) decim8_kernel(const DecimParams p)
     for (int v = threadIdx.x; v < GE::NX / 4; v += DEC_NT) {
         float4 f = ld_stream4(p.src, x_base + 4ll * v);
         int r = 2 * v;
-        xe[pad32(r)] = f.x;
-        xo[pad32(r)] = f.y;
-        xe[pad32(r + 1)] = f.z;
-        xo[pad32(r + 1)] = f.w;
+        xe[pp4<GE::SX>(r)] = f.x;
+        xo[pp4<GE::SX>(r)] = f.y;
+        xe[pp4<GE::SX>(r + 1)] = f.z;
+        xo[pp4<GE::SX>(r + 1)] = f.w;
     }
     __syncthreads();
     const float* tA = c_hbf_taps[p.preset][2];
     const float* tB = c_hbf_taps[p.preset][1];
     const float* tC = c_hbf_taps[p.preset][0];
     // relative index of the first output of each stage: out_base - in_base/2
-    hbf_stage<MA, false>(xe, xo, (int)(a_base - x_base / 2), GE::NA, tA, ae, ao, p, a_base, 0, 0);
+    hbf_stage<MA, GE::SX, GE::SA, false>(xe, xo, (int)(a_base - x_base / 2), GE::NA, tA, ae, ao, p, a_base, 0, 0);
     __syncthreads();
-    hbf_stage<MB, false>(ae, ao, (int)(b_base - a_base / 2), GE::NB, tB, be, bo, p, b_base, 0, 0);
+    hbf_stage<MB, GE::SA, GE::SB, false>(ae, ao, (int)(b_base - a_base / 2), GE::NB, tB, be, bo, p, b_base, 0, 0);
     __syncthreads();
     const long long lo = p.m0 > p.drain ? p.m0 : p.drain;
-    hbf_stage<MC, true>(be, bo, (int)(c_base - b_base / 2), DEC_OB, tC, nullptr, nullptr, p, c_base, lo, mhi);
+    hbf_stage<MC, GE::SB, GE::SB, true>(be, bo, (int)(c_base - b_base / 2), DEC_OB, tC, nullptr, nullptr, p, c_base, lo, mhi);
 }
 
 // ---------------------------------------------------------------------------------------------
