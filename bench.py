@@ -20,9 +20,7 @@ reference cannot be built offline) on the box's host cores.
 import argparse
 import json
 import os
-import subprocess
 import sys
-import tempfile
 import threading
 import time
 
@@ -44,50 +42,55 @@ def peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks + throttle reasons during the timed region (B200_PROFILING.md recipe)."""
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
-         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    """SM clock + throttle reasons sampled DURING the timed region (NVML polled from a thread every
+    ~2 ms; the timed region is tens of milliseconds, too short for `nvidia-smi -lms`)."""
 
     def __init__(self, index):
         self.index = index
-        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
-        self.p = None
+        self.samples = []
+        self.reasons = set()
+        self.max_mhz = None
+        self._stop = threading.Event()
+        self._t = None
+        self._err = None
+
+    def _run(self):
+        try:
+            import pynvml as nv
+            nv.nvmlInit()
+            h = nv.nvmlDeviceGetHandleByIndex(self.index)
+            self.max_mhz = float(nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM))
+            names = {"hw_slowdown": getattr(nv, "nvmlClocksEventReasonHwSlowdown", 0x8),
+                     "hw_thermal_slowdown": getattr(nv, "nvmlClocksEventReasonHwThermalSlowdown", 0x40),
+                     "sw_thermal_slowdown": getattr(nv, "nvmlClocksEventReasonSwThermalSlowdown", 0x20),
+                     "sw_power_cap": getattr(nv, "nvmlClocksEventReasonSwPowerCap", 0x4)}
+            get_reasons = getattr(nv, "nvmlDeviceGetCurrentClocksEventReasons", None) or \
+                nv.nvmlDeviceGetCurrentClocksThrottleReasons
+            while not self._stop.is_set():
+                self.samples.append(float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)))
+                r = get_reasons(h)
+                for k, bit in names.items():
+                    if r & bit:
+                        self.reasons.add(k)
+                time.sleep(0.002)
+            nv.nvmlShutdown()
+        except Exception as e:  # noqa: BLE001
+            self._err = repr(e)
 
     def start(self):
-        try:
-            self.p = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
-                                       "--format=csv,noheader,nounits", "-lms", "100"],
-                                      stdout=self.f, stderr=subprocess.DEVNULL)
-        except OSError:
-            self.p = None
+        self._t = threading.Thread(target=self._run, daemon=True)
+        self._t.start()
+        time.sleep(0.01)
 
     def stop(self):
-        if self.p is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.12)
-        self.p.terminate()
-        self.p.wait()
-        self.f.flush()
-        self.f.seek(0)
-        sm, mx, reasons = [], [], set()
-        for line in self.f.read().splitlines():
-            c = [v.strip() for v in line.split(",")]
-            if len(c) < 9:
-                continue
-            try:
-                sm.append(float(c[1]))
-                mx.append(float(c[2]))
-            except ValueError:
-                continue
-            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), c[5:9]):
-                if v.lower().startswith("active"):
-                    reasons.add(name)
-        os.unlink(self.f.name)
-        if not sm:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
-        sm.sort()
-        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm)}
+        self._stop.set()
+        if self._t is not None:
+            self._t.join(timeout=2.0)
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": ["no samples: %s" % self._err]}
+        sm = sorted(self.samples)
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
+                "samples": len(sm)}
 
 
 def cpu_baseline(seconds_target=12.0, threads=1, n_fft=N_FFT):

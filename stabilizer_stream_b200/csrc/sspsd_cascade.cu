@@ -4,10 +4,12 @@
 
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 
 #include "sspsd_decim_kernel.cuh"
 #include "sspsd_stage_kernel.cuh"
+#include "sspsd_stage_kernel_r16.cuh"
 
 namespace sspsd {
 
@@ -74,8 +76,23 @@ int prepare_stage_t(int hop, int budget_bytes, int* tmax)
 
 #define SSPSD_FOR_SIZES(X) X(6) X(7) X(8) X(9) X(10) X(11) X(12) X(13)
 
+// N = 4096 uses the radix-16 kernel unless SSPSD_K2=r8 is set (A/B switch for profiling)
+bool use_r16()
+{
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("SSPSD_K2");
+        v = (e && std::string(e) == "r8") ? 0 : 1;
+    }
+    return v == 1;
+}
+
 int launch_stage(int log2n, const StageParams& p, int grid, cudaStream_t s)
 {
+    if (log2n == 12 && use_r16()) {
+        psd_stage_kernel_r16<<<grid, R16::NT, stage_r16_smem_bytes(p.T, p.hop), s>>>(p);
+        return cuda_ok(cudaGetLastError(), "psd_stage_kernel_r16 launch") ? SSPSD_OK : SSPSD_ECUDA;
+    }
     switch (log2n) {
 #define X(L) \
     case L:  \
@@ -89,6 +106,15 @@ int launch_stage(int log2n, const StageParams& p, int grid, cudaStream_t s)
 
 int prepare_stage(int log2n, int hop, int* tmax, int* nt)
 {
+    if (log2n == 12 && use_r16()) {
+        int t = 64;
+        while (t > 1 && (long long)stage_r16_smem_bytes(t, hop) > 112 * 1024) --t;
+        *tmax = t;
+        *nt = R16::NT;
+        SSPSD_CUDA(cudaFuncSetAttribute(psd_stage_kernel_r16, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        (int)stage_r16_smem_bytes(t, hop)));
+        return SSPSD_OK;
+    }
     switch (log2n) {
 #define X(L)                                                                   \
     case L:                                                                    \

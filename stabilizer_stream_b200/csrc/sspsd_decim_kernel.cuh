@@ -63,18 +63,21 @@ struct DecimParams {
     int preset;
 };
 
-template <int M, int SI, int SO, bool FINAL>
-__device__ __forceinline__ void hbf_stage(const float* __restrict__ ine, const float* __restrict__ ino, int rel0,
+template <int M, int SI, int SO, int REL0, bool FINAL>
+__device__ __forceinline__ void hbf_stage(const float* __restrict__ ine, const float* __restrict__ ino,
                                           int n_out, const float* __restrict__ taps, float* __restrict__ oute,
                                           float* __restrict__ outo, const DecimParams& p, long long out_base,
                                           long long m0, long long m1)
 {
     for (int w = threadIdx.x; w < n_out / 4; w += DEC_NT) {
-        const int r0 = rel0 + 4 * w;
+        // plane index of window element i is 4w + (REL0 - 2M + 1 + i): its phase and offset are compile
+        // time constants, only `w` is per thread (unit stride across lanes)
         float win[2 * M + 3];
 #pragma unroll
-        for (int i = 0; i < 2 * M + 3; ++i)
-            win[i] = ino[pp4<SI>(r0 - 2 * M + 1 + i)];
+        for (int i = 0; i < 2 * M + 3; ++i) {
+            const int c = REL0 - 2 * M + 1 + i;
+            win[i] = ino[(c & 3) * SI + (c >> 2) + w];
+        }
         float y[4];
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
@@ -82,7 +85,8 @@ __device__ __forceinline__ void hbf_stage(const float* __restrict__ ine, const f
 #pragma unroll
             for (int i = 0; i < M; ++i)
                 acc = fmaf(win[q + i] + win[q + 2 * M - 1 - i], taps[i], acc);
-            y[q] = ine[pp4<SI>(r0 + q - M + 1)] + acc;
+            const int ce = REL0 + q - M + 1;
+            y[q] = ine[(ce & 3) * SI + (ce >> 2) + w] + acc;
         }
         if constexpr (FINAL) {
 #pragma unroll
@@ -140,13 +144,13 @@ __global__ void __launch_bounds__(DEC_NT) decim8_kernel(const DecimParams p)
     const float* tA = c_hbf_taps[p.preset][2];
     const float* tB = c_hbf_taps[p.preset][1];
     const float* tC = c_hbf_taps[p.preset][0];
-    // relative index of the first output of each stage: out_base - in_base/2
-    hbf_stage<MA, GE::SX, GE::SA, false>(xe, xo, (int)(a_base - x_base / 2), GE::NA, tA, ae, ao, p, a_base, 0, 0);
+    // relative index of each stage's first output inside its input planes: out_base - in_base/2
+    hbf_stage<MA, GE::SX, GE::SA, GE::NX / 2 - GE::NA, false>(xe, xo, GE::NA, tA, ae, ao, p, a_base, 0, 0);
     __syncthreads();
-    hbf_stage<MB, GE::SA, GE::SB, false>(ae, ao, (int)(b_base - a_base / 2), GE::NB, tB, be, bo, p, b_base, 0, 0);
+    hbf_stage<MB, GE::SA, GE::SB, GE::NA / 2 - GE::NB, false>(ae, ao, GE::NB, tB, be, bo, p, b_base, 0, 0);
     __syncthreads();
     const long long lo = p.m0 > p.drain ? p.m0 : p.drain;
-    hbf_stage<MC, GE::SB, GE::SB, true>(be, bo, (int)(c_base - b_base / 2), DEC_OB, tC, nullptr, nullptr, p, c_base, lo, mhi);
+    hbf_stage<MC, GE::SB, GE::SB, GE::NB / 2 - DEC_OB, true>(be, bo, DEC_OB, tC, nullptr, nullptr, p, c_base, lo, mhi);
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -204,8 +204,8 @@ class PsdCascade:
 
     def __del__(self):
         h = getattr(self, "_h", None)
-        if h:
-            L.lib().sspsd_cascade_destroy(h)
+        if h and L is not None and getattr(L, "_lib", None) is not None:
+            L._lib.sspsd_cascade_destroy(h)
             self._h = None
 
 
@@ -258,8 +258,8 @@ class Psd:
 
     def __del__(self):
         h = getattr(self, "_h", None)
-        if h:
-            L.lib().sspsd_stage_destroy(h)
+        if h and L is not None and getattr(L, "_lib", None) is not None:
+            L._lib.sspsd_stage_destroy(h)
             self._h = None
 
 
@@ -369,8 +369,8 @@ class FrameDecoder:
 
     def __del__(self):
         h = getattr(self, "_h", None)
-        if h:
-            L.lib().sspsd_decoder_destroy(h)
+        if h and L is not None and getattr(L, "_lib", None) is not None:
+            L._lib.sspsd_decoder_destroy(h)
             self._h = None
 
 
