@@ -10,6 +10,7 @@
 #include "sspsd_decim_kernel.cuh"
 #include "sspsd_stage_kernel.cuh"
 #include "sspsd_stage_kernel_r16.cuh"
+#include "sspsd_stage_kernel_ring.cuh"
 
 namespace sspsd {
 
@@ -76,16 +77,19 @@ int prepare_stage_t(int hop, int budget_bytes, int* tmax)
 
 #define SSPSD_FOR_SIZES(X) X(6) X(7) X(8) X(9) X(10) X(11) X(12) X(13)
 
-// N = 4096 uses the radix-16 kernel unless SSPSD_K2=r8 is set (A/B switch for profiling)
-bool use_r16()
+// K2 variant for N = 4096 (A/B switch for profiling): SSPSD_K2 = r8 | r16 | ring (default ring:
+// persistent TMA-ring kernel for the Hann window, tiled radix-16 kernel for the rectangular one)
+int k2_variant()
 {
     static int v = -1;
     if (v < 0) {
         const char* e = getenv("SSPSD_K2");
-        v = (e && std::string(e) == "r8") ? 0 : 1;
+        std::string m = e ? e : "ring";
+        v = m == "r8" ? 0 : m == "r16" ? 1 : 2;
     }
-    return v == 1;
+    return v;
 }
+bool use_r16() { return k2_variant() >= 1; }
 
 int launch_stage(int log2n, const StageParams& p, int grid, cudaStream_t s)
 {
@@ -113,6 +117,8 @@ int prepare_stage(int log2n, int hop, int* tmax, int* nt)
         *nt = R16::NT;
         SSPSD_CUDA(cudaFuncSetAttribute(psd_stage_kernel_r16, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                         (int)stage_r16_smem_bytes(t, hop)));
+        SSPSD_CUDA(cudaFuncSetAttribute(psd_stage_kernel_ring, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        (int)stage_ring_smem_bytes(RingCfg::MAX_W)));
         return SSPSD_OK;
     }
     switch (log2n) {
@@ -389,6 +395,26 @@ int Cascade::launch_psd(size_t i, const StreamSrc& src, uint64_t k0, uint64_t ns
     p.k0 = (long long)k0;
     p.nseg = (int)nseg;
     long long t = ((long long)nseg + 2ll * num_sms_ - 1) / (2ll * num_sms_);
+    const bool ring = log2n_ == 12 && k2_variant() == 2 && hop_ * 2 == n_;
+    if (ring) {
+        // persistent kernel: two CTAs per SM, each streams through a contiguous range of segments
+        p.T = (int)std::max<long long>(2, std::min<long long>(t, RingCfg::MAX_W));
+        p.hop = (int)hop_;
+        p.detrend = detrend_;
+        p.tile_cap = 0;
+        p.win = d_win_;
+        p.twM = d_twM_;
+        p.twN = d_twN_;
+        p.acc = d_acc_ + i * acc_stride_;
+        p.jb = jb;
+        p.g_first = g_first;
+        p.g_s = g_s;
+        int grid = (int)((nseg + p.T - 1) / p.T);
+        prof_begin(i == 0 ? SSPSD_PROF_PSD_STAGE0 : SSPSD_PROF_PSD_DEEP, nseg * (uint64_t)hop_);
+        psd_stage_kernel_ring<<<grid, R16::NT, stage_ring_smem_bytes(p.T), stream_>>>(p);
+        prof_end();
+        return cuda_ok(cudaGetLastError(), "psd_stage_kernel_ring launch") ? SSPSD_OK : SSPSD_ECUDA;
+    }
     p.T = (int)std::max<long long>(1, std::min<long long>(t, tmax_));
     p.hop = (int)hop_;
     p.detrend = detrend_;
