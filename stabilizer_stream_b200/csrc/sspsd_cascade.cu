@@ -44,7 +44,7 @@ struct DeviceGuard {
     }
 };
 
-inline long long roundup4(long long v) { return (v + 3) & ~3ll; }
+inline long long floor4(long long v) { return v & ~3ll; }
 
 // ---- kernel dispatch over the FFT size ----
 template <int LOG2N>
@@ -163,15 +163,6 @@ int upload_taps_once(int device)
     return SSPSD_OK;
 }
 
-__global__ void set_small_kernel(float* dst, int n, float v0, float v1, float v2)
-{
-    if (threadIdx.x == 0) {
-        if (n > 0) dst[0] = v0;
-        if (n > 1) dst[1] = v1;
-        if (n > 2) dst[2] = v2;
-    }
-}
-
 // EWMA bookkeeping for a batch of S segments, psd.rs:215-225
 struct EwmaPlan {
     int jb;         // first segment of the batch whose factor differs from 1 (>= S: pure boxcar)
@@ -220,11 +211,8 @@ Cascade::~Cascade()
     DeviceGuard g(cfg_.device);
     if (stream_)
         cudaStreamSynchronize(stream_);
-    for (auto& st : stages_) {
-        cudaFree(st.carry[0]);
-        cudaFree(st.carry[1]);
-        cudaFree(st.fresh);
-    }
+    if (deep_stream_) cudaStreamSynchronize(deep_stream_);
+    free_stages();
     cudaFree(d_win_);
     cudaFree(d_twM_);
     cudaFree(d_twN_);
@@ -240,6 +228,9 @@ Cascade::~Cascade()
         if (ev_free_[i]) cudaEventDestroy(ev_free_[i]);
         if (ev_stage_[i]) cudaEventDestroy(ev_stage_[i]);
     }
+    if (ev_stage0_) cudaEventDestroy(ev_stage0_);
+    if (ev_deep_) cudaEventDestroy(ev_deep_);
+    if (deep_stream_) cudaStreamDestroy(deep_stream_);
     if (copy_stream_) cudaStreamDestroy(copy_stream_);
     if (own_stream_ && stream_) cudaStreamDestroy(stream_);
 }
@@ -309,6 +300,11 @@ int Cascade::init(const sspsd_config& cfg, uint32_t max_stages)
         own_stream_ = true;
     }
     SSPSD_CUDA(cudaStreamCreateWithFlags(&copy_stream_, cudaStreamNonBlocking));
+    if (max_stages_ > 1 && !getenv("SSPSD_NO_OVERLAP")) {
+        SSPSD_CUDA(cudaStreamCreateWithFlags(&deep_stream_, cudaStreamNonBlocking));
+        SSPSD_CUDA(cudaEventCreateWithFlags(&ev_stage0_, cudaEventDisableTiming));
+        SSPSD_CUDA(cudaEventCreateWithFlags(&ev_deep_, cudaEventDisableTiming));
+    }
     for (int i = 0; i < 2; ++i) {
         SSPSD_CUDA(cudaEventCreateWithFlags(&ev_copied_[i], cudaEventDisableTiming));
         SSPSD_CUDA(cudaEventCreateWithFlags(&ev_free_[i], cudaEventDisableTiming));
@@ -361,13 +357,15 @@ int Cascade::add_stage()
     StageState st;
     st.avg = single_stage_avg_set_ ? single_stage_avg_ : stage_avg(stages_.size());
     const size_t cap = (size_t)hb_ + n_ + 16;
+    cudaStream_t ss = stage_stream(stages_.size());
     SSPSD_CUDA(cudaMalloc(&st.carry[0], cap * sizeof(float)));
     SSPSD_CUDA(cudaMalloc(&st.carry[1], cap * sizeof(float)));
     // zero history for g < 0: the decimator starts from HbfDec8::default() (psd.rs:141)
-    SSPSD_CUDA(cudaMemsetAsync(st.carry[0], 0, cap * sizeof(float), stream_));
-    SSPSD_CUDA(cudaMemsetAsync(st.carry[1], 0, cap * sizeof(float), stream_));
+    SSPSD_CUDA(cudaMemsetAsync(st.carry[0], 0, cap * sizeof(float), ss));
+    SSPSD_CUDA(cudaMemsetAsync(st.carry[1], 0, cap * sizeof(float), ss));
     st.carry_start = -(long long)hb_;
-    SSPSD_CUDA(cudaMemsetAsync(d_acc_ + stages_.size() * acc_stride_, 0, acc_stride_ * sizeof(float), stream_));
+    SSPSD_CUDA(cudaMemsetAsync(d_acc_ + stages_.size() * acc_stride_, 0, acc_stride_ * sizeof(float), ss));
+    for (int b = 0; b < 2; ++b) SSPSD_CUDA(cudaEventCreateWithFlags(&st.ev_read[b], cudaEventDisableTiming));
     stages_.push_back(st);
     return SSPSD_OK;
 }
@@ -376,14 +374,21 @@ int Cascade::ensure_fresh(StageState& st, size_t need)
 {
     if (need <= st.fresh_cap)
         return SSPSD_OK;
-    // earlier batches may still be reading the old buffer on the stream
-    if (st.fresh) {
-        SSPSD_CUDA(cudaStreamSynchronize(stream_));
-        SSPSD_CUDA(cudaFree(st.fresh));
-        st.fresh = nullptr;
-    }
+    // earlier batches may still be reading the old buffers; the head of fresh[fb] (copies of the carry
+    // tail, written by the previous batch's carry_copy_kernel) has to survive the reallocation
+    SSPSD_CUDA(cudaStreamSynchronize(stream_));
+    if (deep_stream_) SSPSD_CUDA(cudaStreamSynchronize(deep_stream_));
     size_t cap = std::max(need + 64, st.fresh_cap * 2);
-    SSPSD_CUDA(cudaMalloc(&st.fresh, cap * sizeof(float)));
+    for (int b = 0; b < 2; ++b) {
+        float* nb = nullptr;
+        SSPSD_CUDA(cudaMalloc(&nb, cap * sizeof(float)));
+        if (st.fresh[b]) {
+            SSPSD_CUDA(cudaMemcpy(nb, st.fresh[b], 4 * sizeof(float), cudaMemcpyDeviceToDevice));
+            SSPSD_CUDA(cudaFree(st.fresh[b]));
+        }
+        st.fresh[b] = nb;
+        st.ev_read_pending[b] = false;
+    }
     st.fresh_cap = cap;
     return SSPSD_OK;
 }
@@ -410,9 +415,9 @@ int Cascade::launch_psd(size_t i, const StreamSrc& src, uint64_t k0, uint64_t ns
         p.g_first = g_first;
         p.g_s = g_s;
         int grid = (int)((nseg + p.T - 1) / p.T);
-        prof_begin(i == 0 ? SSPSD_PROF_PSD_STAGE0 : SSPSD_PROF_PSD_DEEP, nseg * (uint64_t)hop_);
-        psd_stage_kernel_ring<<<grid, R16::NT, stage_ring_smem_bytes(p.T), stream_>>>(p);
-        prof_end();
+        prof_begin(i == 0 ? SSPSD_PROF_PSD_STAGE0 : SSPSD_PROF_PSD_DEEP, nseg * (uint64_t)hop_, stage_stream(i));
+        psd_stage_kernel_ring<<<grid, R16::NT, stage_ring_smem_bytes(p.T), stage_stream(i)>>>(p);
+        prof_end(stage_stream(i));
         return cuda_ok(cudaGetLastError(), "psd_stage_kernel_ring launch") ? SSPSD_OK : SSPSD_ECUDA;
     }
     p.T = (int)std::max<long long>(1, std::min<long long>(t, tmax_));
@@ -427,14 +432,14 @@ int Cascade::launch_psd(size_t i, const StreamSrc& src, uint64_t k0, uint64_t ns
     p.g_first = g_first;
     p.g_s = g_s;
     int grid = (int)((nseg + p.T - 1) / p.T);
-    prof_begin(i == 0 ? SSPSD_PROF_PSD_STAGE0 : SSPSD_PROF_PSD_DEEP, nseg * (uint64_t)hop_);
-    int rc = launch_stage((int)log2n_, p, grid, stream_);
-    prof_end();
+    prof_begin(i == 0 ? SSPSD_PROF_PSD_STAGE0 : SSPSD_PROF_PSD_DEEP, nseg * (uint64_t)hop_, stage_stream(i));
+    int rc = launch_stage((int)log2n_, p, grid, stage_stream(i));
+    prof_end(stage_stream(i));
     return rc;
 }
 
 int Cascade::launch_decim(size_t i, const StreamSrc& src, uint64_t m0, uint64_t m1, float* out_fresh,
-                          long long out_split, float* out_carry, long long out_carry_start)
+                          long long out_split)
 {
     DecimParams p{};
     p.src = src;
@@ -443,25 +448,26 @@ int Cascade::launch_decim(size_t i, const StreamSrc& src, uint64_t m0, uint64_t 
     p.drain = drain_;
     p.out_fresh = out_fresh;
     p.out_split = out_split;
-    p.out_carry = out_carry;
-    p.out_carry_start = out_carry_start;
     p.preset = cfg_.hbf;
     long long lo = std::max<long long>(p.m0, p.drain);
     if (p.m1 <= lo)
         return SSPSD_OK;
     int grid = (int)((p.m1 - lo + DEC_OB - 1) / DEC_OB);
-    prof_begin(i == 0 ? SSPSD_PROF_DECIM_STAGE0 : SSPSD_PROF_DECIM_DEEP, (uint64_t)(p.m1 - lo) * 8);
-    int rc = cfg_.hbf == SSPSD_HBF_98 ? launch_decim_t<3, 6, 15>(p, grid, stream_)
-                                      : launch_decim_t<5, 10, 23>(p, grid, stream_);
-    prof_end();
+    cudaStream_t ss = stage_stream(i);
+    prof_begin(i == 0 ? SSPSD_PROF_DECIM_STAGE0 : SSPSD_PROF_DECIM_DEEP, (uint64_t)(p.m1 - lo) * 8, ss);
+    int rc = cfg_.hbf == SSPSD_HBF_98 ? launch_decim_t<3, 6, 15>(p, grid, ss) : launch_decim_t<5, 10, 23>(p, grid, ss);
+    prof_end(ss);
     return rc;
 }
 
-// One batch of one stage: n_new samples have been appended to the stage's stream (in `fresh` for
-// g >= split, in the carry sliver for L <= g < split).
+// One batch of one stage: n_new samples have been appended to the stage's stream.  They live in
+// `fresh` from logical index split = floor4(L) on (fresh[0 .. L - split) are copies of the carry tail).
+// Stage 0 runs on stream_, stages >= 1 on deep_stream_ (if enabled) so that they overlap the next
+// batch's stage 0; the only cross-stream hazards are the next stage's two fresh buffers.
 int Cascade::run_stage(size_t i, const float* fresh, long long split, uint64_t n_new)
 {
     StageState& st = stages_[i];
+    cudaStream_t ss = stage_stream(i);
     const uint64_t L1 = st.L + n_new;
     const uint64_t craw0 = st.craw;
     const uint64_t craw1 = L1 < n_ ? 0 : 1 + (L1 - n_) / hop_;
@@ -473,9 +479,9 @@ int Cascade::run_stage(size_t i, const float* fresh, long long split, uint64_t n
         EwmaPlan e = ewma_plan(st.count, st.avg, S);
         if (e.total != 1.0f) {
             int nb = (int)(n_ / 2 + 1);
-            prof_begin(SSPSD_PROF_OTHER, 0);
-            scale_kernel<<<(nb + 255) / 256, 256, 0, stream_>>>(d_acc_ + i * acc_stride_, nb, e.total);
-            prof_end();
+            prof_begin(SSPSD_PROF_OTHER, 0, ss);
+            scale_kernel<<<(nb + 255) / 256, 256, 0, ss>>>(d_acc_ + i * acc_stride_, nb, e.total);
+            prof_end(ss);
             SSPSD_CUDA(cudaGetLastError());
         }
         rc = launch_psd(i, src, craw0, S, e.jb, e.g_first, e.g_s);
@@ -488,6 +494,7 @@ int Cascade::run_stage(size_t i, const float* fresh, long long split, uint64_t n
     const uint64_t D1 = decimated(st);
     uint64_t n_next = 0;
     long long nsplit = 0;
+    const float* nfresh = nullptr;
     if (D1 > D0) {
         const uint64_t m0 = D0 / 8, m1 = D1 / 8;
         const uint64_t em1 = m1 > (uint64_t)drain_ ? m1 - drain_ : 0;
@@ -499,9 +506,10 @@ int Cascade::run_stage(size_t i, const float* fresh, long long split, uint64_t n
                     set_error("internal: sink overflow");
                     return SSPSD_EINVAL;
                 }
-                rc = launch_decim(i, src, m0, m1, d_sink_ + sink_len_, (long long)st.emitted, nullptr, 0);
+                rc = launch_decim(i, src, m0, m1, d_sink_ + sink_len_, (long long)st.emitted);
                 if (rc) return rc;
                 sink_len_ += n_next;
+                st.emitted = em1;
                 n_next = 0;
             } else {
                 if (i + 1 >= stages_.size()) {
@@ -509,34 +517,89 @@ int Cascade::run_stage(size_t i, const float* fresh, long long split, uint64_t n
                     if (rc) return rc;
                 }
                 StageState& nx = stages_[i + 1];
-                nsplit = roundup4((long long)nx.L);
-                if ((long long)em1 > nsplit) {
-                    rc = ensure_fresh(nx, (size_t)((long long)em1 - nsplit));
-                    if (rc) return rc;
-                }
-                rc = launch_decim(i, src, m0, m1, nx.fresh, nsplit, nx.carry[nx.cur], nx.carry_start);
+                nsplit = floor4((long long)nx.L);
+                rc = ensure_fresh(nx, (size_t)((long long)em1 - nsplit));
                 if (rc) return rc;
+                const int b = nx.fb;
+                // the next stage may still be reading this buffer from two batches ago (other stream)
+                if (nx.ev_read_pending[b] && stage_stream(i) != stage_stream(i + 1)) {
+                    SSPSD_CUDA(cudaStreamWaitEvent(ss, nx.ev_read[b], 0));
+                    nx.ev_read_pending[b] = false;
+                }
+                rc = launch_decim(i, src, m0, m1, nx.fresh[b], nsplit);
+                if (rc) return rc;
+                nfresh = nx.fresh[b];
+                stages_[i].emitted = em1;
             }
-            stages_[i].emitted = em1;
         }
     }
 
-    // next batch's carry: history for the decimator + pending samples, [D1 - hb, L1)
+    // next batch's carry: history for the decimator + pending samples, [D1 - hb, L1); the last L1 % 4
+    // samples are also copied to the head of the buffer the next batch's fresh samples will go to
     {
         StageState& s2 = stages_[i];
         const long long cs = (long long)D1 - hb_;
         const int n = (int)((long long)L1 - cs);
-        prof_begin(SSPSD_PROF_OTHER, 0);
-        carry_copy_kernel<<<std::max(1, std::min(64, (n + 255) / 256)), 256, 0, stream_>>>(src, cs, n, s2.carry[s2.cur ^ 1]);
-        prof_end();
+        const int head_n = (int)(L1 & 3);
+        float* head_dst = nullptr;
+        if (head_n) {
+            if (i == 0) {
+                // stage 0: the next batch goes through the staging buffer d_in_[in_buf_] whenever L % 4 != 0
+                rc = ensure_in_buffers(1);
+                if (rc) return rc;
+                head_dst = d_in_[in_buf_];
+            } else {
+                head_dst = s2.fresh[s2.fb ^ 1];
+            }
+        }
+        prof_begin(SSPSD_PROF_OTHER, 0, ss);
+        carry_copy_kernel<<<std::max(1, std::min(64, (n + 255) / 256)), 256, 0, ss>>>(src, cs, n, s2.carry[s2.cur ^ 1],
+                                                                                     head_dst, head_n);
+        prof_end(ss);
         SSPSD_CUDA(cudaGetLastError());
         s2.cur ^= 1;
         s2.carry_start = cs;
         s2.L = L1;
+        if (i > 0) {
+            // this stage is done with fresh[fb]: the previous stage's decimator may reuse it
+            SSPSD_CUDA(cudaEventRecord(s2.ev_read[s2.fb], ss));
+            s2.ev_read_pending[s2.fb] = true;
+            s2.fb ^= 1;
+        }
     }
-    if (n_next > 0)
-        return run_stage(i + 1, stages_[i + 1].fresh, nsplit, n_next);
+    if (n_next > 0) {
+        if (i == 0 && deep_stream_) {
+            // hand over to the deep stream: it may start once stage 0's decimator has written its output
+            SSPSD_CUDA(cudaEventRecord(ev_stage0_, stream_));
+            SSPSD_CUDA(cudaStreamWaitEvent(deep_stream_, ev_stage0_, 0));
+            deep_dirty_ = true;
+        }
+        return run_stage(i + 1, nfresh, nsplit, n_next);
+    }
     return SSPSD_OK;
+}
+
+int Cascade::join_streams()
+{
+    if (deep_stream_ && deep_dirty_) {
+        SSPSD_CUDA(cudaEventRecord(ev_deep_, deep_stream_));
+        SSPSD_CUDA(cudaStreamWaitEvent(stream_, ev_deep_, 0));
+        deep_dirty_ = false;
+    }
+    return SSPSD_OK;
+}
+
+void Cascade::free_stages()
+{
+    for (auto& st : stages_) {
+        cudaFree(st.carry[0]);
+        cudaFree(st.carry[1]);
+        cudaFree(st.fresh[0]);
+        cudaFree(st.fresh[1]);
+        for (int b = 0; b < 2; ++b)
+            if (st.ev_read[b]) cudaEventDestroy(st.ev_read[b]);
+    }
+    stages_.clear();
 }
 
 // x: device memory, valid in stream order
@@ -550,29 +613,31 @@ int Cascade::feed_device_chunk(const float* x, size_t n)
         if (rc) return rc;
     }
     StageState& st = stages_[0];
-    const long long split = roundup4((long long)st.L);
-    const size_t sliver = std::min<size_t>((size_t)(split - (long long)st.L), n);
-    if (sliver)
-        SSPSD_CUDA(cudaMemcpyAsync(st.carry[st.cur] + ((long long)st.L - st.carry_start), x, sliver * sizeof(float),
-                                   cudaMemcpyDeviceToDevice, stream_));
-    const float* fresh = x + sliver;
-    const size_t rest = n - sliver;
-    if (rest && (reinterpret_cast<uintptr_t>(fresh) & 15u)) {
-        // unaligned device input: realign through the staging buffer (one extra device copy)
-        rc = ensure_in_buffers(rest);
-        if (rc) return rc;
-        SSPSD_CUDA(cudaMemcpyAsync(d_in_[in_buf_], fresh, rest * sizeof(float), cudaMemcpyDeviceToDevice, stream_));
-        fresh = d_in_[in_buf_];
-        in_buf_ ^= 1;
-    }
-    return run_stage(0, fresh, split, n);
+    const long long split = floor4((long long)st.L);
+    const size_t head = (size_t)((long long)st.L - split);
+    if (head == 0 && (reinterpret_cast<uintptr_t>(x) & 15u) == 0)
+        return run_stage(0, x, split, n);  // zero copy: the kernels read the caller's buffer in place
+    // unaligned stream position or pointer: realign through the staging buffer (one extra device copy);
+    // its head already holds the carry tail (written by the previous batch's carry_copy_kernel)
+    rc = ensure_in_buffers(n + 4);
+    if (rc) return rc;
+    float* buf = d_in_[in_buf_];
+    SSPSD_CUDA(cudaMemcpyAsync(buf + head, x, n * sizeof(float), cudaMemcpyDeviceToDevice, stream_));
+    in_buf_ ^= 1;
+    return run_stage(0, buf, split, n);
 }
 
 int Cascade::process_device(const float* x, size_t n)
 {
+    // chunks of at most max_batch; inputs above 2^26 samples are cut into >= 2 roughly equal chunks so
+    // that the deep stages of chunk c (deep_stream_) overlap stage 0 of chunk c+1 (stream_)
+    size_t nchunks = (n + cfg_.max_batch - 1) / cfg_.max_batch;
+    if (deep_stream_ && n > (1ull << 26)) nchunks = std::max<size_t>(nchunks, (n + (1ull << 26) - 1) >> 26);
+    size_t per = (n + nchunks - 1) / nchunks;
+    per = (per + 4095) & ~(size_t)4095;  // keep chunk boundaries 16-byte aligned relative to x
     size_t pos = 0;
     while (pos < n) {
-        size_t c = std::min<size_t>(n - pos, cfg_.max_batch);
+        size_t c = std::min<size_t>(n - pos, per);
         int rc = feed_device_chunk(x + pos, c);
         if (rc) return rc;
         pos += c;
@@ -586,13 +651,16 @@ int Cascade::ensure_in_buffers(size_t need)
         return SSPSD_OK;
     SSPSD_CUDA(cudaStreamSynchronize(stream_));
     SSPSD_CUDA(cudaStreamSynchronize(copy_stream_));
-    for (int i = 0; i < 2; ++i) {
-        if (d_in_[i]) SSPSD_CUDA(cudaFree(d_in_[i]));
-        d_in_[i] = nullptr;
-    }
     size_t cap = need + 64;
-    for (int i = 0; i < 2; ++i)
-        SSPSD_CUDA(cudaMalloc(&d_in_[i], cap * sizeof(float)));
+    for (int i = 0; i < 2; ++i) {
+        float* nb = nullptr;
+        SSPSD_CUDA(cudaMalloc(&nb, cap * sizeof(float)));
+        if (d_in_[i]) {
+            SSPSD_CUDA(cudaMemcpy(nb, d_in_[i], 4 * sizeof(float), cudaMemcpyDeviceToDevice));  // keep the head
+            SSPSD_CUDA(cudaFree(d_in_[i]));
+        }
+        d_in_[i] = nb;
+    }
     d_in_cap_ = cap;
     return SSPSD_OK;
 }
@@ -607,36 +675,23 @@ int Cascade::feed_host_chunk(const float* xh, size_t n)
         rc = add_stage();
         if (rc) return rc;
     }
-    rc = ensure_in_buffers(std::min<uint64_t>(std::max<uint64_t>(n, host_chunk()), cfg_.max_batch));
+    rc = ensure_in_buffers(std::min<uint64_t>(std::max<uint64_t>(n, host_chunk()), cfg_.max_batch) + 4);
     if (rc) return rc;
     StageState& st = stages_[0];
-    const long long split = roundup4((long long)st.L);
-    const size_t sliver = std::min<size_t>((size_t)(split - (long long)st.L), n);
-    if (sliver) {
-        // <= 3 samples complete the carry's last float4 group; passed by value, no host lifetime issue
-        float v[3] = {0.f, 0.f, 0.f};
-        for (size_t q = 0; q < sliver; ++q) v[q] = xh[q];
-        prof_begin(SSPSD_PROF_OTHER, 0);
-        set_small_kernel<<<1, 32, 0, stream_>>>(st.carry[st.cur] + ((long long)st.L - st.carry_start), (int)sliver,
-                                                v[0], v[1], v[2]);
-        prof_end();
-        SSPSD_CUDA(cudaGetLastError());
-    }
-    const size_t rest = n - sliver;
+    const long long split = floor4((long long)st.L);
+    const size_t head = (size_t)((long long)st.L - split);
     const int b = in_buf_;
-    if (rest) {
-        SSPSD_CUDA(cudaStreamWaitEvent(copy_stream_, ev_free_[b], 0));
-        SSPSD_CUDA(cudaMemcpyAsync(d_in_[b], xh + sliver, rest * sizeof(float), cudaMemcpyHostToDevice, copy_stream_));
-        SSPSD_CUDA(cudaEventRecord(ev_copied_[b], copy_stream_));
-        SSPSD_CUDA(cudaStreamWaitEvent(stream_, ev_copied_[b], 0));
-        last_copy_ = b;
-    }
+    // d_in_[b][0 .. head) already holds the carry tail (previous batch's carry_copy_kernel on stream_);
+    // the copy below touches only [head, head + n)
+    SSPSD_CUDA(cudaStreamWaitEvent(copy_stream_, ev_free_[b], 0));
+    SSPSD_CUDA(cudaMemcpyAsync(d_in_[b] + head, xh, n * sizeof(float), cudaMemcpyHostToDevice, copy_stream_));
+    SSPSD_CUDA(cudaEventRecord(ev_copied_[b], copy_stream_));
+    SSPSD_CUDA(cudaStreamWaitEvent(stream_, ev_copied_[b], 0));
+    last_copy_ = b;
+    in_buf_ ^= 1;
     rc = run_stage(0, d_in_[b], split, n);
     if (rc) return rc;
-    if (rest) {
-        SSPSD_CUDA(cudaEventRecord(ev_free_[b], stream_));
-        in_buf_ ^= 1;
-    }
+    SSPSD_CUDA(cudaEventRecord(ev_free_[b], stream_));
     return SSPSD_OK;
 }
 
@@ -763,6 +818,8 @@ int Cascade::sync()
     if (!g.ok) return SSPSD_ECUDA;
     int rc = flush_staged();
     if (rc) return rc;
+    rc = join_streams();
+    if (rc) return rc;
     SSPSD_CUDA(cudaStreamSynchronize(stream_));
     return SSPSD_OK;
 }
@@ -811,12 +868,9 @@ int Cascade::reset()
     if (!g.ok) return SSPSD_ECUDA;
     SSPSD_CUDA(cudaStreamSynchronize(stream_));
     SSPSD_CUDA(cudaStreamSynchronize(copy_stream_));
-    for (auto& st : stages_) {
-        cudaFree(st.carry[0]);
-        cudaFree(st.carry[1]);
-        cudaFree(st.fresh);
-    }
-    stages_.clear();
+    if (deep_stream_) SSPSD_CUDA(cudaStreamSynchronize(deep_stream_));
+    free_stages();
+    deep_dirty_ = false;
     staged_ = 0;
     sink_len_ = 0;
     SSPSD_CUDA(cudaMemsetAsync(d_acc_, 0, (size_t)SSPSD_MAX_STAGES * acc_stride_ * sizeof(float), stream_));
@@ -849,10 +903,23 @@ int Cascade::clone_from(Cascade& o)
         d.cur = 0;
         const size_t cap = (size_t)hb_ + n_ + 16;
         SSPSD_CUDA(cudaMemcpyAsync(d.carry[0], s.carry[s.cur], cap * sizeof(float), cudaMemcpyDeviceToDevice, stream_));
+        if (i > 0 && s.fresh[s.fb]) {
+            // the head of the next incoming fresh buffer (copies of the carry tail) is stream state too
+            int rc2 = ensure_fresh(d, 8);
+            if (rc2) return rc2;
+            d.fb = 0;
+            SSPSD_CUDA(cudaMemcpyAsync(d.fresh[0], s.fresh[s.fb], 4 * sizeof(float), cudaMemcpyDeviceToDevice, stream_));
+        }
+    }
+    if (o.d_in_[o.in_buf_]) {
+        int rc2 = ensure_in_buffers(8);
+        if (rc2) return rc2;
+        SSPSD_CUDA(cudaMemcpyAsync(d_in_[in_buf_], o.d_in_[o.in_buf_], 4 * sizeof(float), cudaMemcpyDeviceToDevice, stream_));
     }
     SSPSD_CUDA(cudaMemcpyAsync(d_acc_, o.d_acc_, (size_t)SSPSD_MAX_STAGES * acc_stride_ * sizeof(float),
                                cudaMemcpyDeviceToDevice, stream_));
     SSPSD_CUDA(cudaStreamSynchronize(stream_));
+    if (deep_stream_) SSPSD_CUDA(cudaStreamSynchronize(deep_stream_));
     return SSPSD_OK;
 }
 
@@ -937,20 +1004,20 @@ int Cascade::psd(const sspsd_merge_opts& o, float* p, size_t* p_len, sspsd_break
     return SSPSD_OK;
 }
 
-void Cascade::prof_begin(int cls, uint64_t units)
+void Cascade::prof_begin(int cls, uint64_t units, cudaStream_t s)
 {
     launches_[cls]++;
     if (!prof_on_) return;
     ProfRec r{cls, nullptr, nullptr, units};
     if (cudaEventCreate(&r.a) != cudaSuccess || cudaEventCreate(&r.b) != cudaSuccess) return;
-    cudaEventRecord(r.a, stream_);
+    cudaEventRecord(r.a, s);
     prof_.push_back(r);
 }
 
-void Cascade::prof_end()
+void Cascade::prof_end(cudaStream_t s)
 {
     if (!prof_on_ || prof_.empty()) return;
-    cudaEventRecord(prof_.back().b, stream_);
+    cudaEventRecord(prof_.back().b, s);
 }
 
 int Cascade::profile_read(sspsd_profile* out)
@@ -958,6 +1025,8 @@ int Cascade::profile_read(sspsd_profile* out)
     if (!out) return SSPSD_EINVAL;
     DeviceGuard g(cfg_.device);
     if (!g.ok) return SSPSD_ECUDA;
+    int rcj = join_streams();
+    if (rcj) return rcj;
     SSPSD_CUDA(cudaStreamSynchronize(stream_));
     std::memset(out, 0, sizeof(*out));
     for (auto& r : prof_) {

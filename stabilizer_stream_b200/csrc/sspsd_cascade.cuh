@@ -36,12 +36,17 @@ struct StageState {
     uint32_t count = 0;   // effective averaging count (Psd::count, psd.rs:128)
     uint32_t avg = 0xffffffffu;
     uint64_t emitted = 0; // samples handed to the next stage
-    // device stream storage: carry[cur] holds [carry_start, split) with split = roundup4(L)
+    // device stream storage: carry[cur] holds [carry_start, L); the batch's new samples live in a
+    // "fresh" buffer from split = floor4(L) on (its first L - split entries are copies of the carry tail)
     float* carry[2] = {nullptr, nullptr};
     int cur = 0;
     long long carry_start = 0;
-    float* fresh = nullptr; // written by the previous stage's decimator (stages >= 1)
+    // stages >= 1: two fresh buffers written alternately by the previous stage's decimator
+    float* fresh[2] = {nullptr, nullptr};
+    int fb = 0;  // buffer the next incoming batch is written to
     size_t fresh_cap = 0;
+    cudaEvent_t ev_read[2] = {nullptr, nullptr};  // recorded when this stage has finished reading fresh[b]
+    bool ev_read_pending[2] = {false, false};
 };
 
 class Cascade {
@@ -81,10 +86,13 @@ public:
 
 private:
     int add_stage();
+    void free_stages();
     int run_stage(size_t i, const float* fresh, long long split, uint64_t n_new);
     int launch_psd(size_t i, const StreamSrc& src, uint64_t k0, uint64_t nseg, int jb, float g_first, float g_s);
     int launch_decim(size_t i, const StreamSrc& src, uint64_t m0, uint64_t m1, float* out_fresh,
-                     long long out_split, float* out_carry, long long out_carry_start);
+                     long long out_split);
+    cudaStream_t stage_stream(size_t i) const { return (i == 0 || !deep_stream_) ? stream_ : deep_stream_; }
+    int join_streams();  // make stream_ wait for everything queued on deep_stream_
     int ensure_fresh(StageState& st, size_t need);
     int ensure_in_buffers(size_t need);
     int process_host(const float* x, size_t n);
@@ -104,8 +112,8 @@ private:
     bool prof_on_ = false;
     std::vector<ProfRec> prof_;
     uint64_t launches_[SSPSD_PROF_NCLASS] = {0, 0, 0, 0, 0};
-    void prof_begin(int cls, uint64_t units);
-    void prof_end();
+    void prof_begin(int cls, uint64_t units, cudaStream_t s);
+    void prof_end(cudaStream_t s);
 
     sspsd_config cfg_{};
     uint32_t n_ = 0, log2n_ = 0, hop_ = 0, max_stages_ = SSPSD_MAX_STAGES;
@@ -121,6 +129,9 @@ private:
     cudaStream_t stream_ = nullptr;
     bool own_stream_ = false;
     cudaStream_t copy_stream_ = nullptr;
+    cudaStream_t deep_stream_ = nullptr;  // stages >= 1 run here, overlapping the next batch's stage 0
+    cudaEvent_t ev_stage0_ = nullptr, ev_deep_ = nullptr;
+    bool deep_dirty_ = false;
     cudaEvent_t ev_copied_[2] = {nullptr, nullptr}, ev_free_[2] = {nullptr, nullptr};
     cudaEvent_t ev_stage_[2] = {nullptr, nullptr};
     int last_copy_ = -1;

@@ -54,12 +54,10 @@ struct DecimParams {
     StreamSrc src;
     long long m0, m1;  // outputs m in [m0, m1) are produced by this launch (m = chunk index of 8 inputs)
     long long drain;   // outputs m < drain are discarded (psd.rs:254-260)
-    // output m is sample g = m - drain of the next stage's stream: it goes to out_fresh[g - out_split]
-    // for g >= out_split, else to the tail of the next stage's carry, out_carry[g - out_carry_start]
+    // output m is sample g = m - drain of the next stage's stream; it is stored at
+    // out_fresh[g - out_split] (out_split = floor4 of the next stage's sample count, so g >= out_split)
     float* out_fresh;
     long long out_split;
-    float* out_carry;
-    long long out_carry_start;
     int preset;
 };
 
@@ -93,11 +91,7 @@ __device__ __forceinline__ void hbf_stage(const float* __restrict__ ine, const f
             for (int q = 0; q < 4; ++q) {
                 long long m = out_base + 4 * w + q;
                 if (m >= m0 && m < m1) {
-                    long long g = m - p.drain;
-                    if (g >= p.out_split)
-                        p.out_fresh[g - p.out_split] = y[q];
-                    else
-                        p.out_carry[g - p.out_carry_start] = y[q];
+                    p.out_fresh[m - p.drain - p.out_split] = y[q];
                 }
             }
         } else {
@@ -156,11 +150,18 @@ __global__ void __launch_bounds__(DEC_NT) decim8_kernel(const DecimParams p)
 // ---------------------------------------------------------------------------------------------
 // small helpers
 // ---------------------------------------------------------------------------------------------
-// dst[i] = stream[g0 + i], i < n  (builds the next batch's carry buffer)
-__global__ void carry_copy_kernel(StreamSrc src, long long g0, int n, float* __restrict__ dst)
+// dst[i] = stream[g0 + i], i < n  (builds the next batch's carry buffer = [g0, L)); additionally the
+// last `head_n` (< 4) samples, [L - head_n, L), are written to the head of the buffer the NEXT batch's
+// fresh samples go to, so that buffer is valid from floor4(L) on and aligned 128-bit loads never have
+// to straddle the carry/fresh boundary.
+__global__ void carry_copy_kernel(StreamSrc src, long long g0, int n, float* __restrict__ dst,
+                                  float* __restrict__ head_dst, int head_n)
 {
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
-        dst[i] = ld_stream1(src, g0 + i);
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        float v = ld_stream1(src, g0 + i);
+        dst[i] = v;
+        if (i >= n - head_n) head_dst[i - (n - head_n)] = v;
+    }
 }
 
 // acc[i] *= s (EWMA rescale of the running average before a batch, psd.rs:218-232)
