@@ -301,7 +301,10 @@ int Cascade::init(const sspsd_config& cfg, uint32_t max_stages)
     }
     SSPSD_CUDA(cudaStreamCreateWithFlags(&copy_stream_, cudaStreamNonBlocking));
     if (max_stages_ > 1 && !getenv("SSPSD_NO_OVERLAP")) {
-        SSPSD_CUDA(cudaStreamCreateWithFlags(&deep_stream_, cudaStreamNonBlocking));
+        // high priority: the small deep-stage grids should be scheduled ahead of the remaining stage-0 CTAs
+        int lo_prio = 0, hi_prio = 0;
+        SSPSD_CUDA(cudaDeviceGetStreamPriorityRange(&lo_prio, &hi_prio));
+        SSPSD_CUDA(cudaStreamCreateWithPriority(&deep_stream_, cudaStreamNonBlocking, hi_prio));
         SSPSD_CUDA(cudaEventCreateWithFlags(&ev_stage0_, cudaEventDisableTiming));
         SSPSD_CUDA(cudaEventCreateWithFlags(&ev_deep_, cudaEventDisableTiming));
     }
@@ -403,6 +406,9 @@ int Cascade::launch_psd(size_t i, const StreamSrc& src, uint64_t k0, uint64_t ns
     const bool ring = log2n_ == 12 && k2_variant() == 2 && hop_ * 2 == n_;
     if (ring) {
         // persistent kernel: two CTAs per SM, each streams through a contiguous range of segments
+        // with the deep stages overlapping on a second stream, stage 0 is cut into ~4 waves of CTAs so
+        // that SM slots free up for them while it runs (a fully persistent grid would hold every slot)
+        if (i == 0 && deep_stream_) t = (t + 3) / 4;
         p.T = (int)std::max<long long>(2, std::min<long long>(t, RingCfg::MAX_W));
         p.hop = (int)hop_;
         p.detrend = detrend_;
@@ -621,10 +627,15 @@ int Cascade::feed_device_chunk(const float* x, size_t n)
     // its head already holds the carry tail (written by the previous batch's carry_copy_kernel)
     rc = ensure_in_buffers(n + 4);
     if (rc) return rc;
-    float* buf = d_in_[in_buf_];
+    const int b = in_buf_;
+    float* buf = d_in_[b];
     SSPSD_CUDA(cudaMemcpyAsync(buf + head, x, n * sizeof(float), cudaMemcpyDeviceToDevice, stream_));
     in_buf_ ^= 1;
-    return run_stage(0, buf, split, n);
+    rc = run_stage(0, buf, split, n);
+    if (rc) return rc;
+    // a later host-pointer call refills this buffer from the copy stream: it must wait for these kernels
+    SSPSD_CUDA(cudaEventRecord(ev_free_[b], stream_));
+    return SSPSD_OK;
 }
 
 int Cascade::process_device(const float* x, size_t n)
