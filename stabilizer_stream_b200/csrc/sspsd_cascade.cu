@@ -300,7 +300,10 @@ int Cascade::init(const sspsd_config& cfg, uint32_t max_stages)
         own_stream_ = true;
     }
     SSPSD_CUDA(cudaStreamCreateWithFlags(&copy_stream_, cudaStreamNonBlocking));
-    if (max_stages_ > 1 && !getenv("SSPSD_NO_OVERLAP")) {
+    // Optional second stream for stages >= 1 (SSPSD_OVERLAP=1).  Off by default: the persistent stage-0
+    // kernel holds every SM slot, so on one stream of large batches the overlap measured slower
+    // (146 vs 164 GS/s, profiles/r01_ncu_summary.md); it pays for many small concurrent batches only.
+    if (max_stages_ > 1 && getenv("SSPSD_OVERLAP")) {
         // high priority: the small deep-stage grids should be scheduled ahead of the remaining stage-0 CTAs
         int lo_prio = 0, hi_prio = 0;
         SSPSD_CUDA(cudaDeviceGetStreamPriorityRange(&lo_prio, &hi_prio));

@@ -22,7 +22,7 @@ namespace sspsd {
 
 __constant__ float c_hbf_taps[SSPSD_HBF_NPRESET][3][SSPSD_HBF_MAXTAPS];
 
-constexpr int DEC_OB = 512;  // outputs per CTA
+constexpr int DEC_OB = 1024;  // outputs per CTA (8192 input samples + 472 of halo)
 constexpr int DEC_NT = 256;
 
 constexpr int roundup(int v, int m) { return (v + m - 1) / m * m; }
@@ -64,8 +64,7 @@ struct DecimParams {
 template <int M, int SI, int SO, int REL0, bool FINAL>
 __device__ __forceinline__ void hbf_stage(const float* __restrict__ ine, const float* __restrict__ ino,
                                           int n_out, const float* __restrict__ taps, float* __restrict__ oute,
-                                          float* __restrict__ outo, const DecimParams& p, long long out_base,
-                                          long long m0, long long m1)
+                                          float* __restrict__ outo, float* __restrict__ gout, int rel_lo, int rel_hi)
 {
     for (int w = threadIdx.x; w < n_out / 4; w += DEC_NT) {
         // plane index of window element i is 4w + (REL0 - 2M + 1 + i): its phase and offset are compile
@@ -87,12 +86,11 @@ __device__ __forceinline__ void hbf_stage(const float* __restrict__ ine, const f
             y[q] = ine[(ce & 3) * SI + (ce >> 2) + w] + acc;
         }
         if constexpr (FINAL) {
+            // gout points at the block's first output; only [rel_lo, rel_hi) of the block is stored
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
-                long long m = out_base + 4 * w + q;
-                if (m >= m0 && m < m1) {
-                    p.out_fresh[m - p.drain - p.out_split] = y[q];
-                }
+                const int r = 4 * w + q;
+                if (r >= rel_lo && r < rel_hi) gout[r] = y[q];
             }
         } else {
             // out_base is even and 4w is a multiple of 4: q = 0,2 -> even plane, q = 1,3 -> odd plane
@@ -121,30 +119,60 @@ __global__ void __launch_bounds__(DEC_NT) decim8_kernel(const DecimParams p)
     // the lowest one is clipped (by the m >= m0 store guard)
     const long long mhi = p.m1 - (long long)blockIdx.x * DEC_OB;
     const long long x_base = 8 * mhi - GE::NX;          // multiple of 8
-    const long long a_base = 4 * mhi - GE::NA;          // first stage-A output index (even)
-    const long long b_base = 2 * mhi - GE::NB;          // first stage-B output index (even)
     const long long c_base = mhi - DEC_OB;
 
-    // ---- load + de-interleave ----
-    for (int v = threadIdx.x; v < GE::NX / 4; v += DEC_NT) {
-        float4 f = ld_stream4(p.src, x_base + 4ll * v);
-        int r = 2 * v;
-        xe[pp4<GE::SX>(r)] = f.x;
-        xo[pp4<GE::SX>(r)] = f.y;
-        xe[pp4<GE::SX>(r + 1)] = f.z;
-        xo[pp4<GE::SX>(r + 1)] = f.w;
+    // ---- load + de-interleave into the polyphase planes: x[x_base + 4v .. +3] = (e, o, e, o) ----
+    // plane index r = 2v (+1): phase (r & 3) = 2 (v & 1) (+1), offset r >> 2 = v >> 1
+    if (x_base >= p.src.split) {
+        // whole block inside the fresh buffer (all but the first block of a batch): straight 128-bit loads
+        const float4* __restrict__ gx = reinterpret_cast<const float4*>(p.src.fresh + (x_base - p.src.split));
+        constexpr int NV = GE::NX / 4;
+#pragma unroll 2
+        for (int v0 = 0; v0 < NV; v0 += 4 * DEC_NT) {
+            float4 f[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int v = v0 + u * DEC_NT + threadIdx.x;
+                if (v < NV) f[u] = __ldg(gx + v);
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int v = v0 + u * DEC_NT + threadIdx.x;
+                if (v < NV) {
+                    const int pos = 2 * (v & 1) * GE::SX + (v >> 1);
+                    xe[pos] = f[u].x;
+                    xo[pos] = f[u].y;
+                    xe[pos + GE::SX] = f[u].z;
+                    xo[pos + GE::SX] = f[u].w;
+                }
+            }
+        }
+    } else {
+        for (int v = threadIdx.x; v < GE::NX / 4; v += DEC_NT) {
+            float4 f = ld_stream4(p.src, x_base + 4ll * v);
+            const int pos = 2 * (v & 1) * GE::SX + (v >> 1);
+            xe[pos] = f.x;
+            xo[pos] = f.y;
+            xe[pos + GE::SX] = f.z;
+            xo[pos + GE::SX] = f.w;
+        }
     }
     __syncthreads();
     const float* tA = c_hbf_taps[p.preset][2];
     const float* tB = c_hbf_taps[p.preset][1];
     const float* tC = c_hbf_taps[p.preset][0];
-    // relative index of each stage's first output inside its input planes: out_base - in_base/2
-    hbf_stage<MA, GE::SX, GE::SA, GE::NX / 2 - GE::NA, false>(xe, xo, GE::NA, tA, ae, ao, p, a_base, 0, 0);
+    // REL0 = relative index of each stage's first output inside its input planes: out_base - in_base/2
+    hbf_stage<MA, GE::SX, GE::SA, GE::NX / 2 - GE::NA, false>(xe, xo, GE::NA, tA, ae, ao, nullptr, 0, 0);
     __syncthreads();
-    hbf_stage<MB, GE::SA, GE::SB, GE::NA / 2 - GE::NB, false>(ae, ao, GE::NB, tB, be, bo, p, b_base, 0, 0);
+    hbf_stage<MB, GE::SA, GE::SB, GE::NA / 2 - GE::NB, false>(ae, ao, GE::NB, tB, be, bo, nullptr, 0, 0);
     __syncthreads();
+    // outputs m in [max(m0, drain), mhi) of this block [c_base, mhi); output m is sample m - drain of the
+    // next stage's stream, stored at out_fresh[m - drain - out_split]
     const long long lo = p.m0 > p.drain ? p.m0 : p.drain;
-    hbf_stage<MC, GE::SB, GE::SB, GE::NB / 2 - DEC_OB, true>(be, bo, DEC_OB, tC, nullptr, nullptr, p, c_base, lo, mhi);
+    const int rel_lo = lo > c_base ? (int)(lo - c_base) : 0;
+    hbf_stage<MC, GE::SB, GE::SB, GE::NB / 2 - DEC_OB, true>(be, bo, DEC_OB, tC, nullptr, nullptr,
+                                                            p.out_fresh + (c_base - p.drain - p.out_split), rel_lo,
+                                                            DEC_OB);
 }
 
 // ---------------------------------------------------------------------------------------------
