@@ -134,11 +134,11 @@ int prepare_stage(int log2n, int hop, int* tmax, int* nt)
     }
 }
 
-template <int MA, int MB, int MC>
+template <int MA, int MB, int MC, int PRESET>
 int launch_decim_t(const DecimParams& p, int grid, cudaStream_t s)
 {
     using GE = DecGeom<MA, MB, MC>;
-    decim8_kernel<MA, MB, MC><<<grid, DEC_NT, GE::SMEM_FLOATS * sizeof(float), s>>>(p);
+    decim8_kernel<MA, MB, MC, PRESET><<<grid, DEC_NT, GE::SMEM_FLOATS * sizeof(float), s>>>(p);
     return cuda_ok(cudaGetLastError(), "decim8_kernel launch") ? SSPSD_OK : SSPSD_ECUDA;
 }
 
@@ -154,9 +154,9 @@ int upload_taps_once(int device)
         return SSPSD_OK;
     static_assert(sizeof(sspsd_hbf_taps) == sizeof(float) * SSPSD_HBF_NPRESET * 3 * SSPSD_HBF_MAXTAPS, "tap table");
     SSPSD_CUDA(cudaMemcpyToSymbol(c_hbf_taps, sspsd_hbf_taps, sizeof(sspsd_hbf_taps)));
-    SSPSD_CUDA(cudaFuncSetAttribute(decim8_kernel<5, 10, 23>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    SSPSD_CUDA(cudaFuncSetAttribute(decim8_kernel<5, 10, 23, SSPSD_HBF_140>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                     (int)(DecGeom<5, 10, 23>::SMEM_FLOATS * sizeof(float))));
-    SSPSD_CUDA(cudaFuncSetAttribute(decim8_kernel<3, 6, 15>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    SSPSD_CUDA(cudaFuncSetAttribute(decim8_kernel<3, 6, 15, SSPSD_HBF_98>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                     (int)(DecGeom<3, 6, 15>::SMEM_FLOATS * sizeof(float))));
     if (device < 64)
         done[device] = true;
@@ -464,7 +464,8 @@ int Cascade::launch_decim(size_t i, const StreamSrc& src, uint64_t m0, uint64_t 
     int grid = (int)((p.m1 - lo + DEC_OB - 1) / DEC_OB);
     cudaStream_t ss = stage_stream(i);
     prof_begin(i == 0 ? SSPSD_PROF_DECIM_STAGE0 : SSPSD_PROF_DECIM_DEEP, (uint64_t)(p.m1 - lo) * 8, ss);
-    int rc = cfg_.hbf == SSPSD_HBF_98 ? launch_decim_t<3, 6, 15>(p, grid, ss) : launch_decim_t<5, 10, 23>(p, grid, ss);
+    int rc = cfg_.hbf == SSPSD_HBF_98 ? launch_decim_t<3, 6, 15, SSPSD_HBF_98>(p, grid, ss)
+                                      : launch_decim_t<5, 10, 23, SSPSD_HBF_140>(p, grid, ss);
     prof_end(ss);
     return rc;
 }

@@ -61,9 +61,9 @@ struct DecimParams {
     int preset;
 };
 
-template <int M, int SI, int SO, int REL0, bool FINAL>
+template <int M, int SI, int SO, int REL0, bool FINAL, int PRESET, int SET>
 __device__ __forceinline__ void hbf_stage(const float* __restrict__ ine, const float* __restrict__ ino,
-                                          int n_out, const float* __restrict__ taps, float* __restrict__ oute,
+                                          int n_out, float* __restrict__ oute,
                                           float* __restrict__ outo, float* __restrict__ gout, int rel_lo, int rel_hi)
 {
     for (int w = threadIdx.x; w < n_out / 4; w += DEC_NT) {
@@ -81,7 +81,7 @@ __device__ __forceinline__ void hbf_stage(const float* __restrict__ ine, const f
             float acc = 0.f;
 #pragma unroll
             for (int i = 0; i < M; ++i)
-                acc = fmaf(win[q + i] + win[q + 2 * M - 1 - i], taps[i], acc);
+                acc = fmaf(win[q + i] + win[q + 2 * M - 1 - i], c_hbf_taps[PRESET][SET][i], acc);
             const int ce = REL0 + q - M + 1;
             y[q] = ine[(ce & 3) * SI + (ce >> 2) + w] + acc;
         }
@@ -103,7 +103,7 @@ __device__ __forceinline__ void hbf_stage(const float* __restrict__ ine, const f
     }
 }
 
-template <int MA, int MB, int MC>
+template <int MA, int MB, int MC, int PRESET>
 __global__ void __launch_bounds__(DEC_NT) decim8_kernel(const DecimParams p)
 {
     using GE = DecGeom<MA, MB, MC>;
@@ -158,19 +158,16 @@ __global__ void __launch_bounds__(DEC_NT) decim8_kernel(const DecimParams p)
         }
     }
     __syncthreads();
-    const float* tA = c_hbf_taps[p.preset][2];
-    const float* tB = c_hbf_taps[p.preset][1];
-    const float* tC = c_hbf_taps[p.preset][0];
     // REL0 = relative index of each stage's first output inside its input planes: out_base - in_base/2
-    hbf_stage<MA, GE::SX, GE::SA, GE::NX / 2 - GE::NA, false>(xe, xo, GE::NA, tA, ae, ao, nullptr, 0, 0);
+    hbf_stage<MA, GE::SX, GE::SA, GE::NX / 2 - GE::NA, false, PRESET, 2>(xe, xo, GE::NA, ae, ao, nullptr, 0, 0);
     __syncthreads();
-    hbf_stage<MB, GE::SA, GE::SB, GE::NA / 2 - GE::NB, false>(ae, ao, GE::NB, tB, be, bo, nullptr, 0, 0);
+    hbf_stage<MB, GE::SA, GE::SB, GE::NA / 2 - GE::NB, false, PRESET, 1>(ae, ao, GE::NB, be, bo, nullptr, 0, 0);
     __syncthreads();
     // outputs m in [max(m0, drain), mhi) of this block [c_base, mhi); output m is sample m - drain of the
     // next stage's stream, stored at out_fresh[m - drain - out_split]
     const long long lo = p.m0 > p.drain ? p.m0 : p.drain;
     const int rel_lo = lo > c_base ? (int)(lo - c_base) : 0;
-    hbf_stage<MC, GE::SB, GE::SB, GE::NB / 2 - DEC_OB, true>(be, bo, DEC_OB, tC, nullptr, nullptr,
+    hbf_stage<MC, GE::SB, GE::SB, GE::NB / 2 - DEC_OB, true, PRESET, 0>(be, bo, DEC_OB, nullptr, nullptr,
                                                             p.out_fresh + (c_base - p.drain - p.out_split), rel_lo,
                                                             DEC_OB);
 }
