@@ -159,7 +159,7 @@ def run_ours(args):
     import numpy as np
     import torch
     import torch.distributed as dist
-    from stabilizer_stream_b200 import MergeOpts, PsdCascade
+    from stabilizer_stream_b200 import MergeOpts, PsdCascade, multi
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -185,10 +185,7 @@ def run_ours(args):
         """readout collective: one NCCL gather of every channel's merged spectrum to rank 0"""
         if world == 1:
             return
-        t = torch.zeros(16 * (N_FFT // 2 + 1), device=dev)
-        t[:p.size] = torch.from_numpy(p).to(dev, non_blocking=True)
-        out = [torch.empty_like(t) for _ in range(world)] if rank == 0 else None
-        dist.gather(t, out, dst=0)
+        multi.gather_spectra(p, dist, dev, dst=0, max_len=16 * (N_FFT // 2 + 1))
 
     def timed(cascade, src, steps, warmup):
         for _ in range(warmup):
