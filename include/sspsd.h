@@ -165,6 +165,30 @@ int32_t sspsd_cascade_partials(sspsd_cascade *h, sspsd_partials *out);
 /* overwrite the per-stage segment counts after an external reduction of `acc` (boxcar averaging only) */
 int32_t sspsd_cascade_set_counts(sspsd_cascade *h, const uint64_t *count_raw, uint32_t n_stages);
 
+/* ---- time-chunked processing of ONE long stream by several handles (GPUs) ----
+ * BASELINE config 5 / north_star item 5; no reference analogue (the reference is sequential).  The
+ * stream is cut into chunks [own_lo, own_hi) of stage-0 samples.  A rank positions a fresh cascade with
+ * sspsd_cascade_seek() somewhat before its chunk (FIR warm-up halo), restricts it with
+ * sspsd_cascade_set_window() and feeds it the samples [pos, feed_hi) of the stream.  All bookkeeping then
+ * runs in GLOBAL stream coordinates (segment k of every stage covers exactly the samples it covers in
+ * a sequential run); a segment is accumulated iff it is fully valid (no warm-up contaminated sample)
+ * and its start lies in [own_lo, own_hi) (stage-0 position own(i, j) = 8^i j + R 8 (8^i - 1)/7 of sample
+ * j of stage i, R = drain), so the ranks' partial accumulators sum to the sequential result.  Only
+ * stages < n_local run locally; the input stream of stage n_local is exported with
+ * sspsd_cascade_take_tail(), gathered, and fed to rank 0's handle with sspsd_cascade_process_stage(),
+ * which then runs the deep stages; sspsd_cascade_set_stream_state() installs the reduced counts.
+ * Boxcar averaging only (EWMA is an order dependent recurrence). */
+int32_t sspsd_cascade_seek(sspsd_cascade *h, uint64_t pos);
+int32_t sspsd_cascade_set_window(sspsd_cascade *h, uint64_t own_lo, uint64_t own_hi, uint32_t n_local);
+/* samples [j_lo, j_hi) of the stage-n_local input stream produced so far (clipped to what exists);
+ * len: capacity in, length out; *first = stream index of out[0] */
+int32_t sspsd_cascade_take_tail(sspsd_cascade *h, uint64_t j_lo, uint64_t j_hi, float *out, size_t *len,
+                                uint64_t *first, int32_t mem);
+/* feed n samples directly into stage `stage`'s stream (the next samples of that stream, in order) */
+int32_t sspsd_cascade_process_stage(sspsd_cascade *h, uint32_t stage, const float *x, size_t n, int32_t mem);
+/* overwrite stage bookkeeping after an external reduction: samples received, segments accumulated */
+int32_t sspsd_cascade_set_stream_state(sspsd_cascade *h, uint32_t stage, uint64_t samples, uint64_t segments);
+
 /* ---- measurement hooks (no reference analogue) ----
  * With profiling enabled every kernel launch of the handle is bracketed by CUDA events on the
  * handle's stream; sspsd_cascade_profile_read() synchronises, sums the event times per kernel class

@@ -87,6 +87,11 @@ PROTOTYPES = {
     "sspsd_break_frequencies": (_i32, [C.POINTER(BreakC), _sz, _vp, _psz]),
     "sspsd_cascade_partials": (_i32, [_vp, C.POINTER(PartialsC)]),
     "sspsd_cascade_set_counts": (_i32, [_vp, C.POINTER(C.c_uint64), C.c_uint32]),
+    "sspsd_cascade_seek": (_i32, [_vp, C.c_uint64]),
+    "sspsd_cascade_set_window": (_i32, [_vp, C.c_uint64, C.c_uint64, C.c_uint32]),
+    "sspsd_cascade_take_tail": (_i32, [_vp, C.c_uint64, C.c_uint64, _vp, _psz, C.POINTER(C.c_uint64), _i32]),
+    "sspsd_cascade_process_stage": (_i32, [_vp, C.c_uint32, _vp, _sz, _i32]),
+    "sspsd_cascade_set_stream_state": (_i32, [_vp, C.c_uint32, C.c_uint64, C.c_uint64]),
     "sspsd_cascade_profile_enable": (_i32, [_vp, _i32]),
     "sspsd_cascade_profile_read": (_i32, [_vp, C.POINTER(ProfileC)]),
     "sspsd_stage_create": (_i32, [C.POINTER(Config), C.POINTER(_vp)]),

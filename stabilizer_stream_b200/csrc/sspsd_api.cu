@@ -186,6 +186,25 @@ int32_t sspsd_cascade_set_counts(sspsd_cascade* h, const uint64_t* craw, uint32_
     return h ? h->c.set_counts(craw, n) : SSPSD_EINVAL;
 }
 
+int32_t sspsd_cascade_seek(sspsd_cascade* h, uint64_t pos) { return h ? h->c.seek(pos) : SSPSD_EINVAL; }
+int32_t sspsd_cascade_set_window(sspsd_cascade* h, uint64_t own_lo, uint64_t own_hi, uint32_t n_local)
+{
+    return h ? h->c.set_window(own_lo, own_hi, n_local) : SSPSD_EINVAL;
+}
+int32_t sspsd_cascade_take_tail(sspsd_cascade* h, uint64_t j_lo, uint64_t j_hi, float* out, size_t* len,
+                                uint64_t* first, int32_t mem)
+{
+    return h ? h->c.take_tail(j_lo, j_hi, out, len, first, mem) : SSPSD_EINVAL;
+}
+int32_t sspsd_cascade_process_stage(sspsd_cascade* h, uint32_t stage, const float* x, size_t n, int32_t mem)
+{
+    return h ? h->c.process_stage(stage, x, n, mem) : SSPSD_EINVAL;
+}
+int32_t sspsd_cascade_set_stream_state(sspsd_cascade* h, uint32_t stage, uint64_t samples, uint64_t segments)
+{
+    return h ? h->c.set_stream_state(stage, samples, segments) : SSPSD_EINVAL;
+}
+
 int32_t sspsd_cascade_profile_enable(sspsd_cascade* h, int32_t on)
 {
     if (!h) return SSPSD_EINVAL;

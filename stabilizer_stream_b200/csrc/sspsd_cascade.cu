@@ -220,6 +220,7 @@ Cascade::~Cascade()
     cudaFree(d_in_[0]);
     cudaFree(d_in_[1]);
     cudaFree(d_sink_);
+    cudaFree(d_tail_);
     if (h_stage_[0]) cudaFreeHost(h_stage_[0]);
     if (h_stage_[1]) cudaFreeHost(h_stage_[1]);
     if (h_acc_) cudaFreeHost(h_acc_);
@@ -370,6 +371,8 @@ int Cascade::add_stage()
     SSPSD_CUDA(cudaMemsetAsync(st.carry[0], 0, cap * sizeof(float), ss));
     SSPSD_CUDA(cudaMemsetAsync(st.carry[1], 0, cap * sizeof(float), ss));
     st.carry_start = -(long long)hb_;
+    // time-chunk mode: warm-up contamination propagates down the cascade (see seek())
+    st.valid_from = stages_.empty() ? seek_pos_ : next_valid_from(stages_.back().valid_from);
     SSPSD_CUDA(cudaMemsetAsync(d_acc_ + stages_.size() * acc_stride_, 0, acc_stride_ * sizeof(float), ss));
     for (int b = 0; b < 2; ++b) SSPSD_CUDA(cudaEventCreateWithFlags(&st.ev_read[b], cudaEventDisableTiming));
     stages_.push_back(st);
@@ -484,7 +487,21 @@ int Cascade::run_stage(size_t i, const float* fresh, long long split, uint64_t n
     const StreamSrc src{st.carry[st.cur], fresh, st.carry_start, split};
     int rc;
 
-    if (craw1 > craw0) {
+    if (windowed_ && i < n_local_ && craw1 > craw0) {
+        // time-chunk mode: accumulate only the fully valid segments this rank owns; their start position
+        // own(i, k*hop) = 8^i k hop + c_i must lie in [own_lo, own_hi)
+        const uint64_t step = (uint64_t)hop_ << (SSPSD_DEPTH * i);
+        const uint64_t c = own_offset(i);
+        auto first_at_or_after = [&](uint64_t pos) { return pos <= c ? 0ull : (pos - c + step - 1) / step; };
+        uint64_t klo = std::max<uint64_t>(first_at_or_after(own_lo_), (st.valid_from + hop_ - 1) / hop_);
+        uint64_t khi = own_hi_ == ~0ull ? ~0ull : first_at_or_after(own_hi_);
+        uint64_t a = std::max(craw0, klo), b = std::min(craw1, khi);
+        if (b > a) {
+            rc = launch_psd(i, src, a, b - a, (int)(b - a), 1.0f, 1.0f);
+            if (rc) return rc;
+            st.count = (uint32_t)std::min<uint64_t>((uint64_t)st.count + (b - a), 0xffffffffull);
+        }
+    } else if (craw1 > craw0) {
         const uint64_t S = craw1 - craw0;
         EwmaPlan e = ewma_plan(st.count, st.avg, S);
         if (e.total != 1.0f) {
@@ -510,7 +527,27 @@ int Cascade::run_stage(size_t i, const float* fresh, long long split, uint64_t n
         const uint64_t em1 = m1 > (uint64_t)drain_ ? m1 - drain_ : 0;
         n_next = em1 - st.emitted;
         if (n_next > 0) {
-            if (i + 1 >= max_stages_) {
+            if (windowed_ && i + 1 == n_local_) {
+                // time-chunk mode: the input stream of the first non-local stage is collected for export
+                if (tail_len_ + n_next > tail_cap_) {
+                    size_t cap = std::max<size_t>(2 * tail_cap_, tail_len_ + n_next + (1u << 16));
+                    float* nb = nullptr;
+                    SSPSD_CUDA(cudaMalloc(&nb, cap * sizeof(float)));
+                    if (d_tail_) {
+                        SSPSD_CUDA(cudaMemcpyAsync(nb, d_tail_, tail_len_ * sizeof(float), cudaMemcpyDeviceToDevice, ss));
+                        SSPSD_CUDA(cudaStreamSynchronize(ss));
+                        SSPSD_CUDA(cudaFree(d_tail_));
+                    }
+                    d_tail_ = nb;
+                    tail_cap_ = cap;
+                }
+                if (tail_len_ == 0) tail_first_ = st.emitted;
+                rc = launch_decim(i, src, m0, m1, d_tail_ + tail_len_, (long long)st.emitted);
+                if (rc) return rc;
+                tail_len_ += n_next;
+                st.emitted = em1;
+                n_next = 0;
+            } else if (i + 1 >= max_stages_) {
                 // single-stage API: the decimated items of this call are collected in the sink
                 if (sink_len_ + n_next > sink_cap_) {
                     set_error("internal: sink overflow");
@@ -1062,6 +1099,134 @@ int Cascade::profile_read(sspsd_profile* out)
     return SSPSD_OK;
 }
 
+uint64_t Cascade::next_valid_from(uint64_t valid) const
+{
+    // decimator outputs m are free of warm-up contamination once every input 8m+7-(H-1) .. 8m+7 is:
+    // m >= (valid + halo + 1) / 8 (halo >= H-1); output m is sample m - R of the next stage
+    if (valid == 0) return 0;
+    const uint64_t mv = (valid + (uint64_t)decim_halo(cfg_.hbf) + 1) / 8;
+    return mv > (uint64_t)drain_ ? mv - drain_ : 0;
+}
+
+uint64_t Cascade::own_offset(size_t i) const
+{
+    // own(i, j) = 8^i j + c_i with c_0 = 0, c_{i+1} = 8 (c_i + R): sample j of stage i+1 is decimator
+    // output j + R of stage i, whose input chunk starts at stage-i sample 8 (j + R)
+    uint64_t c = 0;
+    for (size_t q = 0; q < i; ++q) c = 8 * (c + (uint64_t)drain_);
+    return c;
+}
+
+int Cascade::seek(uint64_t pos)
+{
+    if (!stages_.empty() || staged_) {
+        set_error("seek() needs a fresh cascade");
+        return SSPSD_EINVAL;
+    }
+    DeviceGuard g(cfg_.device);
+    if (!g.ok) return SSPSD_ECUDA;
+    // closed-form state of a sequential run after `pos` samples, unknown history = zeros
+    seek_pos_ = pos;
+    uint64_t L = pos;
+    for (size_t i = 0; L > 0 && i < max_stages_; ++i) {
+        int rc = add_stage();
+        if (rc) return rc;
+        StageState& st = stages_[i];
+        st.L = L;
+        st.craw = L < n_ ? 0 : 1 + (L - n_) / hop_;
+        const uint64_t D = decimated(st);
+        st.emitted = D / 8 > (uint64_t)drain_ ? D / 8 - drain_ : 0;
+        st.count = 0;
+        st.carry_start = (long long)D - hb_;
+        L = st.emitted;
+    }
+    return SSPSD_OK;
+}
+
+int Cascade::set_window(uint64_t own_lo, uint64_t own_hi, uint32_t n_local)
+{
+    if (n_local == 0 || n_local > SSPSD_MAX_STAGES || own_hi < own_lo) {
+        set_error("bad window");
+        return SSPSD_EINVAL;
+    }
+    if (avg_.limit != 0xffffffffu || avg_.count != 0xffffffffu) {
+        set_error("time-chunk mode supports boxcar averaging only");
+        return SSPSD_EINVAL;
+    }
+    windowed_ = true;
+    own_lo_ = own_lo;
+    own_hi_ = own_hi;
+    n_local_ = n_local;
+    return SSPSD_OK;
+}
+
+int Cascade::take_tail(uint64_t j_lo, uint64_t j_hi, float* out, size_t* len, uint64_t* first, int mem)
+{
+    if (!len) return SSPSD_EINVAL;
+    int rc = flush();
+    if (rc) return rc;
+    const uint64_t have_lo = tail_first_, have_hi = tail_first_ + tail_len_;
+    const uint64_t a = std::max(j_lo, have_lo), b = std::min(j_hi, have_hi);
+    const size_t n = b > a ? (size_t)(b - a) : 0;
+    if (first) *first = a;
+    if (*len < n || (n && !out)) {
+        *len = n;
+        set_error("output capacity too small");
+        return SSPSD_ESHORT;
+    }
+    *len = n;
+    if (!n) return SSPSD_OK;
+    DeviceGuard g(cfg_.device);
+    if (!g.ok) return SSPSD_ECUDA;
+    SSPSD_CUDA(cudaMemcpyAsync(out, d_tail_ + (a - have_lo), n * sizeof(float),
+                               mem == SSPSD_MEM_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, stream_));
+    SSPSD_CUDA(cudaStreamSynchronize(stream_));
+    return SSPSD_OK;
+}
+
+int Cascade::process_stage(uint32_t stage, const float* x, size_t n, int mem)
+{
+    if (stage == 0) return process(x, n, mem);
+    if (n == 0) return SSPSD_OK;
+    if (!x || stage >= max_stages_) return SSPSD_EINVAL;
+    int rc = flush();
+    if (rc) return rc;
+    DeviceGuard g(cfg_.device);
+    if (!g.ok) return SSPSD_ECUDA;
+    while (stages_.size() <= stage) {
+        rc = add_stage();
+        if (rc) return rc;
+    }
+    size_t pos = 0;
+    while (pos < n) {
+        const size_t c = std::min<size_t>(n - pos, cfg_.max_batch);
+        StageState& st = stages_[stage];
+        const long long split = floor4((long long)st.L);
+        const size_t head = (size_t)((long long)st.L - split);
+        rc = ensure_fresh(st, c + 8);
+        if (rc) return rc;
+        float* buf = st.fresh[st.fb];
+        SSPSD_CUDA(cudaMemcpyAsync(buf + head, x + pos, c * sizeof(float),
+                                   mem == SSPSD_MEM_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice,
+                                   stage_stream(stage)));
+        if (mem != SSPSD_MEM_DEVICE) SSPSD_CUDA(cudaStreamSynchronize(stage_stream(stage)));
+        rc = run_stage(stage, buf, split, c);
+        if (rc) return rc;
+        pos += c;
+    }
+    return SSPSD_OK;
+}
+
+int Cascade::set_stream_state(uint32_t stage, uint64_t samples, uint64_t segments)
+{
+    if (stage >= stages_.size()) return SSPSD_EINVAL;
+    StageState& st = stages_[stage];
+    st.L = samples;
+    st.craw = samples < n_ ? 0 : 1 + (samples - n_) / hop_;
+    st.count = (uint32_t)std::min<uint64_t>(segments, 0xffffffffull);
+    return SSPSD_OK;
+}
+
 int Cascade::partials(sspsd_partials* out)
 {
     if (!out) return SSPSD_EINVAL;
@@ -1072,7 +1237,7 @@ int Cascade::partials(sspsd_partials* out)
     out->acc_stride = acc_stride_;
     out->n_stages = (uint32_t)stages_.size();
     for (size_t i = 0; i < stages_.size(); ++i)
-        out->count_raw[i] = stages_[i].craw;
+        out->count_raw[i] = windowed_ ? stages_[i].count : stages_[i].craw;
     return SSPSD_OK;
 }
 

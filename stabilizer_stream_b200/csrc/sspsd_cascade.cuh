@@ -36,6 +36,7 @@ struct StageState {
     uint32_t count = 0;   // effective averaging count (Psd::count, psd.rs:128)
     uint32_t avg = 0xffffffffu;
     uint64_t emitted = 0; // samples handed to the next stage
+    uint64_t valid_from = 0;  // time-chunk mode: first stream index not contaminated by the warm-up
     // device stream storage: carry[cur] holds [carry_start, L); the batch's new samples live in a
     // "fresh" buffer from split = floor4(L) on (its first L - split entries are copies of the carry tail)
     float* carry[2] = {nullptr, nullptr};
@@ -65,6 +66,11 @@ public:
     int sync();
     int psd(const sspsd_merge_opts& o, float* p, size_t* p_len, sspsd_break* b, size_t* b_len);
     int partials(sspsd_partials* out);
+    int seek(uint64_t pos);
+    int set_window(uint64_t own_lo, uint64_t own_hi, uint32_t n_local);
+    int take_tail(uint64_t j_lo, uint64_t j_hi, float* out, size_t* len, uint64_t* first, int mem);
+    int process_stage(uint32_t stage, const float* x, size_t n, int mem);
+    int set_stream_state(uint32_t stage, uint64_t samples, uint64_t segments);
     void profile_enable(bool on) { prof_on_ = on; }
     int profile_read(sspsd_profile* out);
     int set_counts(const uint64_t* craw, uint32_t n);
@@ -114,6 +120,17 @@ private:
     uint64_t launches_[SSPSD_PROF_NCLASS] = {0, 0, 0, 0, 0};
     void prof_begin(int cls, uint64_t units, cudaStream_t s);
     void prof_end(cudaStream_t s);
+
+    // time-chunk mode
+    bool windowed_ = false;
+    uint64_t own_lo_ = 0, own_hi_ = ~0ull;
+    uint32_t n_local_ = SSPSD_MAX_STAGES;
+    float* d_tail_ = nullptr;
+    size_t tail_cap_ = 0, tail_len_ = 0;
+    uint64_t tail_first_ = 0;
+    uint64_t seek_pos_ = 0;
+    uint64_t next_valid_from(uint64_t valid) const;
+    uint64_t own_offset(size_t i) const;  // stage-0 position of sample 0 of stage i
 
     sspsd_config cfg_{};
     uint32_t n_ = 0, log2n_ = 0, hop_ = 0, max_stages_ = SSPSD_MAX_STAGES;

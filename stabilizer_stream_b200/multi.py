@@ -92,3 +92,129 @@ def cascade_partials_tensor(cascade):
     cascade.sync()
     t = torch.as_tensor(DeviceArray(pc.acc, (16, int(pc.acc_stride))), device="cuda")
     return t, [int(pc.count_raw[i]) for i in range(pc.n_stages)]
+
+
+# =============================================================================================
+# Time-chunked processing of ONE long stream (BASELINE config 5): planner + orchestration.
+# Mirrors the integer bookkeeping of the library (csrc/sspsd_cascade.cu: seek, next_valid_from,
+# own_offset) so that every rank's owned segments are provably valid and complete.
+# =============================================================================================
+DRAIN = {0: 73, 1: 115}      # hbf_dec_response_length(3) per tap family (sspsd_hbf_taps.h)
+DEC_HALO = {0: 304, 1: 472}  # history the decimator kernel reads before a block (DecGeom::HALO)
+
+
+def own_offset(i, drain):
+    """Stage-0 position of sample 0 of stage i: c_0 = 0, c_{i+1} = 8 (c_i + R)."""
+    c = 0
+    for _ in range(i):
+        c = 8 * (c + drain)
+    return c
+
+
+def stream_state(total, n, hop, drain, max_stages=16):
+    """Closed-form state of a sequential cascade after `total` samples:
+    list of (samples received L_i, segments craw_i, samples emitted to the next stage)."""
+    out, L = [], total
+    while L > 0 and len(out) < max_stages:
+        craw = 0 if L < n else 1 + (L - n) // hop
+        D = n + (craw - 1) * hop if craw else 0
+        em = max(D // 8 - drain, 0)
+        out.append((L, craw, em))
+        L = em
+    return out
+
+
+def needed_input(stage, j_end, n, hop, drain):
+    """Stage-0 samples needed so that stage `stage` has received at least j_end samples."""
+    for _ in range(stage):
+        d = 8 * (j_end + drain)                       # the previous stage must have decimated D >= d
+        craw = 1 + max(0, -(-(d - n) // hop))
+        j_end = n + (craw - 1) * hop
+    return j_end
+
+
+def valid_from(pos, stages, halo, drain):
+    """Per-stage first stream index free of warm-up contamination for a cascade seek()ed to `pos`."""
+    v, out = pos, []
+    for _ in range(stages + 1):
+        out.append(v)
+        v = 0 if v == 0 else max((v + halo + 1) // 8 - drain, 0)
+    return out
+
+
+def first_index_at_or_after(pos, i, unit, drain):
+    """Smallest k with own(i, k*unit) >= pos (unit = hop for segments, 1 for samples)."""
+    c = own_offset(i, drain)
+    step = unit * 8 ** i
+    return 0 if pos <= c else -(-(pos - c) // step)
+
+
+def plan_time_chunks(total, world, n, hbf=1, n_local=3, window_overlap=None):
+    """Cut a stream of `total` samples into `world` chunks.  Returns one dict per rank:
+    own_lo/own_hi (ownership interval in stage-0 samples, own_hi None for the last rank),
+    feed_lo/feed_hi (samples the rank must process: chunk + FIR warm-up halo + completion halo),
+    tail_lo/tail_hi (owned index range of the stage-n_local input stream)."""
+    hop = n - (n // 2 if window_overlap is None else window_overlap)
+    drain, halo = DRAIN[hbf], DEC_HALO[hbf]
+    bounds = [(g * total // world) // hop * hop for g in range(world)] + [total]
+    plans = []
+    for g in range(world):
+        own_lo, own_hi = bounds[g], bounds[g + 1]
+        last = g == world - 1
+        # ---- how far forward: every owned segment complete, every owned tail sample produced ----
+        feed_hi = total
+        if not last:
+            need = own_hi
+            for i in range(n_local):
+                k_hi = first_index_at_or_after(own_hi, i, hop, drain)
+                if k_hi > 0:
+                    need = max(need, needed_input(i, (k_hi - 1) * hop + n, n, hop, drain))
+            j_hi = first_index_at_or_after(own_hi, n_local, 1, drain)
+            need = max(need, needed_input(n_local, j_hi, n, hop, drain))
+            feed_hi = min(total, need)
+        # ---- how far back: first owned segment / tail sample of every stage must be valid ----
+        if own_lo == 0:
+            feed_lo = 0
+        else:
+            back = 8 ** n_local * 64
+            while True:
+                feed_lo = max(0, (own_lo - back) // 8 * 8)
+                v = valid_from(feed_lo, n_local, halo, drain)
+                ok = all(first_index_at_or_after(own_lo, i, hop, drain) * hop >= v[i] for i in range(n_local))
+                ok = ok and first_index_at_or_after(own_lo, n_local, 1, drain) >= v[n_local]
+                if ok or feed_lo == 0:
+                    break
+                back *= 2
+        plans.append(dict(rank=g, own_lo=own_lo, own_hi=None if last else own_hi, feed_lo=feed_lo, feed_hi=feed_hi,
+                          tail_lo=first_index_at_or_after(own_lo, n_local, 1, drain),
+                          tail_hi=None if last else first_index_at_or_after(own_hi, n_local, 1, drain)))
+    return plans
+
+
+def run_chunk(cascade, plan, samples, n_local):
+    """One rank's share: position the fresh cascade, restrict it, process samples[feed_lo:feed_hi]
+    (`samples` is that slice, host or device), and return its slice of the stage-n_local stream."""
+    cascade.seek(plan["feed_lo"])
+    cascade.set_window(plan["own_lo"], plan["own_hi"], n_local)
+    cascade.process(samples)
+    first, tail = cascade.take_tail(plan["tail_lo"], plan["tail_hi"] if plan["tail_hi"] is not None else 2 ** 63)
+    return first, tail
+
+
+def finish_on_root(root, reduced_counts, tails, total, n, hbf, n_local):
+    """Rank 0 after the reduction of the accumulator rows: install the global bookkeeping of the local
+    stages and run the deep stages on the gathered stage-n_local stream."""
+    hop = n // 2
+    st = stream_state(total, n, hop, DRAIN[hbf])
+    for i in range(min(n_local, len(st))):
+        assert reduced_counts[i] == st[i][1], "stage %d: %d segments reduced, %d expected" % (i, reduced_counts[i], st[i][1])
+        root.set_stream_state(i, st[i][0], st[i][1])
+    pos = 0
+    for first, tail in tails:
+        assert first == pos or tail.size == 0, "tail slices are not contiguous: %d != %d" % (first, pos)
+        if tail.size:
+            root.process_stage(n_local, tail)
+            pos = first + tail.size
+    if len(st) > n_local:
+        assert pos == st[n_local][0], "tail stream length %d != %d" % (pos, st[n_local][0])
+    return root

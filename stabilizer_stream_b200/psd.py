@@ -183,6 +183,34 @@ class PsdCascade:
         L.check(L.lib().sspsd_cascade_psd(self._h, C.byref(o), p.ctypes.data, C.byref(pl), b, C.byref(bl)))
         return p[:pl.value].copy(), [Break._from_c(b[i]) for i in range(bl.value)]
 
+    # ---- time-chunked processing of one stream by several handles (include/sspsd.h) ----
+    def seek(self, pos):
+        L.check(L.lib().sspsd_cascade_seek(self._h, pos))
+
+    def set_window(self, own_lo, own_hi, n_local):
+        L.check(L.lib().sspsd_cascade_set_window(self._h, own_lo, own_hi if own_hi is not None else 2 ** 64 - 1, n_local))
+
+    def take_tail(self, j_lo, j_hi):
+        """-> (first stream index, numpy array) of the exported stage-n_local input stream in [j_lo, j_hi)"""
+        n = C.c_size_t(0)
+        first = C.c_uint64(0)
+        st = L.lib().sspsd_cascade_take_tail(self._h, j_lo, j_hi, None, C.byref(n), C.byref(first), L.MEM_HOST)
+        if st not in (L.OK, L.ESHORT):
+            L.check(st)
+        out = np.zeros(max(n.value, 1), np.float32)
+        n = C.c_size_t(out.size)
+        L.check(L.lib().sspsd_cascade_take_tail(self._h, j_lo, j_hi, out.ctypes.data, C.byref(n), C.byref(first),
+                                                L.MEM_HOST))
+        return first.value, out[:n.value]
+
+    def process_stage(self, stage, x):
+        ptr, n, mem, keep = _as_buffer(x)
+        L.check(L.lib().sspsd_cascade_process_stage(self._h, stage, ptr, n, mem))
+        del keep
+
+    def set_stream_state(self, stage, samples, segments):
+        L.check(L.lib().sspsd_cascade_set_stream_state(self._h, stage, samples, segments))
+
     def profile_enable(self, on=True):
         L.check(L.lib().sspsd_cascade_profile_enable(self._h, int(on)))
 

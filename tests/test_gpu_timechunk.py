@@ -1,0 +1,69 @@
+"""Time-chunked processing of one stream (BASELINE config 5) on one GPU: `world` handles play the ranks one
+after the other, their accumulator rows are summed like the NCCL reduction would, rank 0 finishes the deep
+stages on the gathered stage-K stream.  The result must equal the sequential cascade."""
+import numpy as np
+import pytest
+
+from conftest import uniform_noise
+
+pytestmark = pytest.mark.gpu
+
+
+def run_emulated(x, n, world, n_local, hbf=1):
+    import torch
+    from stabilizer_stream_b200 import Hbf, MergeOpts, PsdCascade, multi
+    plans = multi.plan_time_chunks(x.size, world, n, hbf, n_local)
+    xd = torch.from_numpy(x).cuda()
+    cas, tails, accs, counts = [], [], [], []
+    for p in plans:
+        c = PsdCascade(n, hbf=Hbf(hbf))
+        tails.append(multi.run_chunk(c, p, xd[p["feed_lo"]:p["feed_hi"]], n_local))
+        t, cnt = multi.cascade_partials_tensor(c)
+        cas.append(c)
+        accs.append(t)
+        counts.append((cnt + [0] * 16)[:16])
+    total_acc = accs[0][:n_local].clone()
+    for t in accs[1:]:
+        total_acc += t[:n_local]
+    accs[0][:n_local].copy_(total_acc)
+    red = [sum(c[i] for c in counts) for i in range(n_local)]
+    root = multi.finish_on_root(cas[0], red, tails, x.size, n, hbf, n_local)
+    return root, plans
+
+
+def breaks_tuple(b):
+    return (b.start, b.include, b.count, b.bins.start, b.bins.stop, b.fft_size, b.decimation, b.pending, b.processed)
+
+
+@pytest.mark.parametrize("n,total,world,k,hbf", [(512, 3_000_017, 4, 3, 1), (4096, 30_000_000, 3, 2, 1), (512, 2_500_000, 2, 2, 0),
+                                                  (64, 700_001, 5, 3, 1)])
+def test_time_chunked_equals_sequential(oracle, n, total, world, k, hbf):
+    import torch
+    from stabilizer_stream_b200 import Hbf, MergeOpts, PsdCascade
+    x = uniform_noise(total, 77 + n) + np.float32(0.1)
+    root, plans = run_emulated(x, n, world, k, hbf)
+    p, b = root.psd(MergeOpts())
+    seq = PsdCascade(n, hbf=Hbf(hbf))
+    seq.process(torch.from_numpy(x).cuda())
+    ps, bs = seq.psd(MergeOpts())
+    assert [breaks_tuple(v) for v in b] == [breaks_tuple(v) for v in bs]
+    assert p.size == ps.size
+    np.testing.assert_allclose(p, ps, rtol=2e-5, atol=1e-6 * float(np.median(ps)))
+    # and against the CPU oracle, all stages, all bins
+    o = oracle.Cascade(n, hbf)
+    o.process(x)
+    pk, bk = root.psd(MergeOpts(keep_overlap=True, min_count=0, keep_transition_band=True))
+    pok, bok = o.psd(True, 0, True)
+    assert [v.count for v in bk] == [v.count for v in bok]
+    floor = 1e-5 * np.median(pok)
+    assert np.max((np.abs(pk - pok) - floor) / pok) < 1e-4
+    # the halo overhead of the plan is what the planner promised
+    assert all(q["feed_lo"] <= q["own_lo"] for q in plans)
+
+
+def test_window_rejects_ewma():
+    from stabilizer_stream_b200 import AvgOpts, PsdCascade, _lib
+    c = PsdCascade(512)
+    c.set_avg(AvgOpts(limit=999, count=2 ** 32 - 2))
+    with pytest.raises(_lib.SspsdError):
+        c.set_window(0, 1 << 20, 2)
