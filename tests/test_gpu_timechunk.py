@@ -55,8 +55,11 @@ def test_time_chunked_equals_sequential(oracle, n, total, world, k, hbf):
     pk, bk = root.psd(MergeOpts(keep_overlap=True, min_count=0, keep_transition_band=True))
     pok, bok = o.psd(True, 0, True)
     assert [v.count for v in bk] == [v.count for v in bok]
-    floor = 1e-5 * np.median(pok)
-    assert np.max((np.abs(pk - pok) - floor) / pok) < 1e-4
+    for bi in bk:
+        if bi.count:   # a trailing stage with count 0 is normal (gain 0 -> NaN bins in the reference too)
+            sl = slice(bi.start, bi.start + len(bi.bins))
+            floor = 1e-5 * np.median(pok[sl])
+            assert np.max((np.abs(pk[sl] - pok[sl]) - floor) / pok[sl]) < 1e-4, "stage dec=%d" % bi.decimation
     # the halo overhead of the plan is what the planner promised
     assert all(q["feed_lo"] <= q["own_lo"] for q in plans)
 
