@@ -218,3 +218,35 @@ def finish_on_root(root, reduced_counts, tails, total, n, hbf, n_local):
     if len(st) > n_local:
         assert pos == st[n_local][0], "tail stream length %d != %d" % (pos, st[n_local][0])
     return root
+
+
+def time_chunked_psd(cascade, feed, total, n, dist=None, hbf=1, n_local=3, device="cuda"):
+    """Distributed driver of the time-chunked mode: every rank calls this with a FRESH cascade and a
+    callable feed(lo, hi, sink) that pushes stream samples [lo, hi) into sink(x) in order (any block
+    size).  One NCCL sum-reduction of the local stages' accumulator rows + counts, one gather of the
+    (tiny) stage-n_local stream slices; rank 0 returns its completed cascade (call .psd() on it), the
+    other ranks return None."""
+    import torch
+    world = dist.get_world_size() if dist is not None else 1
+    rank = dist.get_rank() if dist is not None else 0
+    plan = plan_time_chunks(total, world, n, hbf, n_local)[rank]
+    cascade.seek(plan["feed_lo"])
+    cascade.set_window(plan["own_lo"], plan["own_hi"], n_local)
+    feed(plan["feed_lo"], plan["feed_hi"], cascade.process)
+    first, tail = cascade.take_tail(plan["tail_lo"], plan["tail_hi"] if plan["tail_hi"] is not None else 2 ** 63)
+    acc, counts = cascade_partials_tensor(cascade)
+    counts = (counts + [0] * 16)[:n_local]
+    if world > 1:
+        rows = acc[:n_local]
+        rows, counts = reduce_partials(rows, counts, dist, dst=0)
+        # gather the stage-n_local slices (variable length) on rank 0
+        meta = torch.tensor([first, tail.size], dtype=torch.int64, device=device)
+        metas = [torch.empty_like(meta) for _ in range(world)] if rank == 0 else None
+        dist.gather(meta, metas, dst=0)
+        tails = gather_spectra(tail, dist, torch.device(device), dst=0)
+        if rank != 0:
+            return None
+        tails = [(int(m[0].item()), t) for m, t in zip(metas, tails)]
+    else:
+        tails = [(first, tail)]
+    return finish_on_root(cascade, counts, tails, total, n, hbf, n_local)

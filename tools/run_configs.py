@@ -1,0 +1,175 @@
+#!/usr/bin/env python3
+"""Run the BASELINE.json parity/throughput configurations that are not the bench.py workload and print one
+JSON line per config (rank 0).  Launch with python (1 GPU) or torchrun (N GPUs, config 5 only).
+
+  --config 1   raw f32, single stage N=4096 Hann (Psd handle), 2^28 samples
+  --config 3   AdcDac frames (22 batches) -> decode + loss + 4 cascades, 2^20 frames
+  --config 5   4.8e9-sample capture, N=4096, time-chunked over WORLD_SIZE GPUs (checked against the
+               sequential 1-GPU run of the same stream when --check is given)
+"""
+import argparse
+import json
+import os
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+
+BLOCK = 1 << 26
+
+
+def noise_block(b, dev):
+    """Block b of the synthetic stream: uniform, zero mean, unit variance; counter-based per block so that
+    every rank generates identical samples for the same stream positions."""
+    g = torch.Generator(device=dev).manual_seed(0x7654321 + b)
+    return (torch.rand(BLOCK, device=dev, generator=g) - 0.5) * (12 ** 0.5)
+
+
+def feed_stream(lo, hi, sink, dev):
+    pos = lo
+    while pos < hi:
+        b = pos // BLOCK
+        blk = noise_block(b, dev)
+        a = pos - b * BLOCK
+        e = min(BLOCK, hi - b * BLOCK)
+        sink(blk[a:e])
+        pos = b * BLOCK + e
+
+
+def config1(dev):
+    from oracle import binding as orc
+    from stabilizer_stream_b200 import Psd
+    n, total = 4096, 1 << 28
+    x = torch.cat([noise_block(b, dev) for b in range(total // BLOCK)])
+    s = Psd(n)
+    s.process(x[:1 << 22])
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    y = s.process(x)
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    p = s.spectrum() / s.gain()
+    flat = bool(np.all(np.abs(p * 0.5 - 1.0) < 10.0 / np.sqrt(s.count())))
+    xs = x[:1 << 24].cpu().numpy()
+    o = orc.Stage(n)
+    t0 = time.perf_counter()
+    o.process(xs)
+    dtc = time.perf_counter() - t0
+    return {"config": 1, "samples": total, "gpu_MSps_incl_D2H_of_decimated_stream": total / dt / 1e6,
+            "cpu_port_MSps_1core": xs.size / dtc / 1e6, "segments": s.count(), "flat_10sigma": flat,
+            "decimated_len": int(y.size)}
+
+
+def config3(dev):
+    from frames_util import make_frames, oracle_decode_stream
+    from oracle import binding as orc
+    from stabilizer_stream_b200 import Detrend, FrameDecoder, Loss, PsdCascade
+    n, batches, nfr = 4096, 22, 1 << 20
+    small, flen, stride, _ = make_frames(1, batches, 4096, seed=3, drop_every=1009, start_seq=0xFFFFFFFF - 9 * 1009 * batches)
+    reps = nfr // 4096
+    # the big stream repeats the small one (sequence numbers then jump back: counted as huge wrapping gaps,
+    # exactly like Loss::update would) -- what matters is bit-exact agreement with the oracle on the same bytes
+    data = small * reps
+    fr = torch.frombuffer(bytearray(data), dtype=torch.uint8).to(dev)
+    cas = [PsdCascade(n) for _ in range(4)]
+    for c in cas:
+        c.set_detrend(Detrend.MIDPOINT)
+    dec = FrameDecoder()
+    loss = Loss()
+    dec.process_frames(cas, fr[:stride * 4096], flen, Loss())
+    for c in cas:
+        c.reset()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    info = dec.process_frames(cas, fr, flen, loss)
+    for c in cas:
+        c.sync()
+    dt = time.perf_counter() - t0
+    st, nf, lo, want = oracle_decode_stream(orc, data, flen, stride, nfr)
+    ok_loss = (loss.received, loss.dropped, loss.seq) == (lo.received, lo.dropped, lo.seq)
+    samples = 4 * info.samples_per_trace
+    return {"config": 3, "frames": nfr, "bytes": len(data), "trace_samples_total": int(samples),
+            "gpu_MSps_decode_plus_4_cascades": samples / dt / 1e6, "frame_GBps": len(data) / dt / 1e9,
+            "loss_bit_exact": bool(ok_loss), "received": int(loss.received), "dropped": int(loss.dropped)}
+
+
+def config5(dev, total, n_local, check):
+    import torch.distributed as dist
+    from stabilizer_stream_b200 import MergeOpts, PsdCascade, multi
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    d = dist if world > 1 else None
+    n = 4096
+    c = PsdCascade(n, device=dev.index)
+    if d is not None:
+        d.barrier()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    gen_s = [0.0]
+
+    def feed(lo, hi, sink):
+        pos = lo
+        while pos < hi:
+            b = pos // BLOCK
+            tg = time.perf_counter()
+            blk = noise_block(b, dev)
+            torch.cuda.synchronize()
+            gen_s[0] += time.perf_counter() - tg
+            a = pos - b * BLOCK
+            e = min(BLOCK, hi - b * BLOCK)
+            sink(blk[a:e])
+            pos = b * BLOCK + e
+
+    root = multi.time_chunked_psd(c, feed, total, n, d, 1, n_local, str(dev))
+    torch.cuda.synchronize()
+    if d is not None:
+        d.barrier()
+    dt = time.perf_counter() - t0
+    if rank != 0:
+        return None
+    p, b = root.psd(MergeOpts())
+    counts = [k.count for k in reversed(b)]
+    want = [s[1] for s in multi.stream_state(total, n, n // 2, multi.DRAIN[1])]
+    flat = all(bool(np.all(np.abs(p[k.start:k.start + len(k.bins)] * 0.5 - 1.0) < 10.0 / np.sqrt(k.count)))
+               for k in b if k.include and k.count >= 20)
+    out = {"config": 5, "samples": total, "world": world, "n_local": n_local, "stage_counts": counts,
+           "counts_match_closed_form": counts == want, "flat_10sigma": flat, "wall_s": dt,
+           "generation_s_rank0": gen_s[0], "MSps_excluding_generation": total / max(dt - gen_s[0], 1e-9) / 1e6,
+           "bins": int(p.size)}
+    if check and world > 1:
+        seq = PsdCascade(n, device=dev.index)
+        feed_stream(0, total, seq.process, dev)
+        ps, bs = seq.psd(MergeOpts())
+        out["max_rel_diff_vs_sequential"] = float(np.max(np.abs(p - ps) / np.maximum(ps, 1e-30)))
+        out["breaks_equal"] = [(k.count, k.pending, k.processed) for k in b] == [(k.count, k.pending, k.processed) for k in bs]
+    return out
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--config", type=int, required=True)
+    ap.add_argument("--total", type=float, default=4.8e9)
+    ap.add_argument("--n-local", type=int, default=5)
+    ap.add_argument("--check", action="store_true")
+    a = ap.parse_args()
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if int(os.environ.get("WORLD_SIZE", "1")) > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+    r = {1: lambda: config1(dev), 3: lambda: config3(dev), 5: lambda: config5(dev, int(a.total), a.n_local, a.check)}[a.config]()
+    if r is not None:
+        print(json.dumps(r))
+    if int(os.environ.get("WORLD_SIZE", "1")) > 1:
+        import torch.distributed as dist
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
