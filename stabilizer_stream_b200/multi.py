@@ -239,6 +239,7 @@ def time_chunked_psd(cascade, feed, total, n, dist=None, hbf=1, n_local=3, devic
     if world > 1:
         rows = acc[:n_local]
         rows, counts = reduce_partials(rows, counts, dist, dst=0)
+        torch.cuda.synchronize()
         # gather the stage-n_local slices (variable length) on rank 0
         meta = torch.tensor([first, tail.size], dtype=torch.int64, device=device)
         metas = [torch.empty_like(meta) for _ in range(world)] if rank == 0 else None
@@ -247,6 +248,8 @@ def time_chunked_psd(cascade, feed, total, n, dist=None, hbf=1, n_local=3, devic
         if rank != 0:
             return None
         tails = [(int(m[0].item()), t) for m, t in zip(metas, tails)]
+        # the reduction wrote into library memory on torch's stream; the library works on its own stream
+        torch.cuda.synchronize()
     else:
         tails = [(first, tail)]
     return finish_on_root(cascade, counts, tails, total, n, hbf, n_local)

@@ -253,9 +253,14 @@ class Psd:
     def set_detrend(self, d: Detrend):
         L.check(L.lib().sspsd_stage_set_detrend(self._h, int(d)))
 
-    def process(self, x):
-        """PsdStage::process(x, y) -> y[..n] (returned as a numpy array)."""
+    def process(self, x, out=None):
+        """PsdStage::process(x, y) -> y[..n].  Returns a numpy array, or a view of `out` (a CUDA float32
+        tensor that receives the decimated items on the device) when given."""
         ptr, n, mem, keep = _as_buffer(x)
+        if out is not None:
+            yl = C.c_size_t(out.numel())
+            L.check(L.lib().sspsd_stage_process_f32(self._h, ptr, n, mem, out.data_ptr(), C.byref(yl), L.MEM_DEVICE))
+            return out[:yl.value]
         y = np.zeros(n // 8 + self.n // 8 + 16, np.float32)
         yl = C.c_size_t(y.size)
         L.check(L.lib().sspsd_stage_process_f32(self._h, ptr, n, mem, y.ctypes.data, C.byref(yl), L.MEM_HOST))

@@ -30,6 +30,7 @@ def test_stage0_partials_sum_to_full_spectrum(oracle):
     assert np.max(np.abs(got - full.spectrum()) / full.spectrum()) < 1e-4
     # install the reduced row + count into rank 0's handle and read it back through psd()
     parts[0][1][0].copy_(total)
+    torch.cuda.synchronize()
     parts[0][0].set_counts([nseg])
     from stabilizer_stream_b200 import MergeOpts
     p, b = parts[0][0].psd(MergeOpts(keep_overlap=True, min_count=0, keep_transition_band=True))

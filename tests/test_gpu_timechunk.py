@@ -26,6 +26,7 @@ def run_emulated(x, n, world, n_local, hbf=1):
     for t in accs[1:]:
         total_acc += t[:n_local]
     accs[0][:n_local].copy_(total_acc)
+    torch.cuda.synchronize()   # torch's stream wrote into library memory; the library uses its own stream
     red = [sum(c[i] for c in counts) for i in range(n_local)]
     root = multi.finish_on_root(cas[0], red, tails, x.size, n, hbf, n_local)
     return root, plans
