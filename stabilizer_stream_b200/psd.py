@@ -111,7 +111,20 @@ def _as_buffer(x):
     return t.data_ptr(), t.numel(), mem, t
 
 
+def _default_stream(device):
+    """With torch in the process, order the handle's work on torch's current stream of that device, so
+    that device tensors handed to process() follow torch's usual stream-ordered lifetime rules (a
+    temporary tensor may be freed right after the call).  Without torch: a private stream."""
+    import sys
+    torch = sys.modules.get("torch")
+    if torch is None or not torch.cuda.is_available() or not torch.cuda.is_initialized():
+        return None
+    return torch.cuda.current_stream(device).cuda_stream
+
+
 def _config(n, window, hbf, device, stream, max_batch, host_stage):
+    if stream is None:
+        stream = _default_stream(device)
     cfg = L.Config()
     L.check(L.lib().sspsd_config_default(n, C.byref(cfg)))
     cfg.window = int(window)
@@ -344,6 +357,8 @@ class FrameDecoder:
 
     def __init__(self, device=0, stream=None):
         h = C.c_void_p()
+        if stream is None:
+            stream = _default_stream(device)
         L.check(L.lib().sspsd_decoder_create(device, stream, C.byref(h)))
         self._h = h
 
