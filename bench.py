@@ -212,7 +212,7 @@ def run_ours(args):
     # reads out at frame rate, i.e. every few 1e6 samples of a 200 MS/s stream, not every batch).
     # `value_readout_every_step` repeats the measurement with a psd() readout after every step.
     def device_run(readout_every_step):
-        c = PsdCascade(N_FFT, device=local, stream=stream.cuda_stream)
+        c = PsdCascade(N_FFT, device=local, stream=stream.cuda_stream or 1)
         c.profile_enable(True)
         for _ in range(args.warmup):
             c.process(x)
@@ -246,7 +246,7 @@ def run_ours(args):
     value_rs = world * SAMPLES_PER_STEP * args.steps / (ms_rs * 1e-3) / 1e6
 
     # ---- end-to-end run: host pinned input, H2D inside the timed region, spectra read back ----
-    c2 = PsdCascade(N_FFT, device=local, stream=stream.cuda_stream)
+    c2 = PsdCascade(N_FFT, device=local, stream=stream.cuda_stream or 1)
     e2e_steps = max(1, min(args.steps, 5))
     ms2, p2, b2 = timed(c2, xh, e2e_steps, min(args.warmup, 2))
     e2e_value = world * SAMPLES_PER_STEP * e2e_steps / (ms2 * 1e-3) / 1e6

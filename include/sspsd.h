@@ -74,7 +74,8 @@ typedef struct {
     int32_t window;      /* SSPSD_WINDOW_*; PsdCascade::default() uses Hann, src/psd.rs:419 */
     int32_t hbf;         /* SSPSD_HBF_* */
     int32_t device;      /* CUDA device ordinal */
-    void *stream;        /* cudaStream_t to order all work on, or NULL for a private stream */
+    void *stream;        /* cudaStream_t to order all work on (cudaStreamLegacy / cudaStreamPerThread are
+                            accepted), or NULL for a private non-blocking stream */
     uint64_t max_batch;  /* largest number of samples handed to one kernel batch (0 = default 1<<28) */
     uint64_t host_stage; /* host-pointer process() calls are staged in pinned memory and launched once
                             this many samples are pending (0 = default 1<<22); psd()/set_*()/flush() launch

@@ -119,7 +119,10 @@ def _default_stream(device):
     torch = sys.modules.get("torch")
     if torch is None or not torch.cuda.is_available() or not torch.cuda.is_initialized():
         return None
-    return torch.cuda.current_stream(device).cuda_stream
+    h = torch.cuda.current_stream(device).cuda_stream
+    # torch's default stream is the legacy NULL stream; a NULL cfg.stream means "private stream" in the
+    # C ABI, so name the legacy stream explicitly (cudaStreamLegacy == (cudaStream_t)1)
+    return h if h else 1
 
 
 def _config(n, window, hbf, device, stream, max_batch, host_stage):

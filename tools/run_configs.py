@@ -149,6 +149,12 @@ def config5(dev, total, n_local, check):
         feed_stream(0, total, seq.process, dev)
         ps, bs = seq.psd(MergeOpts())
         out["max_rel_diff_vs_sequential"] = float(np.max(np.abs(p - ps) / np.maximum(ps, 1e-30)))
+        o = MergeOpts(keep_overlap=True, min_count=0, keep_transition_band=True)
+        pk, bk = root.psd(o)
+        psk, bsk = seq.psd(o)
+        out["per_stage_max_rel"] = {str(k.decimation): float(np.max(np.abs(pk[k.start:k.start + len(k.bins)] - psk[k.start:k.start + len(k.bins)])
+                                                                      / np.maximum(psk[k.start:k.start + len(k.bins)], 1e-30)))
+                                    for k in bk if k.count}
         out["breaks_equal"] = [(k.count, k.pending, k.processed) for k in b] == [(k.count, k.pending, k.processed) for k in bs]
     return out
 
