@@ -114,9 +114,15 @@ def config5(dev, total, n_local, check):
     feed_stream(lo, hi, lambda t: parts.append(t.clone()), dev)
     xs = torch.cat(parts)
     del parts
+    # warm-up pass of the whole pipeline on a short stream: NCCL connections (reduce, gather), library
+    # buffers and kernels are set up outside the timed region
+    wtotal = 400_000_000
+    multi.time_chunked_psd(PsdCascade(n, device=dev.index),
+                           lambda a, b, sink: sink((torch.rand(b - a, device=dev) - 0.5) * (12 ** 0.5)),
+                           wtotal, n, d, 1, min(n_local, 4), str(dev))
+    c.process(xs[:1 << 22])   # allocates the handle's buffers
+    c.reset()
     if d is not None:
-        w = torch.zeros(1, device=dev)
-        d.all_reduce(w)   # communicator set-up outside the timed region
         d.barrier()
     torch.cuda.synchronize()
     t0 = time.perf_counter()
