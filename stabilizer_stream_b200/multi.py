@@ -220,36 +220,64 @@ def finish_on_root(root, reduced_counts, tails, total, n, hbf, n_local):
     return root
 
 
-def time_chunked_psd(cascade, feed, total, n, dist=None, hbf=1, n_local=3, device="cuda"):
+def time_chunked_psd(cascade, feed, total, n, dist=None, hbf=1, n_local=3, device="cuda", timings=None):
     """Distributed driver of the time-chunked mode: every rank calls this with a FRESH cascade and a
     callable feed(lo, hi, sink) that pushes stream samples [lo, hi) into sink(x) in order (any block
     size).  One NCCL sum-reduction of the local stages' accumulator rows + counts, one gather of the
     (tiny) stage-n_local stream slices; rank 0 returns its completed cascade (call .psd() on it), the
-    other ranks return None."""
+    other ranks return None.  `timings` (dict) receives wall-clock seconds per phase."""
+    import time
+
     import torch
     world = dist.get_world_size() if dist is not None else 1
     rank = dist.get_rank() if dist is not None else 0
+    t = [time.perf_counter()]
+
+    def lap(name):
+        if timings is not None:
+            torch.cuda.synchronize()
+            now = time.perf_counter()
+            timings[name] = now - t[0]
+            t[0] = now
+
     plan = plan_time_chunks(total, world, n, hbf, n_local)[rank]
     cascade.seek(plan["feed_lo"])
     cascade.set_window(plan["own_lo"], plan["own_hi"], n_local)
     feed(plan["feed_lo"], plan["feed_hi"], cascade.process)
     first, tail = cascade.take_tail(plan["tail_lo"], plan["tail_hi"] if plan["tail_hi"] is not None else 2 ** 63)
+    lap("process+tail")
     acc, counts = cascade_partials_tensor(cascade)
     counts = (counts + [0] * 16)[:n_local]
     if world > 1:
-        rows = acc[:n_local]
-        rows, counts = reduce_partials(rows, counts, dist, dst=0)
+        # ONE collective for the readout: accumulator rows of the local stages, their counts and the
+        # rank's slice of the stage-n_local stream travel in one buffer; rows and counts are summed, the
+        # slices land in disjoint slots (everybody else contributes zeros there)
+        stride = acc.shape[1]
+        slot = (stream_state(total, n, n // 2, DRAIN[hbf]) + [(0, 0, 0)] * 16)[n_local][0] // world + 64
+        buf = torch.zeros(n_local * stride + n_local + world * (slot + 2), dtype=torch.float64, device=device)
+        buf[:n_local * stride] = acc[:n_local].reshape(-1).double()
+        buf[n_local * stride:n_local * stride + n_local] = torch.tensor(counts, dtype=torch.float64, device=device)
+        base = n_local * stride + n_local + rank * (slot + 2)
+        assert tail.size <= slot, "tail slice larger than its slot"
+        buf[base] = float(first)
+        buf[base + 1] = float(tail.size)
+        if tail.size:
+            buf[base + 2:base + 2 + tail.size] = torch.from_numpy(tail).to(device).double()
+        dist.reduce(buf, dst=0, op=dist.ReduceOp.SUM)
         torch.cuda.synchronize()
-        # gather the stage-n_local slices (variable length) on rank 0
-        meta = torch.tensor([first, tail.size], dtype=torch.int64, device=device)
-        metas = [torch.empty_like(meta) for _ in range(world)] if rank == 0 else None
-        dist.gather(meta, metas, dst=0)
-        tails = gather_spectra(tail, dist, torch.device(device), dst=0)
+        lap("reduce")
         if rank != 0:
             return None
-        tails = [(int(m[0].item()), t) for m, t in zip(metas, tails)]
-        # the reduction wrote into library memory on torch's stream; the library works on its own stream
+        acc[:n_local] = buf[:n_local * stride].reshape(n_local, stride).float()
+        counts = [int(v) for v in buf[n_local * stride:n_local * stride + n_local].round().tolist()]
+        host = buf[n_local * stride + n_local:].cpu().numpy()
+        tails = []
+        for r in range(world):
+            seg = host[r * (slot + 2):(r + 1) * (slot + 2)]
+            tails.append((int(seg[0]), seg[2:2 + int(seg[1])].astype(np.float32)))
         torch.cuda.synchronize()
     else:
         tails = [(first, tail)]
-    return finish_on_root(cascade, counts, tails, total, n, hbf, n_local)
+    root = finish_on_root(cascade, counts, tails, total, n, hbf, n_local)
+    lap("finish")
+    return root

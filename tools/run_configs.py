@@ -132,7 +132,8 @@ def config5(dev, total, n_local, check):
         assert a == lo and b == hi
         sink(xs)
 
-    root = multi.time_chunked_psd(c, feed, total, n, d, 1, n_local, str(dev))
+    tim = {}
+    root = multi.time_chunked_psd(c, feed, total, n, d, 1, n_local, str(dev), tim)
     torch.cuda.synchronize()
     if d is not None:
         d.barrier()
@@ -146,7 +147,7 @@ def config5(dev, total, n_local, check):
                for k in b if k.include and k.count >= 20)
     out = {"config": 5, "samples": total, "world": world, "n_local": n_local, "stage_counts": counts,
            "counts_match_closed_form": counts == want, "flat_10sigma": flat, "wall_s": dt,
-           "MSps": total / dt / 1e6, "halo_overhead": (hi - lo) * world / total - 1 if world > 1 else 0.0,
+           "MSps": total / dt / 1e6, "phases_s_rank0": tim, "halo_overhead": (hi - lo) * world / total - 1 if world > 1 else 0.0,
            "bins": int(p.size)}
     if check and world > 1:
         seq = PsdCascade(n, device=dev.index)
