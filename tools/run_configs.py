@@ -48,10 +48,10 @@ def config1(dev):
     x = torch.cat([noise_block(b, dev) for b in range(total // BLOCK)])
     s = Psd(n)
     ybuf = torch.empty(total // 8 + n, device=dev)
-    s.process(x[:1 << 22], out=ybuf)
+    s.process(x, out=ybuf)   # first pass: allocates the handle's buffers at their final size
     torch.cuda.synchronize()
     t0 = time.perf_counter()
-    y = s.process(x, out=ybuf)
+    y = s.process(x, out=ybuf)   # timed: second pass over the same 2^28 samples (the stream simply continues)
     torch.cuda.synchronize()
     dt = time.perf_counter() - t0
     p = s.spectrum() / s.gain()
