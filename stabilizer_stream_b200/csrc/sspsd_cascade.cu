@@ -59,7 +59,7 @@ template <int LOG2N>
 int prepare_stage_t(int hop, int budget_bytes, int* tmax)
 {
     using PL = Plan<LOG2N>;
-    int t = 64;
+    int t = 256;
     while (t > 1 && (long long)stage_smem_bytes<LOG2N>(t, hop) > budget_bytes)
         --t;
     if ((long long)stage_smem_bytes<LOG2N>(t, hop) > budget_bytes) {
@@ -432,7 +432,16 @@ int Cascade::launch_psd(size_t i, const StreamSrc& src, uint64_t k0, uint64_t ns
         prof_end(stage_stream(i));
         return cuda_ok(cudaGetLastError(), "psd_stage_kernel_ring launch") ? SSPSD_OK : SSPSD_ECUDA;
     }
-    p.T = (int)std::max<long long>(1, std::min<long long>(t, tmax_));
+    const bool tiled_r16 = log2n_ == 12 && use_r16();
+    if (tiled_r16) {
+        p.T = (int)std::max<long long>(1, std::min<long long>(t, tmax_));
+    } else {
+        // persistent tiled kernel: tiles as large as shared memory allows once there is enough work, CTAs
+        // (2 per SM) walk over contiguous ranges of tiles
+        int groups = std::max(1, nt_ / (int)(n_ / 16));
+        p.T = (int)std::max<long long>(std::min<long long>(groups, (long long)nseg), std::min<long long>(t, tmax_));
+        p.T = std::min(p.T, tmax_);
+    }
     p.hop = (int)hop_;
     p.detrend = detrend_;
     p.tile_cap = (p.T - 1) * (int)hop_ + (int)n_;
@@ -443,7 +452,9 @@ int Cascade::launch_psd(size_t i, const StreamSrc& src, uint64_t k0, uint64_t ns
     p.jb = jb;
     p.g_first = g_first;
     p.g_s = g_s;
-    int grid = (int)((nseg + p.T - 1) / p.T);
+    long long ntiles = ((long long)nseg + p.T - 1) / p.T;
+    p.tpc = tiled_r16 ? 1 : (int)std::max<long long>(1, (ntiles + 2ll * num_sms_ - 1) / (2ll * num_sms_));
+    int grid = (int)((ntiles + p.tpc - 1) / p.tpc);
     prof_begin(i == 0 ? SSPSD_PROF_PSD_STAGE0 : SSPSD_PROF_PSD_DEEP, nseg * (uint64_t)hop_, stage_stream(i));
     int rc = launch_stage((int)log2n_, p, grid, stage_stream(i));
     prof_end(stage_stream(i));

@@ -1,11 +1,13 @@
 // sspsd_stage_kernel.cuh -- K2: fused detrend + window + real FFT + |X|^2 accumulate for one
 // PSD stage (reference src/psd.rs:210-233, one iteration of the `while` loop per segment).
 //
-// One CTA loads a tile of `T` consecutive hops (+ the overlap) of the stage's stream into shared
-// memory once (every sample crosses HBM once; the 50 % overlap is served from shared memory) and
-// transforms its segments with groups of TPS = N/16 threads.  |X|^2 is accumulated in registers
-// over all segments of the tile (each thread owns the same 8 bins for every segment) and flushed
-// with one atomicAdd per bin per thread at the end.
+// Generic version for N = 64 ... 8192 (N = 4096 has its own kernels).  A persistent CTA walks over a
+// contiguous range of tiles; a tile is `T` consecutive hops (+ the overlap) of the stage's stream,
+// brought into one of two shared-memory buffers by TMA bulk copies (every sample crosses HBM once; the
+// 50 % overlap is served from shared memory; tile t+1 streams in while tile t is transformed).  The
+// segments of a tile are transformed by groups of TPS = N/16 threads.  |X|^2 is accumulated in
+// registers over ALL tiles of the CTA (each thread owns the same 8 bins for every segment) and
+// flushed with one atomicAdd per bin per thread at the end.
 #pragma once
 #include "sspsd_device.cuh"
 
@@ -15,7 +17,8 @@ struct StageParams {
     StreamSrc src;
     long long k0;      // global index of the first segment of this launch
     int nseg;          // segments in this launch
-    int T;             // segments per CTA
+    int T;             // segments per tile (ring kernel: segments per CTA)
+    int tpc;           // tiles per CTA (persistent tiled kernel)
     int hop;           // N - overlap
     int detrend;       // SSPSD_DETREND_*
     int tile_cap;      // floats reserved for the tile in shared memory
@@ -144,34 +147,35 @@ psd_stage_kernel(const StageParams p)
     using PL = Plan<LOG2N>;
     constexpr int N = PL::N, M = PL::M, TPS = PL::TPS, NT = PL::NT, G = PL::G, K = PL::K, WS = PL::WS;
     extern __shared__ __align__(16) float smem[];
-    float* tile = smem;
-    float* wsb = smem + p.tile_cap;
+    float* tiles = smem;                       // 2 * p.tile_cap
+    float* wsb = smem + 2 * p.tile_cap;
     float* wgt = wsb + G * 2 * WS;
     float* red = wgt + ((p.T + 3) & ~3);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(red + ((G * (TPS > 32 ? TPS / 32 : 1) + 1) & ~1));
 
     const int tid = threadIdx.x;
     const int group = tid / TPS;
     const int j = tid % TPS;
     const int hop = p.hop;
-    const int seg0 = blockIdx.x * p.T;
-    const int ns = min(p.T, p.nseg - seg0);
-    const long long g0 = (p.k0 + seg0) * (long long)hop;
-    const int tile_len = (ns - 1) * hop + N;
+    const int ntiles = (p.nseg + p.T - 1) / p.T;
+    const int tile0 = blockIdx.x * p.tpc;
+    const int tile1 = min(tile0 + p.tpc, ntiles);
 
-    // ---- tile load: coalesced 128-bit loads, every sample read from HBM once ----
-    for (int v = tid; v < tile_len / 4; v += NT)
-        reinterpret_cast<float4*>(tile)[v] = ld_stream4(p.src, g0 + 4ll * v);
-
-    // ---- per-segment averaging weights (0.25 folds the /2 of the real-input split) ----
-    if (tid < ns) {
-        int jj = seg0 + tid;
-        int n_s = p.nseg - 1 - max(jj, p.jb);
-        double w = 1.0;
-        if (n_s > 0)
-            w = pow((double)p.g_s, (double)n_s);
-        if (jj < p.jb && p.jb < p.nseg)
-            w *= (double)p.g_first;
-        wgt[tid] = (float)(0.25 * w);
+    auto issue_tile = [&](int tl) {
+        const int s0 = tl * p.T;
+        const int n_s = min(p.T, p.nseg - s0);
+        const int b = (tl - tile0) & 1;
+        ring_issue(p.src, (p.k0 + s0) * (long long)hop, (n_s - 1) * hop + N, tiles + b * p.tile_cap, &bars[b]);
+    };
+    if (tid == 0) {
+        mbar_init(&bars[0], 1);
+        mbar_init(&bars[1], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    if (tid == 0 && tile0 < tile1) {
+        issue_tile(tile0);
+        if (tile0 + 1 < tile1) issue_tile(tile0 + 1);
     }
 
     // ---- segment-invariant per-thread constants ----
@@ -214,6 +218,23 @@ psd_stage_kernel(const StageParams p)
     for (int i = 0; i < 8; ++i) acc[i] = 0.f;
     float accx = 0.f;
 
+    for (int tl = tile0; tl < tile1; ++tl) {
+    const int buf = (tl - tile0) & 1;
+    const int seg0 = tl * p.T;
+    const int ns = min(p.T, p.nseg - seg0);
+    const float* tile = tiles + buf * p.tile_cap;
+    // per-segment averaging weights of this tile (0.25 folds the /2 of the real-input split)
+    for (int i = tid; i < ns; i += NT) {
+        int jj = seg0 + i;
+        int n_s = p.nseg - 1 - max(jj, p.jb);
+        double w = 1.0;
+        if (n_s > 0)
+            w = pow((double)p.g_s, (double)n_s);
+        if (jj < p.jb && p.jb < p.nseg)
+            w *= (double)p.g_first;
+        wgt[i] = (float)(0.25 * w);
+    }
+    mbar_wait(&bars[buf], (uint32_t)((tl - tile0) >> 1) & 1u);
     __syncthreads();
 
     const int iters = (ns + G - 1) / G;
@@ -322,6 +343,11 @@ psd_stage_kernel(const StageParams p)
         }
     }
 
+    // every thread is done with this tile buffer and weight table: refill it with tile tl + 2
+    __syncthreads();
+    if (tid == 0 && tl + 2 < tile1) issue_tile(tl + 2);
+    }  // tiles
+
     // ---- flush: one atomic per owned bin ----
     if (j != 0) {
 #pragma unroll
@@ -349,8 +375,9 @@ inline size_t stage_smem_bytes(int T, int hop)
 {
     using PL = Plan<LOG2N>;
     size_t tile = (size_t)(T - 1) * hop + PL::N;
-    size_t fl = tile + (size_t)PL::G * 2 * PL::WS + ((T + 3) & ~3) + (size_t)PL::G * (PL::TPS > 32 ? PL::TPS / 32 : 1);
-    return fl * sizeof(float);
+    size_t redn = ((size_t)PL::G * (PL::TPS > 32 ? PL::TPS / 32 : 1) + 1) & ~(size_t)1;
+    size_t fl = 2 * tile + (size_t)PL::G * 2 * PL::WS + ((T + 3) & ~3) + redn;
+    return fl * sizeof(float) + 2 * sizeof(uint64_t);
 }
 
 }  // namespace sspsd

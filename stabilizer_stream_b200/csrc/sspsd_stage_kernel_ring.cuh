@@ -24,53 +24,6 @@ struct RingCfg {
     static constexpr int MAX_W = 2048;    // per-CTA weight table (segments per CTA upper bound)
 };
 
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count)
-{
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes)
-{
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity)
-{
-    asm volatile(
-        "{\n\t"
-        ".reg .pred p;\n\t"
-        "WAIT_%=:\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
-        "@p bra DONE_%=;\n\t"
-        "bra WAIT_%=;\n\t"
-        "DONE_%=:\n\t"
-        "}" ::"r"(smem_u32(bar)),
-        "r"(parity)
-        : "memory");
-}
-// 1-D TMA bulk copy global -> shared, completion reported to an mbarrier in bytes
-__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar)
-{
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-                     smem_u32(dst)),
-                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
-                 : "memory");
-}
-
-// issue the copies of stream samples [g, g + n) into dst (n multiple of 4, g multiple of 4)
-__device__ __forceinline__ void ring_issue(const StreamSrc& s, long long g, int n, float* dst, uint64_t* bar)
-{
-    mbar_expect_tx(bar, (uint32_t)n * 4u);
-    long long nc = s.split - g;  // samples that live in the carry
-    if (nc > n) nc = n;
-    if (nc > 0) {
-        bulk_g2s(dst, s.carry + (g - s.carry_start), (uint32_t)nc * 4u, bar);
-    } else {
-        nc = 0;
-    }
-    if (nc < n) bulk_g2s(dst + nc, s.fresh + (g + nc - s.split), (uint32_t)(n - nc) * 4u, bar);
-}
-
 __global__ void __launch_bounds__(R16::NT, 2) psd_stage_kernel_ring(const StageParams p)
 {
     constexpr int N = R16::N, M = R16::M, TPS = R16::TPS, NT = R16::NT, G = R16::G, K = R16::K, WS = R16::WS;
