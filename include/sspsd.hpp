@@ -1,0 +1,271 @@
+// sspsd.hpp -- header-only C++17 mirror of the reference's Rust API on top of the C ABI (sspsd.h).
+//
+// Same names, argument meaning and error behaviour as quartiq/stabilizer-stream:
+//   PsdCascade<N>  src/psd.rs:399-544      Psd<N> / PsdStage  src/psd.rs:119-288
+//   Break          src/psd.rs:290-337      MergeOpts / AvgOpts src/psd.rs:339-376
+//   Detrend        src/psd.rs:59-72        Window              src/psd.rs:12-56
+//   Loss           src/loss.rs:4-38        FrameDecoder        src/de/frame.rs:49-60 + src/de/data.rs
+//   Var            src/var.rs:4-45
+// The reference's PSD API is infallible (it panics on programming errors such as Detrend::Linear,
+// src/psd.rs:110); here such conditions throw sspsd::Error.  Decode errors map de::Error
+// (src/de/mod.rs:19-27) onto DecodeError::status.
+#pragma once
+#include <cstddef>
+#include <cstdint>
+#include <limits>
+#include <stdexcept>
+#include <string>
+#include <utility>
+#include <vector>
+
+#include "sspsd.h"
+
+namespace sspsd {
+
+struct Error : std::runtime_error {
+    int32_t status;
+    Error(int32_t st, const char* msg) : std::runtime_error(std::string(msg ? msg : "")), status(st) {}
+};
+
+inline void check(int32_t st)
+{
+    if (st != SSPSD_OK) throw Error(st, sspsd_last_error());
+}
+
+/// enum Detrend, src/psd.rs:59-72
+enum class Detrend : int32_t { None = 0, Midpoint = 1, Span = 2, Mean = 3, Linear = 4 };
+/// Window::rectangular / Window::hann, src/psd.rs:24-55
+enum class Window : int32_t { Rectangular = 0, Hann = 1 };
+enum class Mem : int32_t { Host = SSPSD_MEM_HOST, Device = SSPSD_MEM_DEVICE };
+
+/// src/psd.rs:360-376
+struct AvgOpts {
+    uint32_t limit = std::numeric_limits<uint32_t>::max();
+    uint32_t count = std::numeric_limits<uint32_t>::max();
+};
+
+/// src/psd.rs:339-358
+struct MergeOpts {
+    bool keep_overlap = false;
+    uint32_t min_count = 1;
+    bool keep_transition_band = false;
+};
+
+/// src/psd.rs:290-337
+struct Break {
+    size_t start;
+    bool include;
+    uint32_t count;
+    uint32_t avg;
+    std::pair<size_t, size_t> bins;  // Range<usize>: [first, second)
+    size_t fft_size;
+    size_t decimation;
+    size_t pending;
+    size_t processed;
+
+    size_t effective_fft_size() const { return fft_size * decimation; }
+    float rbw() const { return 1.0f / (float)effective_fft_size(); }
+
+    /// Break::frequencies, src/psd.rs:315-327
+    static std::vector<float> frequencies(const std::vector<Break>& b)
+    {
+        std::vector<float> f;
+        for (const auto& bi : b) {
+            if (!bi.include) continue;
+            float r = bi.rbw();
+            for (size_t k = bi.bins.first; k < bi.bins.second; ++k) f.push_back((float)k * r);
+        }
+        return f;
+    }
+};
+
+/// PsdCascade<N>, src/psd.rs:399-544.  Default construction == PsdCascade::<N>::default().
+template <size_t N>
+class PsdCascade {
+public:
+    explicit PsdCascade(int device = 0, void* stream = nullptr, int32_t hbf = SSPSD_HBF_140)
+    {
+        sspsd_config cfg;
+        check(sspsd_config_default((uint32_t)N, &cfg));
+        cfg.device = device;
+        cfg.stream = stream;
+        cfg.hbf = hbf;
+        check(sspsd_cascade_create(&cfg, &h_));
+    }
+    PsdCascade(const PsdCascade& o) { check(sspsd_cascade_clone(o.h_, &h_)); }  // #[derive(Clone)]
+    PsdCascade& operator=(const PsdCascade& o)
+    {
+        if (this != &o) {
+            sspsd_cascade* n = nullptr;
+            check(sspsd_cascade_clone(o.h_, &n));
+            sspsd_cascade_destroy(h_);
+            h_ = n;
+        }
+        return *this;
+    }
+    PsdCascade(PsdCascade&& o) noexcept : h_(o.h_) { o.h_ = nullptr; }
+    ~PsdCascade() { sspsd_cascade_destroy(h_); }
+
+    float rbw() const
+    {
+        float r;
+        check(sspsd_cascade_rbw(h_, &r));
+        return r;
+    }
+    void set_avg(AvgOpts a) { check(sspsd_cascade_set_avg(h_, sspsd_avg_opts{a.limit, a.count})); }
+    void set_detrend(Detrend d) { check(sspsd_cascade_set_detrend(h_, (int32_t)d)); }
+    /// process(&mut self, x: &[f32])
+    void process(const float* x, size_t n, Mem mem = Mem::Host) { check(sspsd_cascade_process_f32(h_, x, n, (int32_t)mem)); }
+    void process(const std::vector<float>& x) { process(x.data(), x.size()); }
+    /// psd(&self, &MergeOpts) -> (Vec<f32>, Vec<Break>)
+    std::pair<std::vector<float>, std::vector<Break>> psd(const MergeOpts& o = MergeOpts()) const
+    {
+        sspsd_merge_opts mo{o.keep_overlap, o.min_count, o.keep_transition_band};
+        std::vector<float> p(SSPSD_MAX_STAGES * (N / 2 + 1));
+        sspsd_break cb[SSPSD_MAX_STAGES];
+        size_t pl = p.size(), bl = SSPSD_MAX_STAGES;
+        check(sspsd_cascade_psd(h_, &mo, p.data(), &pl, cb, &bl));
+        p.resize(pl);
+        std::vector<Break> b;
+        for (size_t i = 0; i < bl; ++i)
+            b.push_back(Break{(size_t)cb[i].start, cb[i].include != 0, cb[i].count, cb[i].avg,
+                              {(size_t)cb[i].bins_start, (size_t)cb[i].bins_end}, (size_t)cb[i].fft_size,
+                              (size_t)cb[i].decimation, (size_t)cb[i].pending, (size_t)cb[i].processed});
+        return {std::move(p), std::move(b)};
+    }
+    void reset() { check(sspsd_cascade_reset(h_)); }
+    void sync() { check(sspsd_cascade_sync(h_)); }
+    sspsd_cascade* handle() const { return h_; }
+
+private:
+    sspsd_cascade* h_ = nullptr;
+};
+
+/// Psd<N> + trait PsdStage, src/psd.rs:119-288
+template <size_t N>
+class Psd {
+public:
+    explicit Psd(Window w = Window::Hann, int device = 0, void* stream = nullptr)
+    {
+        sspsd_config cfg;
+        check(sspsd_config_default((uint32_t)N, &cfg));
+        cfg.window = (int32_t)w;
+        cfg.device = device;
+        cfg.stream = stream;
+        check(sspsd_stage_create(&cfg, &h_));
+    }
+    Psd(const Psd&) = delete;
+    Psd& operator=(const Psd&) = delete;
+    ~Psd() { sspsd_stage_destroy(h_); }
+    void set_avg(uint32_t avg) { check(sspsd_stage_set_avg(h_, avg)); }
+    void set_detrend(Detrend d) { check(sspsd_stage_set_detrend(h_, (int32_t)d)); }
+    /// process(x, y) -> number of items written to y
+    size_t process(const float* x, size_t n, float* y, size_t y_cap, Mem xm = Mem::Host, Mem ym = Mem::Host)
+    {
+        size_t yl = y_cap;
+        check(sspsd_stage_process_f32(h_, x, n, (int32_t)xm, y, &yl, (int32_t)ym));
+        return yl;
+    }
+    std::vector<float> spectrum()
+    {
+        std::vector<float> s(N / 2 + 1);
+        size_t l = s.size();
+        check(sspsd_stage_spectrum(h_, s.data(), &l, SSPSD_MEM_HOST));
+        return s;
+    }
+    uint32_t count()
+    {
+        uint32_t c;
+        check(sspsd_stage_count(h_, &c));
+        return c;
+    }
+    float gain()
+    {
+        float g;
+        check(sspsd_stage_gain(h_, &g));
+        return g;
+    }
+    std::vector<float> buf()
+    {
+        std::vector<float> b(N);
+        size_t l = b.size();
+        check(sspsd_stage_buf(h_, b.data(), &l, SSPSD_MEM_HOST));
+        b.resize(l);
+        return b;
+    }
+
+private:
+    sspsd_stage* h_ = nullptr;
+};
+
+/// struct Loss, src/loss.rs:4-38
+struct Loss {
+    sspsd_loss c{0, 0, 0, 0};
+    void update(uint32_t seq, uint8_t batches) { sspsd_loss_update(&c, seq, batches); }
+    float ratio() const { return sspsd_loss_ratio(&c); }
+};
+
+struct DecodeError : std::runtime_error {
+    int32_t status;       // SSPSD_EHEADER / EFORMAT / ESIZE (de::Error) or EBATCHES / ESHORT (reference panics)
+    uint64_t frames_ok;   // frames decoded (and accounted in Loss) before the malformed one
+    DecodeError(int32_t st, uint64_t ok) : std::runtime_error("malformed frame"), status(st), frames_ok(ok) {}
+};
+
+/// Batched Frame::from_bytes + Loss::update + Payload::traces
+class FrameDecoder {
+public:
+    explicit FrameDecoder(int device = 0, void* stream = nullptr) { check(sspsd_decoder_create(device, stream, &d_)); }
+    FrameDecoder(const FrameDecoder&) = delete;
+    ~FrameDecoder() { sspsd_decoder_destroy(d_); }
+    /// n_frames equally sized frames -> traces[t] (host vectors, resized); returns the batch info
+    sspsd_decode_info decode(const uint8_t* frames, size_t n_frames, size_t frame_len, Loss* loss,
+                             std::vector<float> (&traces)[SSPSD_MAX_TRACES], size_t frame_stride = 0)
+    {
+        if (!frame_stride) frame_stride = frame_len;
+        size_t payload = frame_len > SSPSD_HEADER_SIZE ? frame_len - SSPSD_HEADER_SIZE : 0;
+        size_t cap = n_frames * std::max<size_t>(payload / 64 * 8, payload / 24) + 1;
+        float* ptr[SSPSD_MAX_TRACES];
+        for (int t = 0; t < SSPSD_MAX_TRACES; ++t) {
+            traces[t].assign(cap, 0.f);
+            ptr[t] = traces[t].data();
+        }
+        sspsd_decode_info info{};
+        int32_t st = sspsd_decode_frames(d_, frames, n_frames, frame_len, frame_stride, SSPSD_MEM_HOST,
+                                         loss ? &loss->c : nullptr, ptr, cap, SSPSD_MEM_HOST, &info);
+        for (int t = 0; t < SSPSD_MAX_TRACES; ++t) traces[t].resize(t < (int)info.n_traces ? info.samples_per_trace : 0);
+        if (st >= SSPSD_EHEADER && st <= SSPSD_ESHORT && info.frames_ok < n_frames) throw DecodeError(st, info.frames_ok);
+        check(st);
+        return info;
+    }
+    template <size_t N>
+    sspsd_decode_info process_frames(PsdCascade<N>* const* cascades, uint32_t n, const uint8_t* frames, size_t n_frames,
+                                     size_t frame_len, Loss* loss, Mem mem = Mem::Host)
+    {
+        sspsd_cascade* hs[SSPSD_MAX_TRACES] = {nullptr, nullptr, nullptr, nullptr};
+        for (uint32_t t = 0; t < n && t < SSPSD_MAX_TRACES; ++t) hs[t] = cascades[t] ? cascades[t]->handle() : nullptr;
+        sspsd_decode_info info{};
+        int32_t st = sspsd_cascade_process_frames(d_, hs, n, frames, n_frames, frame_len, frame_len, (int32_t)mem,
+                                                  loss ? &loss->c : nullptr, &info);
+        if (st >= SSPSD_EHEADER && st <= SSPSD_ESHORT && info.frames_ok < n_frames) throw DecodeError(st, info.frames_ok);
+        check(st);
+        return info;
+    }
+
+private:
+    sspsd_decoder* d_ = nullptr;
+};
+
+/// struct Var + VarBuilder defaults, src/var.rs:4-45
+struct Var {
+    int32_t x_exp = -2;
+    int32_t sinx_exp = 4;
+    float clip = std::numeric_limits<float>::max();
+    size_t dc_cut = 2;
+    float eval(const std::vector<float>& phase_psd, const std::vector<float>& frequencies, float tau) const
+    {
+        sspsd_var v{x_exp, sinx_exp, clip, 0, dc_cut};
+        return sspsd_var_eval(&v, phase_psd.data(), frequencies.data(), std::min(phase_psd.size(), frequencies.size()), tau);
+    }
+};
+
+}  // namespace sspsd

@@ -301,10 +301,10 @@ int Cascade::init(const sspsd_config& cfg, uint32_t max_stages)
         own_stream_ = true;
     }
     SSPSD_CUDA(cudaStreamCreateWithFlags(&copy_stream_, cudaStreamNonBlocking));
-    // Optional second stream for stages >= 1 (SSPSD_OVERLAP=1).  Off by default: the persistent stage-0
-    // kernel holds every SM slot, so on one stream of large batches the overlap measured slower
-    // (146 vs 164 GS/s, profiles/r01_ncu_summary.md); it pays for many small concurrent batches only.
-    if (max_stages_ > 1 && getenv("SSPSD_OVERLAP")) {
+    // Optional second (high priority) stream for the deep stages >= SSPSD_OVERLAP (e.g. 2): their many
+    // small launches then hide behind the next batch's stage-0/1 kernels instead of adding their latency.
+    if (max_stages_ > 1 && getenv("SSPSD_OVERLAP") && atoi(getenv("SSPSD_OVERLAP")) > 0) {
+        deep_from_ = (size_t)atoi(getenv("SSPSD_OVERLAP"));
         // high priority: the small deep-stage grids should be scheduled ahead of the remaining stage-0 CTAs
         int lo_prio = 0, hi_prio = 0;
         SSPSD_CUDA(cudaDeviceGetStreamPriorityRange(&lo_prio, &hi_prio));
@@ -414,7 +414,7 @@ int Cascade::launch_psd(size_t i, const StreamSrc& src, uint64_t k0, uint64_t ns
         // persistent kernel: two CTAs per SM, each streams through a contiguous range of segments
         // with the deep stages overlapping on a second stream, stage 0 is cut into ~4 waves of CTAs so
         // that SM slots free up for them while it runs (a fully persistent grid would hold every slot)
-        if (i == 0 && deep_stream_) t = (t + 3) / 4;
+        if (i == 0 && deep_stream_ && getenv("SSPSD_OVERLAP_WAVES")) t = (t + 3) / 4;
         p.T = (int)std::max<long long>(2, std::min<long long>(t, RingCfg::MAX_W));
         p.hop = (int)hop_;
         p.detrend = detrend_;
@@ -626,8 +626,8 @@ int Cascade::run_stage(size_t i, const float* fresh, long long split, uint64_t n
         }
     }
     if (n_next > 0) {
-        if (i == 0 && deep_stream_) {
-            // hand over to the deep stream: it may start once stage 0's decimator has written its output
+        if (i + 1 == deep_from_ && deep_stream_) {
+            // hand over to the deep stream: it may start once this stage's decimator has written its output
             SSPSD_CUDA(cudaEventRecord(ev_stage0_, stream_));
             SSPSD_CUDA(cudaStreamWaitEvent(deep_stream_, ev_stage0_, 0));
             deep_dirty_ = true;
@@ -695,7 +695,8 @@ int Cascade::process_device(const float* x, size_t n)
     // chunks of at most max_batch; inputs above 2^26 samples are cut into >= 2 roughly equal chunks so
     // that the deep stages of chunk c (deep_stream_) overlap stage 0 of chunk c+1 (stream_)
     size_t nchunks = (n + cfg_.max_batch - 1) / cfg_.max_batch;
-    if (deep_stream_ && n > (1ull << 26)) nchunks = std::max<size_t>(nchunks, (n + (1ull << 26) - 1) >> 26);
+    if (deep_stream_ && getenv("SSPSD_OVERLAP_CHUNKS") && n > (1ull << 26))
+        nchunks = std::max<size_t>(nchunks, (n + (1ull << 26) - 1) >> 26);
     size_t per = (n + nchunks - 1) / nchunks;
     per = (per + 4095) & ~(size_t)4095;  // keep chunk boundaries 16-byte aligned relative to x
     size_t pos = 0;

@@ -97,7 +97,7 @@ private:
     int launch_psd(size_t i, const StreamSrc& src, uint64_t k0, uint64_t nseg, int jb, float g_first, float g_s);
     int launch_decim(size_t i, const StreamSrc& src, uint64_t m0, uint64_t m1, float* out_fresh,
                      long long out_split);
-    cudaStream_t stage_stream(size_t i) const { return (i == 0 || !deep_stream_) ? stream_ : deep_stream_; }
+    cudaStream_t stage_stream(size_t i) const { return (i < deep_from_ || !deep_stream_) ? stream_ : deep_stream_; }
     int join_streams();  // make stream_ wait for everything queued on deep_stream_
     int ensure_fresh(StageState& st, size_t need);
     int ensure_in_buffers(size_t need);
@@ -149,6 +149,7 @@ private:
     cudaStream_t deep_stream_ = nullptr;  // stages >= 1 run here, overlapping the next batch's stage 0
     cudaEvent_t ev_stage0_ = nullptr, ev_deep_ = nullptr;
     bool deep_dirty_ = false;
+    size_t deep_from_ = 2;  // first stage that runs on deep_stream_
     cudaEvent_t ev_copied_[2] = {nullptr, nullptr}, ev_free_[2] = {nullptr, nullptr};
     cudaEvent_t ev_stage_[2] = {nullptr, nullptr};
     int last_copy_ = -1;
