@@ -149,7 +149,7 @@ private:
     cudaStream_t deep_stream_ = nullptr;  // stages >= 1 run here, overlapping the next batch's stage 0
     cudaEvent_t ev_stage0_ = nullptr, ev_deep_ = nullptr;
     bool deep_dirty_ = false;
-    size_t deep_from_ = 2;  // first stage that runs on deep_stream_
+    size_t deep_from_ = 1;  // first stage that runs on deep_stream_
     cudaEvent_t ev_copied_[2] = {nullptr, nullptr}, ev_free_[2] = {nullptr, nullptr};
     cudaEvent_t ev_stage_[2] = {nullptr, nullptr};
     int last_copy_ = -1;
