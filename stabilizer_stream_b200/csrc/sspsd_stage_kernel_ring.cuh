@@ -35,10 +35,6 @@ __global__ void __launch_bounds__(R16::NT, 2) psd_stage_kernel_ring(const StageP
     float* wgt = wsb + G * 2 * WS;           // p.T entries (segments per CTA)
     float* red = wgt + ((p.T + 3) & ~3);     // G * 4
     uint64_t* bars = reinterpret_cast<uint64_t*>(red + 8);  // RING mbarriers (8-byte aligned: all counts above are even)
-    // inter-pass twiddles as tables shared by both groups: tw0[t-1][j] = W_M^(j t) (pass 0),
-    // tw1[t-1][o] = W_128^(o t) (pass 1): 15 LDS.64 per pass instead of 11 extra complex products
-    float2* tw0 = reinterpret_cast<float2*>(bars + RING);
-    float2* tw1 = tw0 + 15 * TPS;
 
     const int tid = threadIdx.x;
     const int group = tid / TPS;
@@ -77,15 +73,10 @@ __global__ void __launch_bounds__(R16::NT, 2) psd_stage_kernel_ring(const StageP
         wv[2 * t] = w2.x;
         wv[2 * t + 1] = w2.y;
     }
+    const float2 a1 = __ldg(&p.twM[j]), a2 = __ldg(&p.twM[2 * j]), a4 = __ldg(&p.twM[4 * j]), a8 = __ldg(&p.twM[8 * j]);
     const int o = j & 7;
-    if (group == 0) {
-#pragma unroll
-        for (int t = 1; t < 16; ++t) tw0[(t - 1) * TPS + j] = __ldg(&p.twM[j * t]);
-        if (j < 8) {
-#pragma unroll
-            for (int t = 1; t < 16; ++t) tw1[(t - 1) * 8 + j] = __ldg(&p.twM[16 * j * t]);
-        }
-    }
+    const float2 b1 = __ldg(&p.twM[16 * o]), b2 = __ldg(&p.twM[32 * o]), b4 = __ldg(&p.twM[64 * o]),
+                 b8 = __ldg(&p.twM[128 * o]);
     const int qA = 16 * (j >> 3) + (j & 7);
     const int kA = (j >> 3) + 16 * (j & 7);
     const int kB = K - kA;
@@ -159,8 +150,7 @@ __global__ void __launch_bounds__(R16::NT, 2) psd_stage_kernel_ring(const StageP
         for (int t = 0; t < 16; ++t) { v[t].x *= wv[2 * t]; v[t].y *= wv[2 * t + 1]; }
 
         dft16(v);
-#pragma unroll
-        for (int t = 1; t < 16; ++t) v[t] = cmul(v[t], tw0[(t - 1) * TPS + j]);
+        twiddle16(v, a1, a2, a4, a8);
 #pragma unroll
         for (int t = 0; t < 16; ++t) {
             wre[pos0 + t * 152] = v[t].x;
@@ -175,8 +165,7 @@ __global__ void __launch_bounds__(R16::NT, 2) psd_stage_kernel_ring(const StageP
             v[t] = make_float2(wre[a], wim[a]);
         }
         dft16(v);
-#pragma unroll
-        for (int t = 1; t < 16; ++t) v[t] = cmul(v[t], tw1[(t - 1) * 8 + o]);
+        twiddle16(v, b1, b2, b4, b8);
 #pragma unroll
         for (int t = 0; t < 16; ++t) {
             const int a = pos1 + 8 * t + 4 * ((8 * t) >> 5);
@@ -271,7 +260,7 @@ __global__ void __launch_bounds__(R16::NT, 2) psd_stage_kernel_ring(const StageP
 inline size_t stage_ring_smem_bytes(int segs_per_cta)
 {
     size_t fl = (size_t)RingCfg::RING * (R16::N / 2) + (size_t)R16::G * 2 * R16::WS + ((segs_per_cta + 3) & ~3) + 8;
-    return fl * sizeof(float) + RingCfg::RING * sizeof(uint64_t) + 15 * (R16::TPS + 8) * sizeof(float2) + 16;
+    return fl * sizeof(float) + RingCfg::RING * sizeof(uint64_t) + 16;
 }
 
 }  // namespace sspsd
