@@ -30,6 +30,9 @@ sys.path.insert(0, ROOT)
 N_FFT = 4096
 SAMPLES_PER_STEP = 200_000_000
 BYTES_PER_SAMPLE = 4.0  # algorithmic: every raw f32 sample must cross HBM once
+# measured DRAM traffic of the stage-0 PSD kernel: dram__bytes_read.sum + dram__bytes_write.sum = 270.94 MB +
+# 3.97 MB for a 2^26-sample launch (ncu --set full, profiles/r01_ncu_stage0_ring_metrics.csv)
+TRAFFIC_BYTES_PER_SAMPLE = (270.938624e6 + 3.97184e6) / (1 << 26)
 WORKLOAD = "PsdCascade N=4096 Hann 50% overlap, div-8 half-band per stage, 200e6-sample f32 stream per channel"
 
 
@@ -259,8 +262,10 @@ def run_ours(args):
     peak, peak_kind = peaks()
     k_ms, k_launches, k_units = prof["psd_stage0"]
     achieved = (BYTES_PER_SAMPLE * k_units / (k_ms * 1e-3) / 1e9) if k_ms > 0 else 0.0
-    roof = {"bound": "hbm", "kernel": "psd_stage_kernel<12> (stage 0)", "achieved": achieved, "peak": peak,
-            "peak_kind": peak_kind, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+    roof = {"bound": "hbm", "kernel": "psd_stage_kernel_ring (stage 0, N=4096)", "achieved": achieved, "peak": peak,
+            "peak_kind": peak_kind, "unit": "GB/s", "frac": achieved / peak,
+            "traffic": TRAFFIC_BYTES_PER_SAMPLE * k_units / max(k_launches, 1),
+            "traffic_source": "ncu --set full, profiles/r01_ncu_stage0_ring_metrics.csv, scaled per sample",
             "launches": int(k_launches), "avg_launch_ms": (k_ms / k_launches) if k_launches else None,
             "algorithmic_bytes_per_launch": BYTES_PER_SAMPLE * k_units / max(k_launches, 1),
             "share_of_step": k_ms / ms,
