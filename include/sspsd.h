@@ -111,6 +111,9 @@ typedef struct {
 } sspsd_break;
 
 const char *sspsd_last_error(void);
+/* constants of a half-band tap family: drain = hbf_dec_response_length(3) (src/psd.rs:149), halo = input
+ * history the decimator kernel needs before a block (>= FIR span - 1); pure host query */
+int32_t sspsd_hbf_info(int32_t hbf, uint32_t *drain, uint32_t *halo);
 /* fills cfg with PsdCascade::default() (src/psd.rs:408-423): Hann, HBF_140, device 0 */
 int32_t sspsd_config_default(uint32_t n_fft, sspsd_config *cfg);
 

@@ -71,6 +71,7 @@ _i32 = C.c_int32
 # name -> (restype, argtypes); one entry per declaration in include/sspsd.h
 PROTOTYPES = {
     "sspsd_last_error": (C.c_char_p, []),
+    "sspsd_hbf_info": (_i32, [_i32, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]),
     "sspsd_config_default": (_i32, [C.c_uint32, C.POINTER(Config)]),
     "sspsd_cascade_create": (_i32, [C.POINTER(Config), C.POINTER(_vp)]),
     "sspsd_cascade_destroy": (None, [_vp]),

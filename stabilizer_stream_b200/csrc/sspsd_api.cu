@@ -66,6 +66,8 @@ extern "C" {
 
 const char* sspsd_last_error(void) { return sspsd::last_error(); }
 
+int32_t sspsd_hbf_info(int32_t hbf, uint32_t* drain, uint32_t* halo) { return sspsd::hbf_info(hbf, drain, halo); }
+
 int32_t sspsd_config_default(uint32_t n_fft, sspsd_config* cfg)
 {
     if (!cfg) return SSPSD_EINVAL;

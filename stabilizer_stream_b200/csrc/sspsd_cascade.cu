@@ -203,6 +203,14 @@ EwmaPlan ewma_plan(uint32_t count, uint32_t avg, uint64_t S)
 
 }  // namespace
 
+int hbf_info(int hbf, uint32_t* drain, uint32_t* halo)
+{
+    if (hbf != SSPSD_HBF_98 && hbf != SSPSD_HBF_140) return SSPSD_EINVAL;
+    if (drain) *drain = (uint32_t)sspsd_hbf_drain[hbf];
+    if (halo) *halo = (uint32_t)decim_halo(hbf);
+    return SSPSD_OK;
+}
+
 // =============================================================================================
 Cascade::~Cascade()
 {

@@ -19,6 +19,7 @@ namespace sspsd {
 
 void set_error(const std::string& msg);
 const char* last_error();
+int hbf_info(int hbf, uint32_t* drain, uint32_t* halo);
 bool cuda_ok(cudaError_t e, const char* what);
 #define SSPSD_CUDA(call)                     \
     do {                                     \

@@ -8,12 +8,13 @@
 // recomputes its own warm-up from that halo (overlap-save), which makes CTAs independent.
 //
 // Per CTA: OB final outputs.  The x tile is de-interleaved into even/odd planes in shared memory
-// (a half-band FIR only touches the odd phase plus one even centre tap) and each thread computes 4
-// consecutive outputs from a sliding register window.  Lanes therefore read plane elements
-// 4w + c for a common c: planes are stored "polyphase by 4" (element i at (i&3)*S + (i>>2)), which
-// makes every such read unit-stride across lanes for every c (the first version padded 1/32 and
-// measured 38 % conflicting wavefronts, profiles/r01_ncu_summary.md); S = 8 mod 32 keeps the two
-// phases a store instruction touches on disjoint banks.
+// (a half-band FIR only touches the odd phase plus one even centre tap) and each thread computes
+// DEC_P = 8 consecutive outputs from a sliding register window (2M+7 loads for 8 outputs; the kernel
+// is bound by the shared-memory data pipe, profiles/r01_ncu_summary.md).  Lanes therefore read plane
+// elements 8w + c for a common c: planes are stored "polyphase by 8" (element i at (i&7)*S + (i>>3)),
+// which makes every such read unit-stride across lanes for every c (the first version padded 1/32
+// and measured 38 % conflicting wavefronts); S = 4 mod 32 keeps the phase groups a store instruction
+// touches on disjoint banks.
 #pragma once
 #include "sspsd_device.cuh"
 #include "sspsd_hbf_taps.h"
@@ -22,7 +23,9 @@ namespace sspsd {
 
 __constant__ float c_hbf_taps[SSPSD_HBF_NPRESET][3][SSPSD_HBF_MAXTAPS];
 
-constexpr int DEC_OB = 1024;  // outputs per CTA (8192 input samples + 472 of halo)
+constexpr int DEC_OB = 960;   // outputs per CTA (7680 input samples + 488 of halo)
+constexpr int DEC_P = 8;      // consecutive outputs per thread
+constexpr int DEC_LP = 3;
 constexpr int DEC_NT = 256;
 
 constexpr int roundup(int v, int m) { return (v + m - 1) / m * m; }
@@ -30,18 +33,15 @@ constexpr int roundup(int v, int m) { return (v + m - 1) / m * m; }
 // Tap counts: MA = highest-rate stage (tap set 2), MB = set 1, MC = lowest-rate stage (set 0)
 template <int MA, int MB, int MC>
 struct DecGeom {
-    static constexpr int NB = roundup(2 * DEC_OB + 4 * MC - 2, 4);  // stage-B outputs computed per CTA
-    static constexpr int NA = roundup(2 * NB + 4 * MB - 2, 4);      // stage-A outputs
+    static constexpr int NB = roundup(2 * DEC_OB + 4 * MC - 2, DEC_P);  // stage-B outputs computed per CTA
+    static constexpr int NA = roundup(2 * NB + 4 * MB - 2, DEC_P);      // stage-A outputs
     static constexpr int NX = roundup(2 * NA + 4 * MA - 2, 8);      // input samples loaded
     static constexpr int HALO = NX - 8 * DEC_OB;                    // history needed before the block
-    // polyphase-by-4 plane layout: phase stride S = ceil(len/4) rounded up to 8 mod 32
-    static constexpr int phase_stride(int len) { return ((len + 3) / 4 + 23) / 32 * 32 + 8; }
+    // polyphase-by-8 plane layout: phase stride S = ceil(len/8) rounded up to 4 mod 32
+    static constexpr int phase_stride(int len) { return ((len + DEC_P - 1) / DEC_P + 27) / 32 * 32 + 4; }
     static constexpr int SX = phase_stride(NX / 2), SA = phase_stride(NA / 2), SB = phase_stride(NB / 2);
-    static constexpr int SMEM_FLOATS = 2 * 4 * (SX + SA + SB);
+    static constexpr int SMEM_FLOATS = 2 * DEC_P * (SX + SA + SB);
 };
-
-template <int S>
-__device__ __forceinline__ int pp4(int i) { return (i & 3) * S + (i >> 2); }
 
 // One half-band stage over de-interleaved, padded planes.
 //   ine/ino : input planes; plane index r <-> input sample in_base + 2r (+1 for the odd plane)
@@ -66,39 +66,42 @@ __device__ __forceinline__ void hbf_stage(const float* __restrict__ ine, const f
                                           int n_out, float* __restrict__ oute,
                                           float* __restrict__ outo, float* __restrict__ gout, int rel_lo, int rel_hi)
 {
-    for (int w = threadIdx.x; w < n_out / 4; w += DEC_NT) {
-        // plane index of window element i is 4w + (REL0 - 2M + 1 + i): its phase and offset are compile
+    constexpr int P = DEC_P, LP = DEC_LP;
+    for (int w = threadIdx.x; w < n_out / P; w += DEC_NT) {
+        // plane index of window element i is P w + (REL0 - 2M + 1 + i): its phase and offset are compile
         // time constants, only `w` is per thread (unit stride across lanes)
-        float win[2 * M + 3];
+        float win[2 * M + P - 1];
 #pragma unroll
-        for (int i = 0; i < 2 * M + 3; ++i) {
+        for (int i = 0; i < 2 * M + P - 1; ++i) {
             const int c = REL0 - 2 * M + 1 + i;
-            win[i] = ino[(c & 3) * SI + (c >> 2) + w];
+            win[i] = ino[(c & (P - 1)) * SI + (c >> LP) + w];
         }
-        float y[4];
+        float y[P];
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
+        for (int q = 0; q < P; ++q) {
             float acc = 0.f;
 #pragma unroll
             for (int i = 0; i < M; ++i)
                 acc = fmaf(win[q + i] + win[q + 2 * M - 1 - i], c_hbf_taps[PRESET][SET][i], acc);
             const int ce = REL0 + q - M + 1;
-            y[q] = ine[(ce & 3) * SI + (ce >> 2) + w] + acc;
+            y[q] = ine[(ce & (P - 1)) * SI + (ce >> LP) + w] + acc;
         }
         if constexpr (FINAL) {
             // gout points at the block's first output; only [rel_lo, rel_hi) of the block is stored
 #pragma unroll
-            for (int q = 0; q < 4; ++q) {
-                const int r = 4 * w + q;
+            for (int q = 0; q < P; ++q) {
+                const int r = P * w + q;
                 if (r >= rel_lo && r < rel_hi) gout[r] = y[q];
             }
         } else {
-            // out_base is even and 4w is a multiple of 4: q = 0,2 -> even plane, q = 1,3 -> odd plane
-            const int pe = 2 * w;
-            oute[pp4<SO>(pe)] = y[0];
-            outo[pp4<SO>(pe)] = y[1];
-            oute[pp4<SO>(pe + 1)] = y[2];
-            outo[pp4<SO>(pe + 1)] = y[3];
+            // out_base is even: q even -> even plane, q odd -> odd plane, plane index (P/2) w + q/2, whose
+            // polyphase position is phase (P/2)(w&1) + q/2, offset w >> 1
+            const int pb = (w & 1) * (P / 2) * SO + (w >> 1);
+#pragma unroll
+            for (int r = 0; r < P / 2; ++r) {
+                oute[pb + r * SO] = y[2 * r];
+                outo[pb + r * SO] = y[2 * r + 1];
+            }
         }
     }
 }
@@ -109,11 +112,11 @@ __global__ void __launch_bounds__(DEC_NT) decim8_kernel(const DecimParams p)
     using GE = DecGeom<MA, MB, MC>;
     extern __shared__ __align__(16) float smem[];
     float* xe = smem;
-    float* xo = xe + 4 * GE::SX;
-    float* ae = xo + 4 * GE::SX;
-    float* ao = ae + 4 * GE::SA;
-    float* be = ao + 4 * GE::SA;
-    float* bo = be + 4 * GE::SB;
+    float* xo = xe + DEC_P * GE::SX;
+    float* ae = xo + DEC_P * GE::SX;
+    float* ao = ae + DEC_P * GE::SA;
+    float* be = ao + DEC_P * GE::SA;
+    float* bo = be + DEC_P * GE::SB;
 
     // blocks are counted down from the top of the range so that every block is full size and only
     // the lowest one is clipped (by the m >= m0 store guard)
@@ -122,7 +125,7 @@ __global__ void __launch_bounds__(DEC_NT) decim8_kernel(const DecimParams p)
     const long long c_base = mhi - DEC_OB;
 
     // ---- load + de-interleave into the polyphase planes: x[x_base + 4v .. +3] = (e, o, e, o) ----
-    // plane index r = 2v (+1): phase (r & 3) = 2 (v & 1) (+1), offset r >> 2 = v >> 1
+    // plane index r = 2v (+1): phase (r & 7) = 2 (v & 3) (+1), offset r >> 3 = v >> 2
     if (x_base >= p.src.split) {
         // whole block inside the fresh buffer (all but the first block of a batch): straight 128-bit loads
         const float4* __restrict__ gx = reinterpret_cast<const float4*>(p.src.fresh + (x_base - p.src.split));
@@ -139,7 +142,7 @@ __global__ void __launch_bounds__(DEC_NT) decim8_kernel(const DecimParams p)
             for (int u = 0; u < 4; ++u) {
                 const int v = v0 + u * DEC_NT + threadIdx.x;
                 if (v < NV) {
-                    const int pos = 2 * (v & 1) * GE::SX + (v >> 1);
+                    const int pos = 2 * (v & 3) * GE::SX + (v >> 2);
                     xe[pos] = f[u].x;
                     xo[pos] = f[u].y;
                     xe[pos + GE::SX] = f[u].z;
@@ -150,7 +153,7 @@ __global__ void __launch_bounds__(DEC_NT) decim8_kernel(const DecimParams p)
     } else {
         for (int v = threadIdx.x; v < GE::NX / 4; v += DEC_NT) {
             float4 f = ld_stream4(p.src, x_base + 4ll * v);
-            const int pos = 2 * (v & 1) * GE::SX + (v >> 1);
+            const int pos = 2 * (v & 3) * GE::SX + (v >> 2);
             xe[pos] = f.x;
             xo[pos] = f.y;
             xe[pos + GE::SX] = f.z;

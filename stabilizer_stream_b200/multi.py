@@ -99,8 +99,26 @@ def cascade_partials_tensor(cascade):
 # Mirrors the integer bookkeeping of the library (csrc/sspsd_cascade.cu: seek, next_valid_from,
 # own_offset) so that every rank's owned segments are provably valid and complete.
 # =============================================================================================
-DRAIN = {0: 73, 1: 115}      # hbf_dec_response_length(3) per tap family (sspsd_hbf_taps.h)
-DEC_HALO = {0: 304, 1: 472}  # history the decimator kernel reads before a block (DecGeom::HALO)
+class _HbfTable(dict):
+    """drain / decimator halo per tap family, asked from the library (sspsd_hbf_info) on first use so the
+    planner can never disagree with the kernels' geometry."""
+
+    def __init__(self, which):
+        super().__init__()
+        self.which = which
+
+    def __missing__(self, hbf):
+        import ctypes as C
+
+        from . import _lib as L
+        d, h = C.c_uint32(), C.c_uint32()
+        L.check(L.lib().sspsd_hbf_info(int(hbf), C.byref(d), C.byref(h)))
+        self[hbf] = (d.value, h.value)[self.which]
+        return self[hbf]
+
+
+DRAIN = _HbfTable(0)     # hbf_dec_response_length(3) per tap family
+DEC_HALO = _HbfTable(1)  # history the decimator kernel reads before a block (DecGeom::HALO)
 
 
 def own_offset(i, drain):
