@@ -218,3 +218,53 @@ def test_large_batch_properties(sp):
     g2.process(x * 2.0)
     p2, _ = g2.psd()
     np.testing.assert_allclose(p2, 4.0 * p, rtol=1e-5)
+
+
+def test_ewma_n4096_ring_kernel(sp, oracle):
+    """EWMA weights inside the persistent N=4096 kernel, including the boxcar -> EWMA transition."""
+    n = 4096
+    x = uniform_noise(600 * n, 12)
+    g = sp.PsdCascade(n)
+    o = oracle.Cascade(n, 1)
+    g.set_avg(sp.AvgOpts(limit=99, count=2 ** 32 - 2))
+    o.set_avg(99, 2 ** 32 - 2)
+    for part in np.array_split(x, 5):
+        g.process(part)
+        o.process(part)
+    p, b = g.psd()
+    po, bo = o.psd()
+    assert [breaks_tuple(k) for k in b] == [k.as_tuple() for k in bo]
+    assert b[-1].count == 100 and b[-1].avg == 99
+    assert_bins_close(p, po, "ewma 4096")
+
+
+def test_small_max_batch_chunks_long_inputs(sp, oracle):
+    """process() cuts inputs longer than cfg.max_batch into chunks; results must not change."""
+    import torch
+    n = 512
+    x = uniform_noise(1_000_003, 13)
+    g = sp.PsdCascade(n, max_batch=70_000)
+    g.process(torch.from_numpy(x).cuda())
+    g2 = sp.PsdCascade(n, max_batch=50_000, host_stage=1 << 12)
+    g2.process(x)
+    o = oracle.Cascade(n, 1)
+    o.process(x)
+    po, bo = o.psd()
+    for c in (g, g2):
+        p, b = c.psd()
+        assert [breaks_tuple(k) for k in b] == [k.as_tuple() for k in bo]
+        assert_bins_close(p, po, "chunked")
+
+
+def test_rect_window_stage_with_decimation(sp, oracle):
+    """Window::rectangular (overlap 0, hop = N) through the single-stage API incl. its decimated output."""
+    for n in (512, 4096):
+        x = uniform_noise(50 * n + 5, 14)
+        g = sp.Psd(n, sp.Window.RECTANGULAR)
+        o = oracle.Stage(n, oracle.WINDOW_RECT)
+        yg = np.concatenate([g.process(x[:7 * n + 3]), g.process(x[7 * n + 3:])])
+        yo = np.concatenate([o.process(x[:7 * n + 3]), o.process(x[7 * n + 3:])])
+        assert g.count() == o.count() == 50
+        np.testing.assert_allclose(yg, yo, atol=2e-5)
+        assert_bins_close(g.spectrum(), o.spectrum(), "rect %d" % n)
+        np.testing.assert_array_equal(g.buf(), o.buf())
