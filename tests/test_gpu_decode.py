@@ -122,3 +122,29 @@ def test_frames_into_cascades(sp, oracle):
         po, bo = ocs[t].psd()
         assert [k.count for k in b] == [k.count for k in bo]
         assert p.size == po.size and np.max(np.abs(p - po) / np.maximum(po, 1e-30)) < 1e-4
+
+
+@pytest.mark.parametrize("fmt,batches", [(2, 25), (3, 18), (4, 60)])
+def test_low_rate_formats_into_cascades(sp, oracle, fmt, batches):
+    """Fls / ThermostatEem / Mpll frames (one item per batch per trace) decoded on the device into cascades."""
+    n = 64
+    data, flen, stride, hdrs = make_frames(fmt, batches, 1500, seed=20 + fmt, drop_every=211)
+    st, nf, lo, want = oracle_decode_stream(oracle, data, flen, stride, 1500)
+    ntr = len(want)
+    cas = [sp.PsdCascade(n) for _ in range(ntr)]
+    loss = sp.Loss()
+    dec = sp.FrameDecoder()
+    info = dec.process_frames(cas, data, flen, loss)
+    assert info.n_traces == ntr and info.samples_per_trace == 1500 * batches
+    assert (loss.received, loss.dropped, loss.seq) == (lo.received, lo.dropped, lo.seq)
+    for t in range(ntr):
+        w = np.concatenate(want[t])
+        if not np.all(np.isfinite(w)) or np.max(np.abs(w)) > 1e30:
+            continue   # random f32 payload words (ThermostatEem) may be NaN/huge: decode parity is covered bit exactly above
+        o = oracle.Cascade(n, 1)
+        o.process(w)
+        p, b = cas[t].psd()
+        po, bo = o.psd()
+        assert [k.count for k in b] == [k.count for k in bo]
+        scale = np.median(po)
+        assert np.max((np.abs(p - po) - 1e-5 * scale) / np.maximum(po, 1e-300)) < 1e-4

@@ -1,0 +1,70 @@
+"""Seeded random walks over the public API (process host/device with ragged sizes, option changes, readouts,
+clone, reset) checked against the CPU oracle after every readout: exercises the host state machine
+(carry/fresh buffers, staging, second stream, EWMA plans) far from the happy path."""
+import numpy as np
+import pytest
+
+from conftest import uniform_noise
+
+pytestmark = pytest.mark.gpu
+
+
+def check(g, o, sp, what):
+    p, b = g.psd(sp.MergeOpts(keep_overlap=True, min_count=0, keep_transition_band=True))
+    po, bo = o.psd(True, 0, True)
+    got = [(k.start, k.include, k.count, k.avg, k.bins.start, k.bins.stop, k.decimation, k.pending, k.processed) for k in b]
+    want = [(k.start, bool(k.include), k.count, k.avg, k.bins_start, k.bins_end, k.decimation, k.pending, k.processed) for k in bo]
+    assert got == want, what
+    for k in b:
+        if k.count:
+            sl = slice(k.start, k.start + len(k.bins))
+            w = po[sl].astype(np.float64)
+            floor = 1e-5 * np.median(w)
+            rel = (np.abs(p[sl] - w) - floor) / np.maximum(w, 1e-300)
+            assert np.max(rel[2:]) < 1e-4 and np.max(rel[:2]) < 2e-2, "%s: stage dec=%d rel %.3g" % (what, k.decimation, np.max(rel))
+
+
+@pytest.mark.parametrize("seed,n", [(1, 512), (2, 4096), (3, 64), (4, 2048), (5, 512)])
+def test_random_api_walk(oracle, seed, n):
+    import torch
+    import stabilizer_stream_b200 as sp
+    rng = np.random.default_rng(seed)
+    x = uniform_noise(260 * n * 8, 100 + seed) + np.float32(0.05)
+    xd = torch.from_numpy(x).cuda()
+    g = sp.PsdCascade(n, hbf=sp.Hbf(seed & 1), host_stage=1 << 13, max_batch=int(rng.integers(20 * n, 400 * n)))
+    o = oracle.Cascade(n, seed & 1)
+    pos = 0
+    step = 0
+    while pos < x.size:
+        step += 1
+        r = rng.random()
+        if r < 0.55:
+            k = int(rng.integers(0, 30 * n)) if rng.random() < 0.8 else int(rng.integers(0, 9))
+            if rng.random() < 0.5:
+                g.process(x[pos:pos + k])
+            else:
+                g.process(xd[pos:pos + k])
+            o.process(x[pos:pos + k])
+            pos += k
+        elif r < 0.65:
+            d = int(rng.integers(0, 4))
+            g.set_detrend(sp.Detrend(d))
+            o.set_detrend(d)
+        elif r < 0.72:
+            lim = int(rng.choice([2 ** 32 - 1, 3, 17, 200, 0]))
+            cnt = int(rng.choice([2 ** 32 - 1, 2 ** 32 - 2, 5000, 64]))
+            g.set_avg(sp.AvgOpts(limit=lim, count=cnt))
+            o.set_avg(lim, cnt)
+        elif r < 0.84:
+            check(g, o, sp, "seed %d step %d" % (seed, step))
+        elif r < 0.90:
+            g = g.clone()
+            o = o.clone()
+        elif r < 0.93 and pos > 0:
+            g.reset()
+            o = oracle.Cascade(n, seed & 1)
+            # reset keeps the options (Cmd::Reset re-creates the cascades and Cmd::Send re-applies them)
+            o.set_detrend(0)
+            g.set_detrend(sp.Detrend(0))
+            g.set_avg(sp.AvgOpts())
+    check(g, o, sp, "seed %d final" % seed)
