@@ -21,7 +21,9 @@ def check(g, o, sp, what):
             w = po[sl].astype(np.float64)
             floor = 1e-5 * np.median(w)
             rel = (np.abs(p[sl] - w) - floor) / np.maximum(w, 1e-300)
-            assert np.max(rel[2:]) < 1e-4 and np.max(rel[:2]) < 2e-2, "%s: stage dec=%d rel %.3g" % (what, k.decimation, np.max(rel))
+            # bins next to DC hold what is left of the (decimation-amplified) DC offset after detrending: a
+            # difference of nearly equal numbers, set by how the f32 offset was rounded (tests/test_gpu_psd.py)
+            assert np.max(rel[4:]) < 1e-4 and np.max(rel[:4]) < 2e-2, "%s: stage dec=%d rel %.3g" % (what, k.decimation, np.max(rel))
 
 
 @pytest.mark.parametrize("seed,n", [(1, 512), (2, 4096), (3, 64), (4, 2048), (5, 512)])
