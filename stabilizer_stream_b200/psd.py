@@ -401,6 +401,24 @@ class FrameDecoder:
         L.check(st)
         return (Format(info.format) if info.frames_ok else None), traces, info.frames_ok
 
+    def decode_device(self, frames, frame_len, out, loss: Loss = None, frame_stride=None, n_frames=None):
+        """Like decode(), but the traces stay on the device: `out` is a list of 4 CUDA float32 tensors that
+        receive them.  Returns the sspsd_decode_info (format, n_traces, samples_per_trace, frames_ok)."""
+        frame_stride = frame_stride or frame_len
+        ptr, nbytes, mem, keep = self._frames(frames, frame_len, frame_stride)
+        if n_frames is None:
+            n_frames = 0 if nbytes < frame_len else 1 + (nbytes - frame_len) // frame_stride
+        ptrs = (C.c_void_p * L.MAX_TRACES)(*[t.data_ptr() for t in out])
+        info = L.DecodeInfoC()
+        st = L.lib().sspsd_decode_frames(self._h, ptr, n_frames, frame_len, frame_stride, mem,
+                                         C.byref(loss.c) if loss is not None else None, ptrs,
+                                         min(t.numel() for t in out), L.MEM_DEVICE, C.byref(info))
+        del keep
+        if st in (L.EHEADER, L.EFORMAT, L.ESIZE, L.EBATCHES, L.ESHORT) and info.frames_ok < n_frames:
+            raise DecodeError(st, info.frames_ok)
+        L.check(st)
+        return info
+
     def process_frames(self, cascades, frames, frame_len, loss: Loss = None, frame_stride=None, n_frames=None):
         """Fused decode -> one PsdCascade per trace (src/bin/psd.rs:174-182)."""
         frame_stride = frame_stride or frame_len

@@ -91,11 +91,26 @@ def config3(dev):
     for c in cas:
         c.sync()
     dt = time.perf_counter() - t0
+    # decode + loss only, traces written to device buffers (K1 alone: 2 B read + 4 B written per sample)
+    outs = [torch.empty(nfr * batches * 8, device=dev) for _ in range(4)]
+    dec.decode_device(fr, flen, outs, Loss())
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(5):
+        dec.decode_device(fr, flen, outs, Loss())
+    e1.record()
+    torch.cuda.synchronize()
+    dec_ms = e0.elapsed_time(e1) / 5
     st, nf, lo, want = oracle_decode_stream(orc, data, flen, stride, nfr)
     ok_loss = (loss.received, loss.dropped, loss.seq) == (lo.received, lo.dropped, lo.seq)
+    ok_tr = all(np.array_equal(outs[t][:4096 * batches * 8].cpu().numpy().view(np.uint32),
+                               np.concatenate(want[t][:4096]).view(np.uint32)) for t in range(4))
     samples = 4 * info.samples_per_trace
     return {"config": 3, "frames": nfr, "bytes": len(data), "trace_samples_total": int(samples),
             "gpu_MSps_decode_plus_4_cascades": samples / dt / 1e6, "frame_GBps": len(data) / dt / 1e9,
+            "decode_only_ms": dec_ms, "decode_only_GBps_read_plus_written": (len(data) + samples * 4) / dec_ms / 1e6,
+            "decode_only_GSps": samples / dec_ms / 1e6, "traces_bit_exact_first_4096_frames": bool(ok_tr),
             "loss_bit_exact": bool(ok_loss), "received": int(loss.received), "dropped": int(loss.dropped)}
 
 
