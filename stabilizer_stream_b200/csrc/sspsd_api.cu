@@ -405,7 +405,8 @@ int decode_on_device(sspsd_decoder* d, const uint8_t* frames, size_t n_frames, s
             if (fmt == SSPSD_FORMAT_ADCDAC && flat_ok) {
                 const unsigned long long n_words8 = n_bytes / 8;
                 const unsigned long long n_thr = (n_words8 + 1) / 2;
-                adcdac_flat_kernel<<<(unsigned int)((n_thr + nt - 1) / nt), nt, 0, d->stream>>>(
+                const unsigned long long per_cta = (unsigned long long)ADC_NT * ADC_ITERS;
+                adcdac_flat_kernel<<<(unsigned int)((n_thr + per_cta - 1) / per_cta), ADC_NT, 0, d->stream>>>(
                     dfr, n_words8, frame_stride, frame_len, d->d_res, out);
             } else {
                 const unsigned int bb = fmt == 1 ? 64u : fmt == 2 ? 56u : fmt == 3 ? 80u : 24u;

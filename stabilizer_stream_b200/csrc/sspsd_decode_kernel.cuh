@@ -142,41 +142,59 @@ __device__ __forceinline__ float4 adc_word(uint2 w, bool dac)
 }
 
 // AdcDac fast path: frames base 16-byte aligned, stride a multiple of 8.  Flat scan of the frame
-// buffer with aligned 128-bit loads (the last thread falls back to one 64-bit load when the byte
-// count is an odd multiple of 8); every 8-byte word that falls into a payload is decoded.
-__global__ void adcdac_flat_kernel(const uint8_t* __restrict__ frames, unsigned long long n_words8,
-                                   unsigned long long stride, unsigned long long frame_len,
-                                   const DecodeResult* __restrict__ res, TraceOut out)
+// buffer with aligned 128-bit loads; every 8-byte word that falls into a payload is four i16 samples of
+// one channel and becomes one float4 store (a warp writes 128-byte runs per channel).  A CTA owns a
+// contiguous 64 KiB byte range, so the frame index / offset within the frame is divided out once per
+// thread and then advanced incrementally (no per-word 64-bit division).
+constexpr int ADC_NT = 256;
+constexpr int ADC_ITERS = 16;  // 16-byte words per thread
+__global__ void __launch_bounds__(ADC_NT) adcdac_flat_kernel(const uint8_t* __restrict__ frames,
+                                                              unsigned long long n_words8, unsigned long long stride,
+                                                              unsigned long long frame_len,
+                                                              const DecodeResult* __restrict__ res, TraceOut out)
 {
-    unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (2 * i >= n_words8) return;
     const unsigned long long nb = res->first_bad;
     const unsigned int spf = res->batches * 8u;  // samples per trace per frame
-    uint4 v;
-    const bool two = 2 * i + 1 < n_words8;
-    if (two) {
-        v = __ldg(reinterpret_cast<const uint4*>(frames) + i);
-    } else {
-        uint2 t = __ldg(reinterpret_cast<const uint2*>(frames) + 2 * i);
-        v = make_uint4(t.x, t.y, 0u, 0u);
-    }
+    const unsigned long long n_vec = (n_words8 + 1) / 2;
+    unsigned long long i = (unsigned long long)blockIdx.x * (ADC_NT * ADC_ITERS) + threadIdx.x;
     unsigned long long o = i * 16ull;
     unsigned long long f = o / stride;
-    unsigned int r = (unsigned int)(o - f * stride);
+    unsigned long long r = o - f * stride;
+    const unsigned int step = ADC_NT * 16u;  // bytes between two words of one thread
+#pragma unroll 4
+    for (int it = 0; it < ADC_ITERS; ++it, i += ADC_NT) {
+        if (i < n_vec) {
+            const bool two = 2 * i + 1 < n_words8;
+            uint4 v;
+            if (two) {
+                v = __ldg(reinterpret_cast<const uint4*>(frames) + i);
+            } else {
+                uint2 t = __ldg(reinterpret_cast<const uint2*>(frames) + 2 * i);
+                v = make_uint4(t.x, t.y, 0u, 0u);
+            }
+            unsigned long long ff = f;
+            unsigned long long rr = r;
 #pragma unroll
-    for (int hh = 0; hh < 2; ++hh) {
-        if (r >= stride) {
-            r -= (unsigned int)stride;
+            for (int hh = 0; hh < 2; ++hh) {
+                if (rr >= stride) {
+                    rr -= stride;
+                    ++ff;
+                }
+                if ((hh == 0 || two) && ff < nb && rr >= SSPSD_HEADER_SIZE && rr < frame_len) {
+                    unsigned int w = (unsigned int)(rr - SSPSD_HEADER_SIZE) >> 3;  // 8-byte word of the payload
+                    unsigned int b = w >> 3, c = (w >> 1) & 3u, h = w & 1u;
+                    uint2 wd = hh ? make_uint2(v.z, v.w) : make_uint2(v.x, v.y);
+                    float4 y = adc_word(wd, c >= 2);
+                    *reinterpret_cast<float4*>(out.t[c] + ff * spf + b * 8u + h * 4u) = y;
+                }
+                rr += 8;
+            }
+        }
+        r += step;
+        while (r >= stride) {
+            r -= stride;
             ++f;
         }
-        if ((hh == 0 || two) && f < nb && r >= SSPSD_HEADER_SIZE && r < frame_len) {
-            unsigned int w = (r - SSPSD_HEADER_SIZE) >> 3;  // 8-byte word of the payload
-            unsigned int b = w >> 3, c = (w >> 1) & 3u, h = w & 1u;
-            uint2 wd = hh ? make_uint2(v.z, v.w) : make_uint2(v.x, v.y);
-            float4 y = adc_word(wd, c >= 2);
-            *reinterpret_cast<float4*>(out.t[c] + f * spf + b * 8u + h * 4u) = y;
-        }
-        r += 8;
     }
 }
 
