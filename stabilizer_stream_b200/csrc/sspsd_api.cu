@@ -389,7 +389,7 @@ int decode_on_device(sspsd_decoder* d, const uint8_t* frames, size_t n_frames, s
     if (dst) {
         TraceOut out{};
         for (int t = 0; t < SSPSD_MAX_TRACES; ++t) out.t[t] = dst[t];
-        const bool flat_ok = dst_aligned && (reinterpret_cast<uintptr_t>(dfr) % 16 == 0) && (frame_stride % 8 == 0) &&
+        const bool flat_ok = dst_aligned && (reinterpret_cast<uintptr_t>(dfr) % 8 == 0) && (frame_stride % 8 == 0) &&
                              frame_len >= SSPSD_HEADER_SIZE && ((frame_len - SSPSD_HEADER_SIZE) % 64 == 0);
         // The format byte of frame 0 decides the kernel; peek at it on the host when the frames are host
         // memory, otherwise read it back (4 bytes) -- the call synchronises for the result anyway.
@@ -404,9 +404,8 @@ int decode_on_device(sspsd_decoder* d, const uint8_t* frames, size_t n_frames, s
         if (fmt >= 1 && fmt <= 4 && frame_len >= SSPSD_HEADER_SIZE) {
             if (fmt == SSPSD_FORMAT_ADCDAC && flat_ok) {
                 const unsigned long long n_words8 = n_bytes / 8;
-                const unsigned long long n_thr = (n_words8 + 1) / 2;
                 const unsigned long long per_cta = (unsigned long long)ADC_NT * ADC_ITERS;
-                adcdac_flat_kernel<<<(unsigned int)((n_thr + per_cta - 1) / per_cta), ADC_NT, 0, d->stream>>>(
+                adcdac_flat_kernel<<<(unsigned int)((n_words8 + per_cta - 1) / per_cta), ADC_NT, 0, d->stream>>>(
                     dfr, n_words8, frame_stride, frame_len, d->d_res, out);
             } else {
                 const unsigned int bb = fmt == 1 ? 64u : fmt == 2 ? 56u : fmt == 3 ? 80u : 24u;

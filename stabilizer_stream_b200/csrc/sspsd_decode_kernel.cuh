@@ -141,13 +141,17 @@ __device__ __forceinline__ float4 adc_word(uint2 w, bool dac)
     return o;
 }
 
-// AdcDac fast path: frames base 16-byte aligned, stride a multiple of 8.  Flat scan of the frame
-// buffer with aligned 128-bit loads; every 8-byte word that falls into a payload is four i16 samples of
-// one channel and becomes one float4 store (a warp writes 128-byte runs per channel).  A CTA owns a
-// contiguous 64 KiB byte range, so the frame index / offset within the frame is divided out once per
-// thread and then advanced incrementally (no per-word 64-bit division).
+// AdcDac fast path: frames base 8-byte aligned, stride a multiple of 8.  Flat scan of the frame buffer:
+// one 8-byte word per lane and step (a warp reads 256 contiguous bytes).  A word that falls into a payload
+// is four i16 samples of one channel and becomes one float4 store; neighbouring lanes hold the two halves
+// of one 8-sample group, so every store instruction writes whole 32-byte sectors and a warp writes 64-byte
+// runs per channel.  A CTA owns a contiguous 32 KiB byte range: the frame index / offset within the frame
+// is divided out once per thread and then advanced incrementally, and the loads of 8 steps are issued
+// before the first store so that 8 requests per thread are in flight (the first version was stalled on
+// long_scoreboard with one load in flight and wrote half sectors, profiles/r01_ncu_summary.md).
 constexpr int ADC_NT = 256;
-constexpr int ADC_ITERS = 16;  // 16-byte words per thread
+constexpr int ADC_ITERS = 16;  // 8-byte words per thread
+constexpr int ADC_MLP = 8;     // loads in flight per thread
 __global__ void __launch_bounds__(ADC_NT) adcdac_flat_kernel(const uint8_t* __restrict__ frames,
                                                               unsigned long long n_words8, unsigned long long stride,
                                                               unsigned long long frame_len,
@@ -155,45 +159,32 @@ __global__ void __launch_bounds__(ADC_NT) adcdac_flat_kernel(const uint8_t* __re
 {
     const unsigned long long nb = res->first_bad;
     const unsigned int spf = res->batches * 8u;  // samples per trace per frame
-    const unsigned long long n_vec = (n_words8 + 1) / 2;
-    unsigned long long i = (unsigned long long)blockIdx.x * (ADC_NT * ADC_ITERS) + threadIdx.x;
-    unsigned long long o = i * 16ull;
-    unsigned long long f = o / stride;
-    unsigned long long r = o - f * stride;
-    const unsigned int step = ADC_NT * 16u;  // bytes between two words of one thread
-#pragma unroll 4
-    for (int it = 0; it < ADC_ITERS; ++it, i += ADC_NT) {
-        if (i < n_vec) {
-            const bool two = 2 * i + 1 < n_words8;
-            uint4 v;
-            if (two) {
-                v = __ldg(reinterpret_cast<const uint4*>(frames) + i);
-            } else {
-                uint2 t = __ldg(reinterpret_cast<const uint2*>(frames) + 2 * i);
-                v = make_uint4(t.x, t.y, 0u, 0u);
-            }
-            unsigned long long ff = f;
-            unsigned long long rr = r;
+    const uint2* __restrict__ words = reinterpret_cast<const uint2*>(frames);
+    const unsigned long long j0 = (unsigned long long)blockIdx.x * (ADC_NT * ADC_ITERS) + threadIdx.x;
+    unsigned long long f = (j0 * 8ull) / stride;
+    unsigned long long r = j0 * 8ull - f * stride;
+    const unsigned int step = ADC_NT * 8u;  // bytes between two words of one thread
+#pragma unroll 1
+    for (int it0 = 0; it0 < ADC_ITERS; it0 += ADC_MLP) {
+        uint2 v[ADC_MLP];
 #pragma unroll
-            for (int hh = 0; hh < 2; ++hh) {
-                if (rr >= stride) {
-                    rr -= stride;
-                    ++ff;
-                }
-                if ((hh == 0 || two) && ff < nb && rr >= SSPSD_HEADER_SIZE && rr < frame_len) {
-                    unsigned int w = (unsigned int)(rr - SSPSD_HEADER_SIZE) >> 3;  // 8-byte word of the payload
-                    unsigned int b = w >> 3, c = (w >> 1) & 3u, h = w & 1u;
-                    uint2 wd = hh ? make_uint2(v.z, v.w) : make_uint2(v.x, v.y);
-                    float4 y = adc_word(wd, c >= 2);
-                    *reinterpret_cast<float4*>(out.t[c] + ff * spf + b * 8u + h * 4u) = y;
-                }
-                rr += 8;
-            }
+        for (int u = 0; u < ADC_MLP; ++u) {
+            const unsigned long long j = j0 + (unsigned long long)(it0 + u) * ADC_NT;
+            v[u] = j < n_words8 ? __ldg(words + j) : make_uint2(0u, 0u);
         }
-        r += step;
-        while (r >= stride) {
-            r -= stride;
-            ++f;
+#pragma unroll
+        for (int u = 0; u < ADC_MLP; ++u) {
+            const unsigned long long j = j0 + (unsigned long long)(it0 + u) * ADC_NT;
+            if (j < n_words8 && f < nb && r >= SSPSD_HEADER_SIZE && r < frame_len) {
+                const unsigned int w = (unsigned int)(r - SSPSD_HEADER_SIZE) >> 3;  // 8-byte word of the payload
+                const unsigned int b = w >> 3, c = (w >> 1) & 3u, h = w & 1u;
+                *reinterpret_cast<float4*>(out.t[c] + f * spf + b * 8u + h * 4u) = adc_word(v[u], c >= 2);
+            }
+            r += step;
+            while (r >= stride) {
+                r -= stride;
+                ++f;
+            }
         }
     }
 }
