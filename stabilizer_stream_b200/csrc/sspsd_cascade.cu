@@ -220,7 +220,7 @@ Cascade::~Cascade()
     if (stream_)
         cudaStreamSynchronize(stream_);
     if (deep_stream_) cudaStreamSynchronize(deep_stream_);
-    free_stages();
+    free_stages(false);
     cudaFree(d_win_);
     cudaFree(d_twM_);
     cudaFree(d_twN_);
@@ -373,11 +373,26 @@ int Cascade::add_stage()
         return SSPSD_EINVAL;
     }
     StageState st;
-    st.avg = single_stage_avg_set_ ? single_stage_avg_ : stage_avg(stages_.size());
     const size_t cap = (size_t)hb_ + n_ + 16;
     cudaStream_t ss = stage_stream(stages_.size());
-    SSPSD_CUDA(cudaMalloc(&st.carry[0], cap * sizeof(float)));
-    SSPSD_CUDA(cudaMalloc(&st.carry[1], cap * sizeof(float)));
+    if (!spare_.empty()) {
+        // buffers of a stage released by reset(): reuse them (a reset is the GUI's Cmd::Reset; re-creating
+        // every device buffer each time cost milliseconds)
+        StageState old = spare_.back();
+        spare_.pop_back();
+        st.carry[0] = old.carry[0];
+        st.carry[1] = old.carry[1];
+        st.fresh[0] = old.fresh[0];
+        st.fresh[1] = old.fresh[1];
+        st.fresh_cap = old.fresh_cap;
+        st.ev_read[0] = old.ev_read[0];
+        st.ev_read[1] = old.ev_read[1];
+    } else {
+        SSPSD_CUDA(cudaMalloc(&st.carry[0], cap * sizeof(float)));
+        SSPSD_CUDA(cudaMalloc(&st.carry[1], cap * sizeof(float)));
+        for (int b = 0; b < 2; ++b) SSPSD_CUDA(cudaEventCreateWithFlags(&st.ev_read[b], cudaEventDisableTiming));
+    }
+    st.avg = single_stage_avg_set_ ? single_stage_avg_ : stage_avg(stages_.size());
     // zero history for g < 0: the decimator starts from HbfDec8::default() (psd.rs:141)
     SSPSD_CUDA(cudaMemsetAsync(st.carry[0], 0, cap * sizeof(float), ss));
     SSPSD_CUDA(cudaMemsetAsync(st.carry[1], 0, cap * sizeof(float), ss));
@@ -385,7 +400,6 @@ int Cascade::add_stage()
     // time-chunk mode: warm-up contamination propagates down the cascade (see seek())
     st.valid_from = stages_.empty() ? seek_pos_ : next_valid_from(stages_.back().valid_from);
     SSPSD_CUDA(cudaMemsetAsync(d_acc_ + stages_.size() * acc_stride_, 0, acc_stride_ * sizeof(float), ss));
-    for (int b = 0; b < 2; ++b) SSPSD_CUDA(cudaEventCreateWithFlags(&st.ev_read[b], cudaEventDisableTiming));
     stages_.push_back(st);
     return SSPSD_OK;
 }
@@ -658,17 +672,25 @@ int Cascade::join_streams()
     return SSPSD_OK;
 }
 
-void Cascade::free_stages()
+void Cascade::free_stages(bool keep_buffers)
 {
-    for (auto& st : stages_) {
-        cudaFree(st.carry[0]);
-        cudaFree(st.carry[1]);
-        cudaFree(st.fresh[0]);
-        cudaFree(st.fresh[1]);
-        for (int b = 0; b < 2; ++b)
-            if (st.ev_read[b]) cudaEventDestroy(st.ev_read[b]);
+    if (keep_buffers) {
+        // deepest stage last in, first out: add_stage() hands the buffers back in the same order
+        for (size_t i = stages_.size(); i-- > 0;) spare_.push_back(stages_[i]);
+        stages_.clear();
+        return;
     }
-    stages_.clear();
+    for (auto* v : {&stages_, &spare_}) {
+        for (auto& st : *v) {
+            cudaFree(st.carry[0]);
+            cudaFree(st.carry[1]);
+            cudaFree(st.fresh[0]);
+            cudaFree(st.fresh[1]);
+            for (int b = 0; b < 2; ++b)
+                if (st.ev_read[b]) cudaEventDestroy(st.ev_read[b]);
+        }
+        v->clear();
+    }
 }
 
 // x: device memory, valid in stream order
@@ -944,8 +966,11 @@ int Cascade::reset()
     SSPSD_CUDA(cudaStreamSynchronize(stream_));
     SSPSD_CUDA(cudaStreamSynchronize(copy_stream_));
     if (deep_stream_) SSPSD_CUDA(cudaStreamSynchronize(deep_stream_));
-    free_stages();
+    free_stages(true);
     deep_dirty_ = false;
+    seek_pos_ = 0;
+    windowed_ = false;
+    tail_len_ = 0;
     staged_ = 0;
     sink_len_ = 0;
     SSPSD_CUDA(cudaMemsetAsync(d_acc_, 0, (size_t)SSPSD_MAX_STAGES * acc_stride_ * sizeof(float), stream_));

@@ -93,7 +93,7 @@ public:
 
 private:
     int add_stage();
-    void free_stages();
+    void free_stages(bool keep_buffers);
     int run_stage(size_t i, const float* fresh, long long split, uint64_t n_new);
     int launch_psd(size_t i, const StreamSrc& src, uint64_t k0, uint64_t nseg, int jb, float g_first, float g_s);
     int launch_decim(size_t i, const StreamSrc& src, uint64_t m0, uint64_t m1, float* out_fresh,
@@ -155,6 +155,7 @@ private:
     cudaEvent_t ev_stage_[2] = {nullptr, nullptr};
     int last_copy_ = -1;
     std::vector<StageState> stages_;
+    std::vector<StageState> spare_;  // device buffers of stages released by reset(), reused by add_stage()
     // device tables + accumulators
     float* d_win_ = nullptr;
     float2* d_twM_ = nullptr;
