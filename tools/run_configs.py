@@ -140,8 +140,9 @@ def config5(dev, total, n_local, check):
     multi.time_chunked_psd(PsdCascade(n, device=dev.index),
                            lambda a, b, sink: sink((torch.rand(b - a, device=dev) - 0.5) * (12 ** 0.5)),
                            wtotal, n, d, 1, min(n_local, 4), str(dev))
-    c.process(xs[:1 << 22])   # allocates the handle's buffers
-    c.reset()
+    c.process(xs[:min(xs.numel(), (1 << 28) + (1 << 22))])   # one full-size batch: the handle's buffers reach their final size
+    c.sync()
+    c.reset()                                                # keeps the buffers
     if d is not None:
         d.barrier()
     torch.cuda.synchronize()
