@@ -291,6 +291,34 @@ void sspsd_loss_update(sspsd_loss *loss, uint32_t seq, uint8_t batches);
 float sspsd_loss_ratio(const sspsd_loss *loss);
 
 /* ---------------------------------------------------------------------------------------------
+ * Synthetic sources generated on the device: Data::Noise and Data::Dsm of src/source.rs:66-79,
+ * 104-134 (SourceOpts --noise / --dsm, source.rs:40-47).  The generator state persists between
+ * calls, so the stream does not depend on how it is cut into calls (the reference cuts it into
+ * 4096-sample blocks, source.rs:116, 120).
+ *   SSPSD_SOURCE_NOISE  param = the reference's `noise` exponent: PSD ~ f^param; |param| cascaded
+ *                       first-order differentiators (param > 0, up to 8) or integrators (param < 0,
+ *                       down to -4) over zero-mean unit-RMS uniform noise; seed keys the uniform
+ *                       stream (Philox4x32-10; the reference's default seed is 0x7654321)
+ *   SSPSD_SOURCE_DSM    param = the reference's `dsm` frequency tuning word (u32): sine marker
+ *                       through a MASH-1-1-1 modulator, output in {-3.5 .. 3.5}; seed unused
+ * Errors: SSPSD_EUNIMPLEMENTED for exponents outside -4..=8, SSPSD_EINVAL for bad arguments.
+ * --------------------------------------------------------------------------------------------- */
+typedef struct sspsd_source sspsd_source;
+enum { SSPSD_SOURCE_NOISE = 0, SSPSD_SOURCE_DSM = 1 };
+/* stream: as in sspsd_config (NULL = private stream, (void*)1 = legacy default stream) */
+int32_t sspsd_source_create(int32_t kind, int64_t param, uint64_t seed, int32_t device, void *stream,
+                            sspsd_source **out);
+void sspsd_source_destroy(sspsd_source *s);
+/* back to sample 0 with zeroed state (Source::new) */
+int32_t sspsd_source_reset(sspsd_source *s);
+/* the next n samples into device memory d_out, asynchronously on the source's stream (Source::get) */
+int32_t sspsd_source_generate(sspsd_source *s, float *d_out, size_t n);
+int32_t sspsd_source_position(const sspsd_source *s, uint64_t *pos);
+/* generate the next n samples straight into the cascade (stream_test.rs:52-58 with a synthetic
+ * source): no host memory is touched; generation and consumption share the cascade's stream */
+int32_t sspsd_cascade_process_source(sspsd_cascade *c, sspsd_source *s, size_t n);
+
+/* ---------------------------------------------------------------------------------------------
  * Var::eval (AVAR/MVAR/FVAR from a phase PSD), src/var.rs:26-45 -- host helper on psd() output
  * --------------------------------------------------------------------------------------------- */
 typedef struct {

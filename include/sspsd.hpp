@@ -255,6 +255,48 @@ private:
     sspsd_decoder* d_ = nullptr;
 };
 
+/// Data::Noise / Data::Dsm of src/source.rs:66-79, 104-134, generated on the device.
+class Source {
+public:
+    static constexpr uint64_t SEED = 0x7654321;  // source.rs:69
+    /// `--noise e` (source.rs:40-42): PSD ~ f^e
+    static Source noise(int32_t exponent, uint64_t seed = SEED, int device = 0, void* stream = nullptr)
+    {
+        return Source(SSPSD_SOURCE_NOISE, exponent, seed, device, stream);
+    }
+    /// `--dsm ftw` (source.rs:44-46): MASH-1-1-1 modulated sine marker
+    static Source dsm(uint32_t ftw, int device = 0, void* stream = nullptr)
+    {
+        return Source(SSPSD_SOURCE_DSM, (int64_t)ftw, 0, device, stream);
+    }
+    Source(int32_t kind, int64_t param, uint64_t seed, int device, void* stream)
+    {
+        check(sspsd_source_create(kind, param, seed, device, stream, &h_));
+    }
+    Source(const Source&) = delete;
+    Source& operator=(const Source&) = delete;
+    Source(Source&& o) noexcept : h_(o.h_) { o.h_ = nullptr; }
+    ~Source() { sspsd_source_destroy(h_); }
+    void reset() { check(sspsd_source_reset(h_)); }
+    uint64_t position() const
+    {
+        uint64_t p;
+        check(sspsd_source_position(h_, &p));
+        return p;
+    }
+    /// Source::get: the next n samples into device memory
+    void get(float* d_out, size_t n) { check(sspsd_source_generate(h_, d_out, n)); }
+    /// feed the next n samples to a cascade without touching host memory
+    template <size_t N>
+    void feed(PsdCascade<N>& c, size_t n)
+    {
+        check(sspsd_cascade_process_source(c.handle(), h_, n));
+    }
+
+private:
+    sspsd_source* h_ = nullptr;
+};
+
 /// struct Var + VarBuilder defaults, src/var.rs:4-45
 struct Var {
     int32_t x_exp = -2;

@@ -122,6 +122,11 @@ def lib():
         "orc_loss_ratio": (C.c_float, [C.POINTER(LossC)]),
         "orc_var_eval": (C.c_float, [C.c_int, C.c_int, C.c_float, C.c_size_t, _fp, _fp, C.c_size_t,
                                      C.c_float]),
+        "orc_philox4x32_10": (None, [C.POINTER(C.c_uint32), C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]),
+        "orc_source_new": (vp, [C.c_int, C.c_int64, C.c_uint64]),
+        "orc_source_free": (None, [vp]),
+        "orc_source_get": (None, [vp, _fp, C.c_size_t]),
+        "orc_dsm_input": (C.c_uint32, [C.c_uint64, C.c_uint32]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(L, name)
@@ -327,3 +332,37 @@ class Loss:
 def var_eval(phase_psd, frequencies, tau, x_exp=-2, sinx_exp=4, clip=3.4028234663852886e38, dc_cut=2):
     p, f = _f32(phase_psd), _f32(frequencies)
     return lib().orc_var_eval(x_exp, sinx_exp, clip, dc_cut, _ptr(p), _ptr(f), min(p.size, f.size), tau)
+
+
+SOURCE_NOISE, SOURCE_DSM = 0, 1
+
+
+def philox4x32_10(ctr, key):
+    c = (C.c_uint32 * 4)(*ctr)
+    k = (C.c_uint32 * 2)(*key)
+    o = (C.c_uint32 * 4)()
+    lib().orc_philox4x32_10(c, k, o)
+    return tuple(o)
+
+
+class Source:
+    """Data::Noise / Data::Dsm of source.rs:66-73, 104-134 (sequential f32 restatement)."""
+
+    def __init__(self, kind, param, seed=0x7654321):
+        self.h = lib().orc_source_new(kind, param, seed)
+        if not self.h:
+            raise ValueError("unsupported source")
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            lib().orc_source_free(self.h)
+            self.h = None
+
+    def get(self, n):
+        out = np.empty(n, dtype=np.float32)
+        lib().orc_source_get(self.h, _ptr(out), n)
+        return out
+
+
+def dsm_input(i, ftw):
+    return lib().orc_dsm_input(i, ftw)

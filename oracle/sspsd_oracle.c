@@ -935,3 +935,133 @@ float orc_var_eval(int x_exp, int sinx_exp, float clip, size_t dc_cut, const flo
     }
     return accu;
 }
+
+/* ------------------------------------------------------------------------------------------
+ * Synthetic sources (source.rs:66-73, 104-134)
+ * ------------------------------------------------------------------------------------------ */
+void orc_philox4x32_10(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4])
+{
+    /* Salmon et al., "Parallel random numbers: as easy as 1, 2, 3" (SC'11), Philox-4x32, 10 rounds */
+    uint32_t c0 = ctr[0], c1 = ctr[1], c2 = ctr[2], c3 = ctr[3], k0 = key[0], k1 = key[1];
+    for (int r = 0; r < 10; r++) {
+        uint64_t p0 = (uint64_t)0xD2511F53u * c0, p1 = (uint64_t)0xCD9E8D57u * c2;
+        uint32_t n0 = (uint32_t)(p1 >> 32) ^ c1 ^ k0, n2 = (uint32_t)(p0 >> 32) ^ c3 ^ k1;
+        c1 = (uint32_t)p1;
+        c3 = (uint32_t)p0;
+        c0 = n0;
+        c2 = n2;
+        k0 += 0x9E3779B9u;
+        k1 += 0xBB67AE85u;
+    }
+    out[0] = c0;
+    out[1] = c1;
+    out[2] = c2;
+    out[3] = c3;
+}
+
+struct orc_source {
+    int kind;
+    uint64_t pos;
+    /* noise */
+    uint32_t key[2];
+    int diff, order;
+    float state[ORC_SOURCE_MAX_ORDER];
+    /* dsm */
+    uint32_t ftw, a[3];
+    int c2z, c3z, c3zz;
+};
+
+orc_source *orc_source_new(int kind, int64_t param, uint64_t seed)
+{
+    orc_source *s = calloc(1, sizeof(*s));
+    if (!s)
+        return NULL;
+    s->kind = kind;
+    if (kind == ORC_SOURCE_NOISE) {
+        int64_t o = param < 0 ? -param : param;
+        if (o > ORC_SOURCE_MAX_ORDER) {
+            free(s);
+            return NULL;
+        }
+        s->diff = param > 0; /* source.rs:70 */
+        s->order = (int)o;   /* source.rs:71 */
+        s->key[0] = (uint32_t)seed;
+        s->key[1] = (uint32_t)(seed >> 32);
+    } else if (kind == ORC_SOURCE_DSM) {
+        s->ftw = (uint32_t)param;
+    } else {
+        free(s);
+        return NULL;
+    }
+    return s;
+}
+
+void orc_source_free(orc_source *s)
+{
+    free(s);
+}
+
+static float uniform_open01(uint32_t r)
+{
+    /* 23 random mantissa bits in [1, 2), shifted to (0, 1): never 0, never 1 (rand's Open01) */
+    union {
+        uint32_t u;
+        float f;
+    } v;
+    v.u = 0x3f800000u | (r >> 9);
+    return v.f - (1.0f - 5.9604645e-8f);
+}
+
+uint32_t orc_dsm_input(uint64_t i, uint32_t ftw)
+{
+    /* source.rs:119-126: x starts at 1 and advances by ftw (wrapping) after each sample.  The sine
+     * is evaluated in double and rounded to f32 so that host and device agree bit for bit. */
+    const float M = 4294967296.0f;
+    uint32_t x = 1u + (uint32_t)i * ftw;
+    float arg = (float)x * (6.28318530717958647692f / M);
+    float sn = (float)sin((double)arg);
+    float v = (sn * 0.4999f + 0.5f) * M;
+    return (uint32_t)v;
+}
+
+void orc_source_get(orc_source *s, float *out, size_t n)
+{
+    if (s->kind == ORC_SOURCE_NOISE) {
+        const float scale = sqrtf(12.0f);
+        for (size_t j = 0; j < n; j++, s->pos++) {
+            uint32_t ctr[4] = {(uint32_t)(s->pos >> 2), (uint32_t)(s->pos >> 34), 0, 0}, r[4];
+            orc_philox4x32_10(ctr, s->key, r);
+            float x = (uniform_open01(r[s->pos & 3]) - 0.5f) * scale; /* source.rs:109 */
+            for (int k = 0; k < s->order; k++) {                      /* source.rs:110-114 */
+                float st = s->state[k];
+                if (s->diff) {
+                    s->state[k] = x;
+                    x = x - st;
+                } else {
+                    s->state[k] = x + st;
+                    x = st;
+                }
+            }
+            out[j] = x;
+        }
+    } else {
+        for (size_t j = 0; j < n; j++, s->pos++) {
+            uint32_t x = orc_dsm_input(s->pos, s->ftw), t;
+            int c1, c2, c3;
+            t = s->a[0] + x;
+            c1 = t < x;
+            s->a[0] = t;
+            t = s->a[1] + s->a[0];
+            c2 = t < s->a[0];
+            s->a[1] = t;
+            t = s->a[2] + s->a[1];
+            c3 = t < s->a[1];
+            s->a[2] = t;
+            int y = c1 + (c2 - s->c2z) + (c3 - 2 * s->c3z + s->c3zz);
+            s->c2z = c2;
+            s->c3zz = s->c3z;
+            s->c3z = c3;
+            out[j] = (float)y - 0.5f; /* source.rs:127 */
+        }
+    }
+}

@@ -119,6 +119,24 @@ float orc_loss_ratio(const orc_loss *l);                          /* loss.rs:29-
 float orc_var_eval(int x_exp, int sinx_exp, float clip, size_t dc_cut, const float *phase_psd,
                    const float *frequencies, size_t n, float tau);
 
+/* ---- synthetic sources (source.rs:66-73, 104-134) ----
+ * Noise: uniform (0,1) -> (x - 0.5) * sqrt(12), folded through |noise| first-order integrators
+ * (noise < 0) or differentiators (noise > 0) with f32 state, exactly the fold at source.rs:110-114.
+ * The reference draws from rand 0.10 SmallRng (not under /root/reference; SURVEY.md 8c says "we use
+ * our own seeded generators"): here the uniform stream is Philox4x32-10, key = seed, counter = i/4,
+ * word i%4, pinned against the Random123 known-answer vectors (tests/test_oracle_source.py).
+ * Dsm: phase accumulator + MASH-1-1-1 (idsp::Dsm<3>, not under /root/reference: textbook form
+ * y = c1 + D c2 + D^2 c3 over three wrapping u32 accumulators -- parity unpinned). */
+void orc_philox4x32_10(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4]);
+enum { ORC_SOURCE_NOISE = 0, ORC_SOURCE_DSM = 1 };
+#define ORC_SOURCE_MAX_ORDER 8
+typedef struct orc_source orc_source;
+orc_source *orc_source_new(int kind, int64_t param, uint64_t seed);
+void orc_source_free(orc_source *s);
+void orc_source_get(orc_source *s, float *out, size_t n);
+/* the DSM input word of sample index i (source.rs:122-125) */
+uint32_t orc_dsm_input(uint64_t i, uint32_t ftw);
+
 #ifdef __cplusplus
 }
 #endif

@@ -61,6 +61,7 @@ pub struct DecodeInfo {
 }
 enum CCascade {}
 enum CDecoder {}
+enum CSource {}
 
 extern "C" {
     fn sspsd_last_error() -> *const c_char;
@@ -79,6 +80,10 @@ extern "C" {
     fn sspsd_cascade_process_frames(d: *mut CDecoder, cascades: *const *mut CCascade, n: u32, frames: *const u8,
                                     n_frames: usize, frame_len: usize, frame_stride: usize, mem: i32,
                                     loss: *mut CLoss, info: *mut DecodeInfo) -> i32;
+    fn sspsd_source_create(kind: i32, param: i64, seed: u64, device: i32, stream: *mut core::ffi::c_void,
+                           out: *mut *mut CSource) -> i32;
+    fn sspsd_source_destroy(s: *mut CSource);
+    fn sspsd_cascade_process_source(h: *mut CCascade, s: *mut CSource, n: usize) -> i32;
 }
 
 fn check(status: i32) {
@@ -197,5 +202,37 @@ impl FrameDecoder {
 impl Drop for FrameDecoder {
     fn drop(&mut self) {
         unsafe { sspsd_decoder_destroy(self.d) }
+    }
+}
+
+/// `Data::Noise` / `Data::Dsm` (src/source.rs:66-79, 104-134) generated in GPU memory: instead of
+/// `source.get()` handing 4096 host samples to `PsdCascade::process`, `feed` produces and consumes
+/// them on the device.
+pub struct SyntheticSource {
+    s: *mut CSource,
+}
+unsafe impl Send for SyntheticSource {}
+
+impl SyntheticSource {
+    /// `--noise e` (source.rs:40-42, seed as at source.rs:69)
+    pub fn noise(exponent: i32) -> Self {
+        let mut s = ptr::null_mut();
+        unsafe { check(sspsd_source_create(0, exponent as i64, 0x7654321, 0, ptr::null_mut(), &mut s)) };
+        Self { s }
+    }
+    /// `--dsm ftw` (source.rs:44-46)
+    pub fn dsm(ftw: u32) -> Self {
+        let mut s = ptr::null_mut();
+        unsafe { check(sspsd_source_create(1, ftw as i64, 0, 0, ptr::null_mut(), &mut s)) };
+        Self { s }
+    }
+    pub fn feed<const N: usize>(&mut self, cascade: &mut PsdCascade<N>, n: usize) {
+        unsafe { check(sspsd_cascade_process_source(cascade.h, self.s, n)) }
+    }
+}
+
+impl Drop for SyntheticSource {
+    fn drop(&mut self) {
+        unsafe { sspsd_source_destroy(self.s) }
     }
 }

@@ -113,6 +113,12 @@ PROTOTYPES = {
     "sspsd_loss_update": (None, [C.POINTER(LossC), C.c_uint32, C.c_uint8]),
     "sspsd_loss_ratio": (C.c_float, [C.POINTER(LossC)]),
     "sspsd_var_eval": (C.c_float, [C.POINTER(VarC), _vp, _vp, _sz, C.c_float]),
+    "sspsd_source_create": (_i32, [_i32, C.c_int64, C.c_uint64, _i32, _vp, C.POINTER(_vp)]),
+    "sspsd_source_destroy": (None, [_vp]),
+    "sspsd_source_reset": (_i32, [_vp]),
+    "sspsd_source_generate": (_i32, [_vp, _vp, _sz]),
+    "sspsd_source_position": (_i32, [_vp, C.POINTER(C.c_uint64)]),
+    "sspsd_cascade_process_source": (_i32, [_vp, _vp, _sz]),
 }
 
 _lib = None

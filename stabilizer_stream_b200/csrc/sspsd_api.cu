@@ -10,12 +10,6 @@
 using sspsd::Cascade;
 using sspsd::set_error;
 
-struct sspsd_cascade {
-    Cascade c;
-};
-struct sspsd_stage {
-    Cascade c;
-};
 
 struct sspsd_decoder {
     int device = 0;

@@ -177,3 +177,11 @@ private:
 };
 
 }  // namespace sspsd
+
+// the opaque handles of include/sspsd.h
+struct sspsd_cascade {
+    sspsd::Cascade c;
+};
+struct sspsd_stage {
+    sspsd::Cascade c;
+};

@@ -179,6 +179,11 @@ class PsdCascade:
     def process_raw(self, ptr, n, mem):
         L.check(L.lib().sspsd_cascade_process_f32(self._h, ptr, n, mem))
 
+    def process_source(self, source, n):
+        """Feed the next n samples of a device-resident synthetic Source (no host memory involved);
+        the loop of bin/stream_test.rs:52-58 with `--noise` / `--dsm`."""
+        L.check(L.lib().sspsd_cascade_process_source(self._h, source._h, n))
+
     def flush(self):
         L.check(L.lib().sspsd_cascade_flush(self._h))
 
@@ -457,3 +462,59 @@ class Var:
         f = np.ascontiguousarray(frequencies, np.float32)
         v = L.VarC(self.x_exp, self.sinx_exp, self.clip, 0, self.dc_cut)
         return L.lib().sspsd_var_eval(C.byref(v), p.ctypes.data, f.ctypes.data, min(p.size, f.size), tau)
+
+
+class SourceKind(enum.IntEnum):
+    NOISE = 0
+    DSM = 1
+
+
+class Source:
+    """Data::Noise / Data::Dsm of src/source.rs:66-79, 104-134, generated on the device.
+
+    Source.noise(e): power-law noise with PSD ~ f^e (`--noise e`, source.rs:40-42);
+    Source.dsm(ftw): MASH-1-1-1 modulated sine marker (`--dsm ftw`, source.rs:44-46)."""
+
+    SEED = 0x7654321  # source.rs:69
+
+    def __init__(self, kind, param, seed=SEED, device=0, stream=None):
+        if stream is None:
+            stream = _default_stream(device)
+        h = C.c_void_p()
+        L.check(L.lib().sspsd_source_create(int(kind), int(param), int(seed), device, stream, C.byref(h)))
+        self._h = h
+        self.device = device
+
+    @classmethod
+    def noise(cls, exponent, seed=SEED, device=0, stream=None):
+        return cls(SourceKind.NOISE, exponent, seed, device, stream)
+
+    @classmethod
+    def dsm(cls, ftw, device=0, stream=None):
+        return cls(SourceKind.DSM, ftw, 0, device, stream)
+
+    def reset(self):
+        L.check(L.lib().sspsd_source_reset(self._h))
+
+    def position(self):
+        p = C.c_uint64()
+        L.check(L.lib().sspsd_source_position(self._h, C.byref(p)))
+        return p.value
+
+    def generate_raw(self, ptr, n):
+        """next n samples into device memory at ptr (asynchronous on the source's stream)"""
+        L.check(L.lib().sspsd_source_generate(self._h, ptr, n))
+
+    def get(self, n, out=None):
+        """Source::get with a caller-chosen block length: the next n samples as a device tensor"""
+        import torch
+        if out is None:
+            out = torch.empty(n, dtype=torch.float32, device=f"cuda:{self.device}")
+        assert out.is_cuda and out.dtype == torch.float32 and out.is_contiguous() and out.numel() >= n
+        self.generate_raw(out.data_ptr(), n)
+        return out[:n]
+
+    def __del__(self):
+        h, self._h = getattr(self, "_h", None), None
+        if h and L is not None and L._lib is not None:
+            L._lib.sspsd_source_destroy(h)

@@ -78,6 +78,19 @@ int main()
         }
         REQUIRE(threw);
 
+        // device-resident white noise source (source.rs:104-118) through a cascade: flat PSD (psd.rs:637-643)
+        {
+            PsdCascade<N> dn;
+            Source src = Source::noise(0);
+            src.feed(dn, 1 << 20);
+            src.feed(dn, 12345);
+            REQUIRE(src.position() == (1 << 20) + 12345);
+            auto [pn, bn] = dn.psd(MergeOpts());
+            for (const auto& bi : bn)
+                for (size_t k = bi.start; k < bi.start + (bi.bins.second - bi.bins.first) && bi.include; ++k)
+                    REQUIRE(std::fabs(pn[k] * 0.5f - 1.0f) < 10.0f / std::sqrt((float)bi.count));
+        }
+
         // var.rs:52-60
         float v = Var().eval({1000.0f, 100.0f, 1.2f, 3.4f, 5.6f}, {0.0f, 1.0f, 3.0f, 6.0f, 9.0f}, 2.7f);
         REQUIRE(std::fabs(0.13478442f - v) < 1e-6f);

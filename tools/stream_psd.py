@@ -5,7 +5,9 @@ of the GPU cascade: read a source, feed one PsdCascade per trace, then log break
 Sources (reference src/source.rs:16-48, 102-167):
   --raw FILE          native-endian f32 samples, no header (what stream_to_raw writes, stream_to_raw.rs:20-26)
   --file FILE         stabilizer frames of --frame-size bytes each (default 8 + 30*2*6*4 like source.rs:29-31)
-  --noise N           synthetic power-law noise f^N generated on the device (|N| integrators/differentiators)
+  --noise N           synthetic power-law noise f^N generated on the device (|N| integrators/differentiators,
+                      source.rs:104-118)
+  --dsm FTW           MASH-1-1-1 modulated sine marker generated on the device (source.rs:119-130)
 --repeat wraps files around; the run ends after --samples items per trace (files: at EOF without --repeat).
 Host reads go through a pinned double buffer, so the H2D copy of block b+1 overlaps the kernels of block b.
 """
@@ -19,27 +21,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np  # noqa: E402
 import torch  # noqa: E402
 
-from stabilizer_stream_b200 import (Break, Detrend, FrameDecoder, Loss, MergeOpts, PsdCascade, Var)  # noqa: E402
-
-
-def noise_blocks(power, block, dev, seed=0x7654321):
-    """Power-law noise like source.rs:104-121: uniform(-0.5, 0.5)*sqrt(12) through |power| integrators
-    (power < 0: y[i] = sum_{j<i} x[j]) or differentiators (power > 0: y[i] = x[i] - x[i-1]), streamed."""
-    g = torch.Generator(device=dev).manual_seed(seed)
-    state = [torch.zeros((), device=dev, dtype=torch.float64) for _ in range(abs(power))]
-    while True:
-        x = ((torch.rand(block, device=dev, generator=g) - 0.5) * (12 ** 0.5)).double()
-        for s in range(abs(power)):
-            if power > 0:
-                prev = torch.cat([state[s].reshape(1), x[:-1]])
-                state[s] = x[-1].clone()
-                x = x - prev
-            else:
-                c = torch.cumsum(x, 0) + state[s]
-                y = torch.cat([state[s].reshape(1), c[:-1]])
-                state[s] = c[-1].clone()
-                x = y
-        yield x.float()
+from stabilizer_stream_b200 import (Break, Detrend, FrameDecoder, Loss, MergeOpts, PsdCascade, Source, Var)  # noqa: E402
 
 
 def main():
@@ -48,6 +30,7 @@ def main():
     ap.add_argument("--file")
     ap.add_argument("--frame-size", type=int, default=8 + 30 * 2 * 6 * 4)
     ap.add_argument("--noise", type=int)
+    ap.add_argument("--dsm", type=int)
     ap.add_argument("--repeat", action="store_true")
     ap.add_argument("--samples", type=float, default=0, help="stop after this many items per trace (0: until EOF)")
     ap.add_argument("--fft", type=int, default=512, help="FFT size N (the reference binaries use 512)")
@@ -69,16 +52,16 @@ def main():
             c.set_detrend(det)
             cas.append(c)
 
-    if a.noise is not None:
+    if a.noise is not None or a.dsm is not None:
         cascades(1)
-        names = ["noise"]
-        for x in noise_blocks(a.noise, a.block, dev):
-            if limit and total + x.numel() > limit:
-                x = x[:limit - total]
-            cas[0].process(x)
-            total += x.numel()
-            if limit == 0 or total >= limit:
-                break
+        names = ["noise" if a.dsm is None else "dsm"]
+        src = Source.noise(a.noise) if a.dsm is None else Source.dsm(a.dsm)
+        if limit == 0:
+            ap.error("--noise/--dsm need --samples")
+        while total < limit:
+            n = min(a.block, limit - total)
+            cas[0].process_source(src, n)  # generated and consumed on the device
+            total += n
     elif a.raw:
         cascades(1)
         names = ["raw"]
@@ -122,7 +105,7 @@ def main():
                 if limit and total >= limit:
                     break
     else:
-        ap.error("one of --raw, --file, --noise is required")
+        ap.error("one of --raw, --file, --noise, --dsm is required")
 
     c = cas[min(a.trace, len(cas) - 1)]
     y, b = c.psd(MergeOpts())
