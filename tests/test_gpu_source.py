@@ -118,10 +118,12 @@ def test_process_source_equals_process_of_the_generated_stream(sp, oracle, param
         np.testing.assert_allclose(np.asarray(pa)[inc][4:], np.asarray(po)[inc][4:], rtol=1e-3)
 
 
-@pytest.mark.parametrize("param", [1, 2, -1, -2])
+@pytest.mark.parametrize("param", [1, 2, 3, -1])
 def test_power_law_shape(sp, param):
     """each differentiator / integrator multiplies the PSD by (2 sin(pi f))^(+-2); white level is 2
-    in the reference's normalisation (0.5 * p ~ 1, psd.rs:629)"""
+    in the reference's normalisation (0.5 * p ~ 1, psd.rs:629).  (Two or more integrators are not
+    testable this way: the f32 samples of a 2^24-step double random walk are quantised far above the
+    f^-4 law's high-frequency level, in the reference as much as here.)"""
     n = 1 << 24
     g = sp.Psd(1024, sp.Window.HANN)
     g.set_detrend(sp.Detrend.MEAN)
