@@ -44,7 +44,8 @@ enum {
     SSPSD_ESIZE = 7,          /* de::Error::PayloadSize,   src/de/mod.rs:25-26 */
     SSPSD_EBATCHES = 8,       /* header batch count != payload batches: assert_eq! panic, src/de/data.rs:24,93,150,174 */
     SSPSD_ESHORT = 9,         /* output capacity too small, or frame shorter than its header (src/de/frame.rs:50 panics) */
-    SSPSD_ENCCL = 10          /* reserved for collective failures */
+    SSPSD_ENCCL = 10,         /* reserved for collective failures */
+    SSPSD_EIO = 11            /* socket error of the UDP receiver (std::io::Error in src/source.rs:81-93, 161) */
 };
 
 enum { SSPSD_MEM_HOST = 0, SSPSD_MEM_DEVICE = 1 };
@@ -317,6 +318,33 @@ int32_t sspsd_source_position(const sspsd_source *s, uint64_t *pos);
 /* generate the next n samples straight into the cascade (stream_test.rs:52-58 with a synthetic
  * source): no host memory is touched; generation and consumption share the cascade's stream */
 int32_t sspsd_cascade_process_source(sspsd_cascade *c, sspsd_source *s, size_t n);
+
+/* ---------------------------------------------------------------------------------------------
+ * UDP ingest: the Data::Udp source of src/source.rs:81-93 (socket set-up: 1 MiB receive buffer,
+ * reuse-address, multicast join, bind) and 159-165 (one `socket.read` + Frame::from_bytes +
+ * loss.update + traces per datagram).  Here datagrams are collected with recvmmsg into a ring of
+ * page-locked slots of slot_bytes each (default 2048 like the reference's read buffer,
+ * source.rs:160; a longer datagram is cut the same way) and handed over as one strided frame array,
+ * so a batch crosses PCIe once and is decoded by one kernel pass.
+ * --------------------------------------------------------------------------------------------- */
+typedef struct sspsd_receiver sspsd_receiver;
+enum { SSPSD_RECV_PINNED = 0, SSPSD_RECV_PAGEABLE = 1 /* plain host memory: hosts without a CUDA device */ };
+/* ip: dotted IPv4 (SourceOpts::ip, default "0.0.0.0"); port: SourceOpts::port (default 9293), 0 picks
+ * a free port; slot_bytes: 0 = 2048, multiple of 8; n_slots: 0 = 1024 */
+int32_t sspsd_receiver_create(const char *ip, uint16_t port, uint32_t slot_bytes, uint32_t n_slots, int32_t flags,
+                              sspsd_receiver **out);
+void sspsd_receiver_destroy(sspsd_receiver *r);
+/* bound port, slot size (= frame_stride of the runs) and datagrams received so far; any pointer may be NULL */
+int32_t sspsd_receiver_info(const sspsd_receiver *r, uint16_t *port, size_t *slot_bytes, uint64_t *datagrams);
+/* The next run of up to max_frames equally sized datagrams, in arrival order: *frames points at the
+ * first slot, consecutive frames are slot_bytes apart, the memory stays valid until the next call.
+ * Waits up to timeout_ms for the first datagram (the reference's read timeout is 1000 ms,
+ * source.rs:83); *n_frames == 0 on timeout. */
+int32_t sspsd_receiver_recv(sspsd_receiver *r, uint32_t max_frames, int32_t timeout_ms, const uint8_t **frames,
+                            size_t *n_frames, size_t *frame_len);
+/* recv + sspsd_cascade_process_frames in one call (info->frames_ok == 0 on timeout) */
+int32_t sspsd_receiver_pump(sspsd_receiver *r, sspsd_decoder *d, sspsd_cascade *const *cascades, uint32_t n_cascades,
+                            uint32_t max_frames, int32_t timeout_ms, sspsd_loss *loss, sspsd_decode_info *info);
 
 /* ---------------------------------------------------------------------------------------------
  * Var::eval (AVAR/MVAR/FVAR from a phase PSD), src/var.rs:26-45 -- host helper on psd() output

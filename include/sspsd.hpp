@@ -297,6 +297,40 @@ private:
     sspsd_source* h_ = nullptr;
 };
 
+/// Data::Udp of src/source.rs:81-93, 159-165: recvmmsg into page-locked slots, decoded per batch.
+class Receiver {
+public:
+    explicit Receiver(const char* ip = "0.0.0.0", uint16_t port = 9293, uint32_t slot_bytes = 2048,
+                      uint32_t n_slots = 1024, bool pinned = true)
+    {
+        check(sspsd_receiver_create(ip, port, slot_bytes, n_slots, pinned ? SSPSD_RECV_PINNED : SSPSD_RECV_PAGEABLE, &h_));
+    }
+    Receiver(const Receiver&) = delete;
+    Receiver& operator=(const Receiver&) = delete;
+    ~Receiver() { sspsd_receiver_destroy(h_); }
+    uint16_t port() const
+    {
+        uint16_t p;
+        check(sspsd_receiver_info(h_, &p, nullptr, nullptr));
+        return p;
+    }
+    /// next run of equally sized datagrams: {first slot, count, datagram length}; slots are slot_bytes apart
+    struct Run {
+        const uint8_t* frames;
+        size_t n_frames, frame_len;
+    };
+    Run recv(uint32_t max_frames = 1024, int32_t timeout_ms = 1000)
+    {
+        Run r{};
+        check(sspsd_receiver_recv(h_, max_frames, timeout_ms, &r.frames, &r.n_frames, &r.frame_len));
+        return r;
+    }
+    sspsd_receiver* handle() const { return h_; }
+
+private:
+    sspsd_receiver* h_ = nullptr;
+};
+
 /// struct Var + VarBuilder defaults, src/var.rs:4-45
 struct Var {
     int32_t x_exp = -2;

@@ -10,13 +10,13 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libsspsd.so")
 
-OK, EINVAL, EUNIMPLEMENTED, ECUDA, ENOMEM, EHEADER, EFORMAT, ESIZE, EBATCHES, ESHORT, ENCCL = range(11)
+OK, EINVAL, EUNIMPLEMENTED, ECUDA, ENOMEM, EHEADER, EFORMAT, ESIZE, EBATCHES, ESHORT, ENCCL, EIO = range(12)
 MEM_HOST, MEM_DEVICE = 0, 1
 MAX_STAGES = 16
 MAX_TRACES = 4
 
 STATUS_NAMES = {0: "OK", 1: "EINVAL", 2: "EUNIMPLEMENTED", 3: "ECUDA", 4: "ENOMEM", 5: "EHEADER", 6: "EFORMAT",
-                7: "ESIZE", 8: "EBATCHES", 9: "ESHORT", 10: "ENCCL"}
+                7: "ESIZE", 8: "EBATCHES", 9: "ESHORT", 10: "ENCCL", 11: "EIO"}
 
 
 class Config(C.Structure):
@@ -119,6 +119,12 @@ PROTOTYPES = {
     "sspsd_source_generate": (_i32, [_vp, _vp, _sz]),
     "sspsd_source_position": (_i32, [_vp, C.POINTER(C.c_uint64)]),
     "sspsd_cascade_process_source": (_i32, [_vp, _vp, _sz]),
+    "sspsd_receiver_create": (_i32, [C.c_char_p, C.c_uint16, C.c_uint32, C.c_uint32, _i32, C.POINTER(_vp)]),
+    "sspsd_receiver_destroy": (None, [_vp]),
+    "sspsd_receiver_info": (_i32, [_vp, C.POINTER(C.c_uint16), _psz, C.POINTER(C.c_uint64)]),
+    "sspsd_receiver_recv": (_i32, [_vp, C.c_uint32, _i32, C.POINTER(_vp), _psz, _psz]),
+    "sspsd_receiver_pump": (_i32, [_vp, _vp, C.POINTER(_vp), C.c_uint32, C.c_uint32, _i32, C.POINTER(LossC),
+                                   C.POINTER(DecodeInfoC)]),
 }
 
 _lib = None

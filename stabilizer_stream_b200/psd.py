@@ -518,3 +518,63 @@ class Source:
         h, self._h = getattr(self, "_h", None), None
         if h and L is not None and L._lib is not None:
             L._lib.sspsd_source_destroy(h)
+
+
+class Receiver:
+    """Data::Udp of src/source.rs:81-93, 159-165: datagrams collected with recvmmsg into page-locked
+    slots and handed on as runs of equally sized frames.
+
+    Receiver(ip, port): SourceOpts::{ip, port} (source.rs:17-23).  `pinned=False` keeps the slots in
+    plain host memory (hosts without a CUDA device)."""
+
+    def __init__(self, ip="0.0.0.0", port=9293, slot_bytes=2048, n_slots=1024, pinned=True):
+        h = C.c_void_p()
+        L.check(L.lib().sspsd_receiver_create(ip.encode(), port, slot_bytes, n_slots, 0 if pinned else 1, C.byref(h)))
+        self._h = h
+
+    def _info(self):
+        port, slot, n = C.c_uint16(), C.c_size_t(), C.c_uint64()
+        L.check(L.lib().sspsd_receiver_info(self._h, C.byref(port), C.byref(slot), C.byref(n)))
+        return port.value, slot.value, n.value
+
+    @property
+    def port(self):
+        return self._info()[0]
+
+    @property
+    def slot_bytes(self):
+        return self._info()[1]
+
+    @property
+    def datagrams(self):
+        return self._info()[2]
+
+    def recv(self, max_frames=1024, timeout_ms=1000):
+        """-> (frames, frame_len): frames is a (n, slot_bytes) uint8 view of the slots (valid until the
+        next call), the first frame_len bytes of each row are the datagram; n == 0 on timeout"""
+        ptr, n, ln = C.c_void_p(), C.c_size_t(), C.c_size_t()
+        L.check(L.lib().sspsd_receiver_recv(self._h, max_frames, timeout_ms, C.byref(ptr), C.byref(n), C.byref(ln)))
+        slot = self.slot_bytes
+        if n.value == 0:
+            return np.empty((0, slot), np.uint8), 0
+        buf = (C.c_uint8 * (n.value * slot)).from_address(ptr.value)
+        return np.frombuffer(buf, np.uint8).reshape(n.value, slot), ln.value
+
+    def pump(self, decoder, cascades, loss: "Loss" = None, max_frames=1024, timeout_ms=1000):
+        """recv + FrameDecoder.process_frames in one call; returns the decode info (frames_ok == 0 on
+        timeout).  Malformed datagrams raise DecodeError like process_frames."""
+        hs = (C.c_void_p * L.MAX_TRACES)()
+        for t, c in enumerate(cascades[:L.MAX_TRACES]):
+            hs[t] = c._h if c is not None else None
+        info = L.DecodeInfoC()
+        st = L.lib().sspsd_receiver_pump(self._h, decoder._h, hs, min(len(cascades), L.MAX_TRACES), max_frames,
+                                         timeout_ms, C.byref(loss.c) if loss is not None else None, C.byref(info))
+        if L.EHEADER <= st <= L.ESHORT:
+            raise DecodeError(st, info.frames_ok)
+        L.check(st)
+        return info
+
+    def __del__(self):
+        h, self._h = getattr(self, "_h", None), None
+        if h and L is not None and getattr(L, "_lib", None) is not None:
+            L._lib.sspsd_receiver_destroy(h)
