@@ -54,3 +54,34 @@ def test_frame_file_source(tmp_path, oracle):
 def test_noise_source_runs():
     out = run(["--noise", "-1", "--samples", "5e6", "--fft", "512"])
     assert out["items_per_trace"] == 5_000_000 and out["breaks"][-1]["count"] > 1000
+
+
+def test_dsm_source_runs():
+    out = run(["--dsm", str(0x1234567), "--samples", "3e6", "--fft", "512"])
+    assert out["trace"] == "dsm" and out["items_per_trace"] == 3_000_000
+
+
+def test_udp_source(tmp_path):
+    """the reference's default source: a live UDP stream (here: loopback, resent until the driver has enough)"""
+    import socket
+    import time
+    data, flen, stride, _ = make_frames(1, 22, 64, seed=8)
+    port = 19293
+    p = subprocess.Popen([sys.executable, os.path.join(ROOT, "tools", "stream_psd.py"), "--json", "--udp",
+                          "127.0.0.1:%d" % port, "--samples", "200000", "--fft", "512"],
+                         stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
+    tx = socket.socket(socket.AF_INET, socket.SOCK_DGRAM)
+    t0 = time.time()
+    seq = 0
+    while p.poll() is None and time.time() - t0 < 300:
+        for f in range(64):
+            fr = bytearray(data[f * stride:f * stride + flen])
+            fr[4:8] = seq.to_bytes(4, "little")  # keep the sequence continuous across resends
+            seq = (seq + 22) & 0xFFFFFFFF
+            tx.sendto(bytes(fr), ("127.0.0.1", port))
+        time.sleep(0.02)
+    out, err = p.communicate(timeout=60)
+    assert p.returncode == 0, err
+    res = json.loads(out.strip().splitlines()[-1])
+    assert res["traces"] == 4 and res["items_per_trace"] >= 200_000
+    assert res["loss"]["received"] * 8 >= 200_000

@@ -7,6 +7,8 @@ Sources (reference src/source.rs:16-48, 102-167):
   --file FILE         stabilizer frames of --frame-size bytes each (default 8 + 30*2*6*4 like source.rs:29-31)
   --noise N           synthetic power-law noise f^N generated on the device (|N| integrators/differentiators,
                       source.rs:104-118)
+  --udp IP:PORT       live Stabilizer stream (source.rs:81-93, 159-165): recvmmsg batches into page-locked slots;
+                      ends after --samples items per trace or 1 s without traffic
   --dsm FTW           MASH-1-1-1 modulated sine marker generated on the device (source.rs:119-130)
 --repeat wraps files around; the run ends after --samples items per trace (files: at EOF without --repeat).
 Host reads go through a pinned double buffer, so the H2D copy of block b+1 overlaps the kernels of block b.
@@ -21,7 +23,8 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np  # noqa: E402
 import torch  # noqa: E402
 
-from stabilizer_stream_b200 import (Break, Detrend, FrameDecoder, Loss, MergeOpts, PsdCascade, Source, Var)  # noqa: E402
+from stabilizer_stream_b200 import (Break, Detrend, FrameDecoder, Loss, MergeOpts, PsdCascade, Receiver, Source,
+                                    Var)  # noqa: E402
 
 
 def main():
@@ -31,6 +34,7 @@ def main():
     ap.add_argument("--frame-size", type=int, default=8 + 30 * 2 * 6 * 4)
     ap.add_argument("--noise", type=int)
     ap.add_argument("--dsm", type=int)
+    ap.add_argument("--udp")
     ap.add_argument("--repeat", action="store_true")
     ap.add_argument("--samples", type=float, default=0, help="stop after this many items per trace (0: until EOF)")
     ap.add_argument("--fft", type=int, default=512, help="FFT size N (the reference binaries use 512)")
@@ -104,8 +108,23 @@ def main():
                 total += info.samples_per_trace
                 if limit and total >= limit:
                     break
+    elif a.udp:
+        ip, _, port = a.udp.rpartition(":")
+        rx = Receiver(ip or "0.0.0.0", int(port))
+        dec = FrameDecoder()
+        cascades(4)
+        while True:
+            info = rx.pump(dec, cas, loss, max_frames=1024, timeout_ms=1000)
+            if info.frames_ok == 0:
+                break
+            if not names:
+                from stabilizer_stream_b200.psd import TRACE_NAMES, Format
+                names = list(TRACE_NAMES[Format(info.format)])
+            total += info.samples_per_trace
+            if limit and total >= limit:
+                break
     else:
-        ap.error("one of --raw, --file, --noise, --dsm is required")
+        ap.error("one of --raw, --file, --udp, --noise, --dsm is required")
 
     c = cas[min(a.trace, len(cas) - 1)]
     y, b = c.psd(MergeOpts())
