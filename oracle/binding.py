@@ -180,8 +180,8 @@ class Hbf8:
         return y
 
     def __del__(self):
-        if getattr(self, "_h", None):
-            lib().orc_hbf8_free(self._h)
+        if getattr(self, "_h", None) and _lib is not None:  # (module globals vanish at interpreter exit)
+            _lib.orc_hbf8_free(self._h)
             self._h = None
 
 
@@ -225,8 +225,8 @@ class Stage:
         return out[:n]
 
     def __del__(self):
-        if getattr(self, "_h", None):
-            lib().orc_stage_free(self._h)
+        if getattr(self, "_h", None) and _lib is not None:  # (module globals vanish at interpreter exit)
+            _lib.orc_stage_free(self._h)
             self._h = None
 
 
@@ -276,8 +276,8 @@ class Cascade:
         return p[:n].copy(), [b[i] for i in range(nb.value)]
 
     def __del__(self):
-        if getattr(self, "_h", None):
-            lib().orc_cascade_free(self._h)
+        if getattr(self, "_h", None) and _lib is not None:  # (module globals vanish at interpreter exit)
+            _lib.orc_cascade_free(self._h)
             self._h = None
 
 
@@ -354,8 +354,8 @@ class Source:
             raise ValueError("unsupported source")
 
     def __del__(self):
-        if getattr(self, "h", None):
-            lib().orc_source_free(self.h)
+        if getattr(self, "h", None) and _lib is not None:  # (module globals vanish at interpreter exit)
+            _lib.orc_source_free(self.h)
             self.h = None
 
     def get(self, n):

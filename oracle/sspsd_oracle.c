@@ -627,8 +627,14 @@ orc_cascade *orc_cascade_new(int n, int hbf_preset)
     c->detrend = ORC_DETREND_NONE;              /* psd.rs:418 */
     c->avg_limit = UINT32_MAX;                  /* psd.rs:369-376 */
     c->avg_count = UINT32_MAX;
-    c->a0 = (float *)calloc((size_t)n, sizeof(float));
-    c->a1 = (float *)calloc((size_t)n, sizeof(float));
+    /* The reference ping-pongs two [f32; N] arrays (psd.rs:457).  That is one decimated item short
+     * in a corner it never meets with its own sources: when a stage's first-ever segment completes
+     * inside an 8N chunk that also completes 15 more (possible only if an earlier short call left
+     * more than N/2 items pending), the chunk yields N/8 - drain + 15 N/16 > N items and the slice
+     * `y[n..][..xb.len()]` (psd.rs:253) panics.  The restatement continues the arithmetic instead
+     * (buffers of 2N), which is also what the device library does; tests/test_gpu_psd.py covers it. */
+    c->a0 = (float *)calloc(2 * (size_t)n, sizeof(float));
+    c->a1 = (float *)calloc(2 * (size_t)n, sizeof(float));
     return c;
 }
 

@@ -772,7 +772,8 @@ int Cascade::feed_host_chunk(const float* xh, size_t n)
         rc = add_stage();
         if (rc) return rc;
     }
-    rc = ensure_in_buffers(std::min<uint64_t>(std::max<uint64_t>(n, host_chunk()), cfg_.max_batch) + 4);
+    // sized for the usual chunk so that a stream of equal chunks allocates once; never smaller than n
+    rc = ensure_in_buffers(std::max<uint64_t>(n, std::min<uint64_t>(host_chunk(), cfg_.max_batch)) + 4);
     if (rc) return rc;
     StageState& st = stages_[0];
     const long long split = floor4((long long)st.L);
@@ -797,8 +798,12 @@ int Cascade::flush_staged()
     if (staged_ == 0)
         return SSPSD_OK;
     const int hb = stage_buf_;
-    int rc = feed_host_chunk(h_stage_[hb], staged_);
-    if (rc) return rc;
+    // max_batch bounds every launch, also when it is smaller than the staging buffer
+    const size_t chunk = (size_t)std::min<uint64_t>(host_chunk(), cfg_.max_batch);
+    for (size_t pos = 0; pos < staged_; pos += chunk) {
+        int rc = feed_host_chunk(h_stage_[hb] + pos, std::min(chunk, staged_ - pos));
+        if (rc) return rc;
+    }
     // the pinned buffer may be refilled only after this H2D copy has completed
     SSPSD_CUDA(cudaEventRecord(ev_stage_[hb], copy_stream_));
     stage_pending_[hb] = true;

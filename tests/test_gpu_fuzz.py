@@ -22,11 +22,29 @@ def check(g, o, sp, what):
             floor = 1e-5 * np.median(w)
             rel = (np.abs(p[sl] - w) - floor) / np.maximum(w, 1e-300)
             # bins next to DC hold what is left of the (decimation-amplified) DC offset after detrending: a
-            # difference of nearly equal numbers, set by how the f32 offset was rounded (tests/test_gpu_psd.py)
-            assert np.max(rel[4:]) < 1e-4 and np.max(rel[:4]) < 2e-2, "%s: stage dec=%d rel %.3g" % (what, k.decimation, np.max(rel))
+            # difference of nearly equal numbers, set by how the f32 offset was rounded (tests/test_gpu_psd.py).
+            # Under Detrend::Span the reference accumulates `offset += slope` sequentially in f32
+            # (psd.rs:98-101): inside a binade every step adds the slope rounded to a multiple of ulp(offset),
+            # a systematic error of up to ulp/2 per step, i.e. a ramp of up to N ulp/2 over the segment.  The
+            # device evaluates x0 + i*slope with one rounding.  The ramp leaks into bin k with amplitude ~1/k,
+            # so against a single noisy segment the two differ by ~N^1.5 2^-24 / k relative (1e-3 at N = 8192,
+            # k = 4; 2e-5 at N = 512): the tolerance widens accordingly near DC.
+            kk = np.arange(rel.size, dtype=np.float64)
+            tol = 1e-4 + float(k.fft_size) ** 1.5 * 2.0 ** -24 / np.maximum(kk, 1.0)
+            assert np.all(rel[4:] < tol[4:]) and np.max(rel[:4]) < 2e-2, \
+                "%s: stage dec=%d rel %.3g" % (what, k.decimation, np.max(rel))
 
 
-@pytest.mark.parametrize("seed,n", [(1, 512), (2, 4096), (3, 64), (4, 2048), (5, 512)])
+def _cases():
+    base = [(1, 512), (2, 4096), (3, 64), (4, 2048), (5, 512)]
+    # SSPSD_FUZZ_EXTRA=k adds k more seeded walks over all FFT sizes (for soak runs; default: none)
+    import os
+    extra = int(os.environ.get("SSPSD_FUZZ_EXTRA", "0"))
+    sizes = [64, 128, 256, 512, 1024, 2048, 4096, 8192]
+    return base + [(100 + i, sizes[i % len(sizes)]) for i in range(extra)]
+
+
+@pytest.mark.parametrize("seed,n", _cases())
 def test_random_api_walk(oracle, seed, n):
     import torch
     import stabilizer_stream_b200 as sp

@@ -256,6 +256,25 @@ def test_small_max_batch_chunks_long_inputs(sp, oracle):
         assert_bins_close(p, po, "chunked")
 
 
+@pytest.mark.parametrize("n", [512, 2048])
+def test_first_segment_inside_a_full_chunk(sp, oracle, n):
+    """short first call, then a full 8N chunk: the corner in which the reference's N-sized ping-pong
+    arrays overflow (psd.rs:253 panics); the library and the restatement just continue the stream"""
+    x = uniform_noise(n - 1 + 8 * n + 5 * n, 22)
+    g = sp.PsdCascade(n, host_stage=1 << 10)
+    o = oracle.Cascade(n, 1)
+    for c in (g, o):
+        c.process(x[:n - 1])
+        c.process(x[n - 1:])
+    p, b = g.psd(sp.MergeOpts(keep_overlap=True, min_count=0, keep_transition_band=True))
+    po, bo = o.psd(True, 0, True)
+    assert [breaks_tuple(k) for k in b] == [k.as_tuple() for k in bo]
+    for k in b:
+        if k.count:
+            sl = slice(k.start, k.start + len(k.bins))
+            assert_bins_close(p[sl], po[sl], "first segment in chunk, dec %d" % k.decimation)
+
+
 def test_rect_window_stage_with_decimation(sp, oracle):
     """Window::rectangular (overlap 0, hop = N) through the single-stage API incl. its decimated output."""
     for n in (512, 4096):

@@ -191,6 +191,25 @@ def test_empty_and_short_inputs(oracle):
     assert s.count() == 1 and s.buf().size == 256
 
 
+@pytest.mark.parametrize("preset", [0, 1])
+def test_first_segment_inside_a_full_chunk(oracle, preset):
+    """A short first call followed by a full 8N chunk makes stage 0 emit N/8 - drain + 15 N/16 > N items
+    in one chunk: the reference's [f32; N] ping-pong arrays (psd.rs:457) are too small for that and its
+    slice at psd.rs:253 panics; the restatement continues the arithmetic, and must stay call-size invariant."""
+    n = 512
+    x = uniform_noise(n - 1 + 8 * n + 3 * n, 21)
+    a = oracle.Cascade(n, preset)
+    a.process(x[:n - 1])
+    a.process(x[n - 1:])
+    b = oracle.Cascade(n, preset)
+    for i in range(0, x.size, 300):
+        b.process(x[i:i + 300])
+    pa, ba = a.psd(True, 0, True)
+    pb, bb = b.psd(True, 0, True)
+    assert [k.as_tuple() for k in ba] == [k.as_tuple() for k in bb]
+    assert np.array_equal(pa, pb)
+
+
 def test_var_kat(oracle):
     # reference src/var.rs:52-60
     v = oracle.var_eval([1000.0, 100.0, 1.2, 3.4, 5.6], [0.0, 1.0, 3.0, 6.0, 9.0], 2.7)
