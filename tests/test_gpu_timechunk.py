@@ -71,3 +71,37 @@ def test_window_rejects_ewma():
     c.set_avg(AvgOpts(limit=999, count=2 ** 32 - 2))
     with pytest.raises(_lib.SspsdError):
         c.set_window(0, 1 << 20, 2)
+
+
+def _fuzz_cases():
+    import os
+    return list(range(4)) + [2000 + i for i in range(int(os.environ.get("SSPSD_FUZZ_EXTRA", "0")))]
+
+
+@pytest.mark.parametrize("seed", _fuzz_cases())
+def test_random_time_chunk_plans(seed):
+    """random stream length / rank count / FFT size / tap family / number of locally processed stages:
+    the chunked run must reproduce the sequential run's bookkeeping exactly and its bins to rounding"""
+    import torch
+    from stabilizer_stream_b200 import Hbf, MergeOpts, PsdCascade
+    rng = np.random.default_rng(seed)
+    n = int(rng.choice([64, 128, 256, 512, 1024, 2048, 4096]))
+    world = int(rng.integers(1, 9))
+    hbf = int(rng.integers(0, 2))
+    k = int(rng.integers(1, 4))
+    # long enough that every rank owns at least a few segments of the deepest local stage
+    total = int(rng.integers(world * n * 8 ** k * 2, world * n * 8 ** k * 6)) + int(rng.integers(0, 8 ** k))
+    total = min(total, 60_000_000)
+    if rng.random() < 0.3:  # streams that are short for this many ranks: some ranks own nothing in the deep stages
+        total = int(rng.integers(1, world * n * 8 ** k))
+    x = uniform_noise(total, 300 + seed) + np.float32(0.1)
+    root, plans = run_emulated(x, n, world, k, hbf)
+    p, b = root.psd(MergeOpts(keep_overlap=True, min_count=0, keep_transition_band=True))
+    seq = PsdCascade(n, hbf=Hbf(hbf))
+    seq.process(torch.from_numpy(x).cuda())
+    ps, bs = seq.psd(MergeOpts(keep_overlap=True, min_count=0, keep_transition_band=True))
+    assert [breaks_tuple(v) for v in b] == [breaks_tuple(v) for v in bs]
+    for bi in b:
+        if bi.count:
+            sl = slice(bi.start, bi.start + len(bi.bins))
+            np.testing.assert_allclose(p[sl], ps[sl], rtol=5e-5, atol=1e-5 * float(np.median(ps[sl])))
