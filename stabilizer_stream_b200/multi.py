@@ -229,10 +229,11 @@ def finish_on_root(root, reduced_counts, tails, total, n, hbf, n_local):
         root.set_stream_state(i, st[i][0], st[i][1])
     pos = 0
     for first, tail in tails:
-        assert first == pos or tail.size == 0, "tail slices are not contiguous: %d != %d" % (first, pos)
-        if tail.size:
+        size = int(tail.numel()) if hasattr(tail, "numel") else int(tail.size)
+        assert first == pos or size == 0, "tail slices are not contiguous: %d != %d" % (first, pos)
+        if size:
             root.process_stage(n_local, tail)
-            pos = first + tail.size
+            pos = first + size
     if len(st) > n_local:
         assert pos == st[n_local][0], "tail stream length %d != %d" % (pos, st[n_local][0])
     return root
@@ -262,40 +263,49 @@ def time_chunked_psd(cascade, feed, total, n, dist=None, hbf=1, n_local=3, devic
     cascade.seek(plan["feed_lo"])
     cascade.set_window(plan["own_lo"], plan["own_hi"], n_local)
     feed(plan["feed_lo"], plan["feed_hi"], cascade.process)
-    first, tail = cascade.take_tail(plan["tail_lo"], plan["tail_hi"] if plan["tail_hi"] is not None else 2 ** 63)
-    lap("process+tail")
-    acc, counts = cascade_partials_tensor(cascade)
-    counts = (counts + [0] * 16)[:n_local]
-    if world > 1:
+    tail_hi = plan["tail_hi"] if plan["tail_hi"] is not None else 2 ** 63
+    if world == 1:
+        first, tail = cascade.take_tail(plan["tail_lo"], tail_hi)
+        lap("process+tail")
+        acc, counts = cascade_partials_tensor(cascade)
+        counts = (counts + [0] * 16)[:n_local]
+        tails = [(first, tail)]
+    else:
         # ONE collective for the readout: accumulator rows of the local stages, their counts and the
         # rank's slice of the stage-n_local stream travel in one buffer; rows and counts are summed, the
-        # slices land in disjoint slots (everybody else contributes zeros there)
-        stride = acc.shape[1]
+        # slices land in disjoint slots (everybody else contributes zeros there).  Everything stays on
+        # the device; the root reads back only the 2 * world + n_local bookkeeping numbers.
         slot = (stream_state(total, n, n // 2, DRAIN[hbf]) + [(0, 0, 0)] * 16)[n_local][0] // world + 64
-        buf = torch.zeros(n_local * stride + n_local + world * (slot + 2), dtype=torch.float64, device=device)
-        buf[:n_local * stride] = acc[:n_local].reshape(-1).double()
-        buf[n_local * stride:n_local * stride + n_local] = torch.tensor(counts, dtype=torch.float64, device=device)
-        base = n_local * stride + n_local + rank * (slot + 2)
-        assert tail.size <= slot, "tail slice larger than its slot"
-        buf[base] = float(first)
-        buf[base + 1] = float(tail.size)
-        if tail.size:
-            buf[base + 2:base + 2 + tail.size] = torch.from_numpy(tail).to(device).double()
+        tail32 = torch.empty(slot, dtype=torch.float32, device=device)
+        first, tlen = cascade.take_tail_device(plan["tail_lo"], tail_hi, tail32)
+        lap("process+tail")
+        acc, counts = cascade_partials_tensor(cascade)
+        counts = (counts + [0] * 16)[:n_local]
+        stride = acc.shape[1]
+        nacc = n_local * stride
+        meta = nacc + world * slot
+        buf = torch.zeros(meta + n_local + 2 * world, dtype=torch.float64, device=device)
+        buf[:nacc] = acc[:n_local].reshape(-1)
+        buf[nacc + rank * slot:nacc + rank * slot + tlen] = tail32[:tlen]
+        book = [0.0] * (n_local + 2 * world)
+        book[:n_local] = [float(c) for c in counts]
+        book[n_local + 2 * rank] = float(first)
+        book[n_local + 2 * rank + 1] = float(tlen)
+        buf[meta:] = torch.tensor(book, dtype=torch.float64).to(device, non_blocking=True)
         dist.reduce(buf, dst=0, op=dist.ReduceOp.SUM)
-        torch.cuda.synchronize()
-        lap("reduce")
         if rank != 0:
+            torch.cuda.synchronize()
+            lap("reduce")
             return None
-        acc[:n_local] = buf[:n_local * stride].reshape(n_local, stride).float()
-        counts = [int(v) for v in buf[n_local * stride:n_local * stride + n_local].round().tolist()]
-        host = buf[n_local * stride + n_local:].cpu().numpy()
-        tails = []
-        for r in range(world):
-            seg = host[r * (slot + 2):(r + 1) * (slot + 2)]
-            tails.append((int(seg[0]), seg[2:2 + int(seg[1])].astype(np.float32)))
-        torch.cuda.synchronize()
-    else:
-        tails = [(first, tail)]
+        book = [int(round(v)) for v in buf[meta:].tolist()]  # the one device->host readback (synchronises)
+        lap("reduce")
+        acc[:n_local] = buf[:nacc].reshape(n_local, stride).float()
+        counts = book[:n_local]
+        all32 = buf[nacc:meta].float()
+        torch.cuda.synchronize()  # torch's stream wrote library memory / made the tensors the library reads
+        tails = [(book[n_local + 2 * r], all32[r * slot:r * slot + book[n_local + 2 * r + 1]]) for r in range(world)]
     root = finish_on_root(cascade, counts, tails, total, n, hbf, n_local)
+    if world > 1:
+        root.sync()  # the gathered slices are torch temporaries read asynchronously on the library's deep stream
     lap("finish")
     return root

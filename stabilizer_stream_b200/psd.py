@@ -224,6 +224,14 @@ class PsdCascade:
                                                 L.MEM_HOST))
         return first.value, out[:n.value]
 
+    def take_tail_device(self, j_lo, j_hi, out):
+        """like take_tail, but into the CUDA float32 tensor `out` (no host round trip); -> (first, length)"""
+        n = C.c_size_t(out.numel())
+        first = C.c_uint64(0)
+        L.check(L.lib().sspsd_cascade_take_tail(self._h, j_lo, j_hi, out.data_ptr(), C.byref(n), C.byref(first),
+                                                L.MEM_DEVICE))
+        return first.value, n.value
+
     def process_stage(self, stage, x):
         ptr, n, mem, keep = _as_buffer(x)
         L.check(L.lib().sspsd_cascade_process_stage(self._h, stage, ptr, n, mem))
