@@ -182,7 +182,11 @@ int32_t sspsd_cascade_set_counts(sspsd_cascade *h, const uint64_t *count_raw, ui
  * stages < n_local run locally; the input stream of stage n_local is exported with
  * sspsd_cascade_take_tail(), gathered, and fed to rank 0's handle with sspsd_cascade_process_stage(),
  * which then runs the deep stages; sspsd_cascade_set_stream_state() installs the reduced counts.
- * Boxcar averaging only (EWMA is an order dependent recurrence). */
+ * Averaging (psd.rs:215-233) follows the GLOBAL segment order: with a finite `avg`, a rank weights its owned
+ * segments as the reference would if the stream ended right after its last owned segment; the caller
+ * multiplies each accumulator row by g^(later segments that rescale), g = avg/(avg+1), before the
+ * reduction (stabilizer_stream_b200/multi.py: ewma_tail_factors).  Options must be set before the first
+ * sample and stay constant for the run. */
 int32_t sspsd_cascade_seek(sspsd_cascade *h, uint64_t pos);
 int32_t sspsd_cascade_set_window(sspsd_cascade *h, uint64_t own_lo, uint64_t own_hi, uint32_t n_local);
 /* samples [j_lo, j_hi) of the stage-n_local input stream produced so far (clipped to what exists);
@@ -191,7 +195,7 @@ int32_t sspsd_cascade_take_tail(sspsd_cascade *h, uint64_t j_lo, uint64_t j_hi, 
                                 uint64_t *first, int32_t mem);
 /* feed n samples directly into stage `stage`'s stream (the next samples of that stream, in order) */
 int32_t sspsd_cascade_process_stage(sspsd_cascade *h, uint32_t stage, const float *x, size_t n, int32_t mem);
-/* overwrite stage bookkeeping after an external reduction: samples received, segments accumulated */
+/* overwrite stage bookkeeping after an external reduction: samples received, averaging count (Psd::count) */
 int32_t sspsd_cascade_set_stream_state(sspsd_cascade *h, uint32_t stage, uint64_t samples, uint64_t segments);
 
 /* ---- measurement hooks (no reference analogue) ----

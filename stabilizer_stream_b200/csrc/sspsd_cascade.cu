@@ -533,7 +533,23 @@ int Cascade::run_stage(size_t i, const float* fresh, long long split, uint64_t n
         uint64_t khi = own_hi_ == ~0ull ? ~0ull : first_at_or_after(own_hi_);
         uint64_t a = std::max(craw0, klo), b = std::min(craw1, khi);
         if (b > a) {
-            rc = launch_psd(i, src, a, b - a, (int)(b - a), 1.0f, 1.0f);
+            if (st.avg == 0xffffffffu) {
+                rc = launch_psd(i, src, a, b - a, (int)(b - a), 1.0f, 1.0f);
+            } else {
+                // EWMA follows the global segment order: before global segment a the reference's count
+                // is min(a, avg + 1) (psd.rs:218-225).  The row ends up normalised "as if the stream ended
+                // at b"; the caller multiplies it by g^(segments scaled after b) before the reduction.
+                const uint32_t cnt = (uint32_t)std::min<uint64_t>(a, (uint64_t)st.avg + 1);
+                EwmaPlan e = ewma_plan(cnt, st.avg, b - a);
+                if (e.total != 1.0f) {
+                    int nb = (int)(n_ / 2 + 1);
+                    prof_begin(SSPSD_PROF_OTHER, 0, ss);
+                    scale_kernel<<<(nb + 255) / 256, 256, 0, ss>>>(d_acc_ + i * acc_stride_, nb, e.total);
+                    prof_end(ss);
+                    SSPSD_CUDA(cudaGetLastError());
+                }
+                rc = launch_psd(i, src, a, b - a, e.jb, e.g_first, e.g_s);
+            }
             if (rc) return rc;
             st.count = (uint32_t)std::min<uint64_t>((uint64_t)st.count + (b - a), 0xffffffffull);
         }
@@ -1200,10 +1216,6 @@ int Cascade::set_window(uint64_t own_lo, uint64_t own_hi, uint32_t n_local)
 {
     if (n_local == 0 || n_local > SSPSD_MAX_STAGES || own_hi < own_lo) {
         set_error("bad window");
-        return SSPSD_EINVAL;
-    }
-    if (avg_.limit != 0xffffffffu || avg_.count != 0xffffffffu) {
-        set_error("time-chunk mode supports boxcar averaging only");
         return SSPSD_EINVAL;
     }
     windowed_ = true;

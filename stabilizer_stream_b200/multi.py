@@ -209,6 +209,37 @@ def plan_time_chunks(total, world, n, hbf=1, n_local=3, window_overlap=None):
     return plans
 
 
+def stage_avg(avg, i):
+    """PsdCascade::get_or_add / set_avg: avg_i = min(count >> 3 i, limit) (psd.rs:434, 449)"""
+    if avg is None:
+        return 0xFFFFFFFF
+    return min(avg.count >> (3 * i), avg.limit)
+
+
+def ewma_tail_factors(plan, total, n, hbf, n_local, avg):
+    """Per local stage: the factor a rank's accumulator row is multiplied with before the reduction, and
+    the averaging count (Psd::count) of the completed stage.  A rank's row is normalised as if the stream
+    ended after its last owned segment b; every later segment j rescales the running sum by
+    g = avg/(avg+1) iff the reference's count exceeds avg there, i.e. iff j >= avg + 1 (psd.rs:218-225)."""
+    hop = n // 2
+    drain = DRAIN[hbf]
+    st = stream_state(total, n, hop, drain)
+    factors, counts = [], []
+    for i in range(n_local):
+        a = stage_avg(avg, i)
+        s_i = st[i][1] if i < len(st) else 0
+        if a == 0xFFFFFFFF:
+            factors.append(1.0)
+            counts.append(s_i)
+            continue
+        b = s_i if plan["own_hi"] is None else min(s_i, first_index_at_or_after(plan["own_hi"], i, hop, drain))
+        later = max(0, s_i - max(b, a + 1))
+        g = float(np.float32(a) / np.float32(a + 1))   # the reference divides in f32 (psd.rs:219)
+        factors.append(g ** later)
+        counts.append(min(s_i, a + 1))
+    return factors, counts
+
+
 def run_chunk(cascade, plan, samples, n_local):
     """One rank's share: position the fresh cascade, restrict it, process samples[feed_lo:feed_hi]
     (`samples` is that slice, host or device), and return its slice of the stage-n_local stream."""
@@ -219,14 +250,15 @@ def run_chunk(cascade, plan, samples, n_local):
     return first, tail
 
 
-def finish_on_root(root, reduced_counts, tails, total, n, hbf, n_local):
+def finish_on_root(root, reduced_counts, tails, total, n, hbf, n_local, avg=None):
     """Rank 0 after the reduction of the accumulator rows: install the global bookkeeping of the local
     stages and run the deep stages on the gathered stage-n_local stream."""
     hop = n // 2
     st = stream_state(total, n, hop, DRAIN[hbf])
     for i in range(min(n_local, len(st))):
         assert reduced_counts[i] == st[i][1], "stage %d: %d segments reduced, %d expected" % (i, reduced_counts[i], st[i][1])
-        root.set_stream_state(i, st[i][0], st[i][1])
+        a = stage_avg(avg, i)
+        root.set_stream_state(i, st[i][0], st[i][1] if a == 0xFFFFFFFF else min(st[i][1], a + 1))
     pos = 0
     for first, tail in tails:
         size = int(tail.numel()) if hasattr(tail, "numel") else int(tail.size)
@@ -239,7 +271,7 @@ def finish_on_root(root, reduced_counts, tails, total, n, hbf, n_local):
     return root
 
 
-def time_chunked_psd(cascade, feed, total, n, dist=None, hbf=1, n_local=3, device="cuda", timings=None):
+def time_chunked_psd(cascade, feed, total, n, dist=None, hbf=1, n_local=3, device="cuda", timings=None, avg=None):
     """Distributed driver of the time-chunked mode: every rank calls this with a FRESH cascade and a
     callable feed(lo, hi, sink) that pushes stream samples [lo, hi) into sink(x) in order (any block
     size).  One NCCL sum-reduction of the local stages' accumulator rows + counts, one gather of the
@@ -260,15 +292,22 @@ def time_chunked_psd(cascade, feed, total, n, dist=None, hbf=1, n_local=3, devic
             t[0] = now
 
     plan = plan_time_chunks(total, world, n, hbf, n_local)[rank]
+    if avg is not None:
+        cascade.set_avg(avg)
     cascade.seek(plan["feed_lo"])
     cascade.set_window(plan["own_lo"], plan["own_hi"], n_local)
     feed(plan["feed_lo"], plan["feed_hi"], cascade.process)
+    factors, _ = ewma_tail_factors(plan, total, n, hbf, n_local, avg)
     tail_hi = plan["tail_hi"] if plan["tail_hi"] is not None else 2 ** 63
     if world == 1:
         first, tail = cascade.take_tail(plan["tail_lo"], tail_hi)
         lap("process+tail")
         acc, counts = cascade_partials_tensor(cascade)
         counts = (counts + [0] * 16)[:n_local]
+        for i, f in enumerate(factors):
+            if f != 1.0:
+                acc[i] *= f
+        torch.cuda.synchronize()
         tails = [(first, tail)]
     else:
         # ONE collective for the readout: accumulator rows of the local stages, their counts and the
@@ -286,6 +325,9 @@ def time_chunked_psd(cascade, feed, total, n, dist=None, hbf=1, n_local=3, devic
         meta = nacc + world * slot
         buf = torch.zeros(meta + n_local + 2 * world, dtype=torch.float64, device=device)
         buf[:nacc] = acc[:n_local].reshape(-1)
+        for i, f in enumerate(factors):  # EWMA: weight of everything that follows this rank's chunk
+            if f != 1.0:
+                buf[i * stride:(i + 1) * stride] *= f
         buf[nacc + rank * slot:nacc + rank * slot + tlen] = tail32[:tlen]
         book = [0.0] * (n_local + 2 * world)
         book[:n_local] = [float(c) for c in counts]
@@ -304,7 +346,7 @@ def time_chunked_psd(cascade, feed, total, n, dist=None, hbf=1, n_local=3, devic
         all32 = buf[nacc:meta].float()
         torch.cuda.synchronize()  # torch's stream wrote library memory / made the tensors the library reads
         tails = [(book[n_local + 2 * r], all32[r * slot:r * slot + book[n_local + 2 * r + 1]]) for r in range(world)]
-    root = finish_on_root(cascade, counts, tails, total, n, hbf, n_local)
+    root = finish_on_root(cascade, counts, tails, total, n, hbf, n_local, avg)
     if world > 1:
         root.sync()  # the gathered slices are torch temporaries read asynchronously on the library's deep stream
     lap("finish")

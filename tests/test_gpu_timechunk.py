@@ -9,7 +9,7 @@ from conftest import uniform_noise
 pytestmark = pytest.mark.gpu
 
 
-def run_emulated(x, n, world, n_local, hbf=1):
+def run_emulated(x, n, world, n_local, hbf=1, avg=None):
     import torch
     from stabilizer_stream_b200 import Hbf, MergeOpts, PsdCascade, multi
     plans = multi.plan_time_chunks(x.size, world, n, hbf, n_local)
@@ -17,8 +17,13 @@ def run_emulated(x, n, world, n_local, hbf=1):
     cas, tails, accs, counts = [], [], [], []
     for p in plans:
         c = PsdCascade(n, hbf=Hbf(hbf))
+        if avg is not None:
+            c.set_avg(avg)
         tails.append(multi.run_chunk(c, p, xd[p["feed_lo"]:p["feed_hi"]], n_local))
         t, cnt = multi.cascade_partials_tensor(c)
+        factors, _ = multi.ewma_tail_factors(p, x.size, n, hbf, n_local, avg)
+        for i, f in enumerate(factors):   # what time_chunked_psd does before its reduction
+            t[i] *= f
         cas.append(c)
         accs.append(t)
         counts.append((cnt + [0] * 16)[:16])
@@ -28,7 +33,7 @@ def run_emulated(x, n, world, n_local, hbf=1):
     accs[0][:n_local].copy_(total_acc)
     torch.cuda.synchronize()   # torch's stream wrote into library memory; the library uses its own stream
     red = [sum(c[i] for c in counts) for i in range(n_local)]
-    root = multi.finish_on_root(cas[0], red, tails, x.size, n, hbf, n_local)
+    root = multi.finish_on_root(cas[0], red, tails, x.size, n, hbf, n_local, avg)
     return root, plans
 
 
@@ -65,12 +70,39 @@ def test_time_chunked_equals_sequential(oracle, n, total, world, k, hbf):
     assert all(q["feed_lo"] <= q["own_lo"] for q in plans)
 
 
-def test_window_rejects_ewma():
-    from stabilizer_stream_b200 import AvgOpts, PsdCascade, _lib
-    c = PsdCascade(512)
-    c.set_avg(AvgOpts(limit=999, count=2 ** 32 - 2))
-    with pytest.raises(_lib.SspsdError):
-        c.set_window(0, 1 << 20, 2)
+@pytest.mark.parametrize("n,total,world,k,limit,count", [(512, 3_000_017, 4, 3, 999, 2 ** 32 - 2), (512, 2_000_000, 3, 2, 17, 2 ** 32 - 1),
+                                                          (4096, 30_000_000, 4, 2, 200, 5000), (256, 1_500_000, 5, 3, 0, 64),
+                                                          (512, 1_200_000, 8, 2, 3, 2 ** 32 - 1)])
+def test_time_chunked_ewma_equals_sequential(oracle, n, total, world, k, limit, count):
+    """the `psd` binary's preset (avg limit 999, bin/psd.rs:73-78) and other finite averages: the EWMA is a
+    recurrence over the GLOBAL segment order, so every rank weights its rows for what follows its chunk"""
+    import torch
+    from stabilizer_stream_b200 import AvgOpts, MergeOpts, PsdCascade
+    avg = AvgOpts(limit=limit, count=count)
+    x = uniform_noise(total, 91 + n) + np.float32(0.1)
+    root, plans = run_emulated(x, n, world, k, 1, avg)
+    seq = PsdCascade(n)
+    seq.set_avg(avg)
+    seq.process(torch.from_numpy(x).cuda())
+    o = MergeOpts(keep_overlap=True, min_count=0, keep_transition_band=True)
+    p, b = root.psd(o)
+    ps, bs = seq.psd(o)
+    assert [breaks_tuple(v) + (v.avg,) for v in b] == [breaks_tuple(v) + (v.avg,) for v in bs]
+    for bi in b:
+        if bi.count:
+            sl = slice(bi.start, bi.start + len(bi.bins))
+            np.testing.assert_allclose(p[sl], ps[sl], rtol=5e-5, atol=1e-5 * float(np.median(ps[sl])))
+    # and against the CPU restatement
+    oc = oracle.Cascade(n, 1)
+    oc.set_avg(limit, count)
+    oc.process(x)
+    po, bo = oc.psd(True, 0, True)
+    assert [v.count for v in b] == [v.count for v in bo]
+    for bi in b:
+        if bi.count:
+            sl = slice(bi.start, bi.start + len(bi.bins))
+            floor = 1e-5 * np.median(po[sl])
+            assert np.max((np.abs(p[sl] - po[sl]) - floor) / po[sl]) < 1e-4, "stage dec=%d" % bi.decimation
 
 
 def _fuzz_cases():
@@ -95,9 +127,15 @@ def test_random_time_chunk_plans(seed):
     if rng.random() < 0.3:  # streams that are short for this many ranks: some ranks own nothing in the deep stages
         total = int(rng.integers(1, world * n * 8 ** k))
     x = uniform_noise(total, 300 + seed) + np.float32(0.1)
-    root, plans = run_emulated(x, n, world, k, hbf)
+    from stabilizer_stream_b200 import AvgOpts
+    avg = None
+    if rng.random() < 0.5:
+        avg = AvgOpts(limit=int(rng.choice([0, 1, 5, 60, 999])), count=int(rng.choice([2 ** 32 - 1, 2 ** 32 - 2, 700, 9])))
+    root, plans = run_emulated(x, n, world, k, hbf, avg)
     p, b = root.psd(MergeOpts(keep_overlap=True, min_count=0, keep_transition_band=True))
     seq = PsdCascade(n, hbf=Hbf(hbf))
+    if avg is not None:
+        seq.set_avg(avg)
     seq.process(torch.from_numpy(x).cuda())
     ps, bs = seq.psd(MergeOpts(keep_overlap=True, min_count=0, keep_transition_band=True))
     assert [breaks_tuple(v) for v in b] == [breaks_tuple(v) for v in bs]

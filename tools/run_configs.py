@@ -3,9 +3,13 @@
 JSON line per config (rank 0).  Launch with python (1 GPU) or torchrun (N GPUs, config 5 only).
 
   --config 1   raw f32, single stage N=4096 Hann (Psd handle), 2^28 samples
+  --config 2   PsdCascade N=4096, 200e6 samples per call, default options and the `psd` binary's preset
+               (Detrend::Mean, AvgOpts{limit 999, count u32::MAX-1}, bin/psd.rs:60-78); bench.py measures the
+               default-options case with the full contract, this adds the preset beside it
   --config 3   AdcDac frames (22 batches) -> decode + loss + 4 cascades, 2^20 frames
   --config 5   4.8e9-sample capture, N=4096, time-chunked over WORLD_SIZE GPUs (checked against the
-               sequential 1-GPU run of the same stream when --check is given)
+               sequential 1-GPU run of the same stream when --check is given); --preset uses the binary's
+               options (EWMA over the global segment order)
 """
 import argparse
 import json
@@ -119,14 +123,62 @@ def config3(dev):
             "loss_bit_exact": bool(ok_loss), "received": int(loss.received), "dropped": int(loss.dropped)}
 
 
-def config5(dev, total, n_local, check):
+def config2(dev):
+    from oracle import binding as orc
+    from stabilizer_stream_b200 import AvgOpts, Detrend, MergeOpts, PsdCascade
+    n, per, steps = 4096, 200_000_000, 10
+    x = torch.cat([noise_block(b, dev) for b in range(4)])[:per]
+    out = {"config": 2, "samples_per_call": per, "calls": steps}
+    for name, det, avg in (("default", Detrend.NONE, None), ("binary_preset", Detrend.MEAN, AvgOpts(limit=999, count=2 ** 32 - 2))):
+        c = PsdCascade(n, device=dev.index)
+        c.set_detrend(det)
+        if avg is not None:
+            c.set_avg(avg)
+        for _ in range(3):
+            c.process(x)
+        c.sync()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(steps):
+            c.process(x)
+        p, br = c.psd(MergeOpts())
+        b.record()
+        torch.cuda.synchronize()
+        ms = a.elapsed_time(b)
+        # (the same 200e6-sample block is resubmitted every call, as in bench.py, so the averaged spectrum does
+        # not converge like 1/sqrt(count): no flatness check here; tests/ and config 5 cover that)
+        out[name] = {"GSps": per * steps / ms / 1e6, "ms_per_call": ms / steps, "counts": [k.count for k in reversed(br)],
+                     "avg": [k.avg for k in reversed(br)]}
+    # parity of the preset against the CPU restatement on a bounded prefix (the full stream takes minutes on a core)
+    m = 30_000_000
+    xs = x[:m].cpu().numpy()
+    c = PsdCascade(n, device=dev.index)
+    c.set_detrend(Detrend.MEAN)
+    c.set_avg(AvgOpts(limit=999, count=2 ** 32 - 2))
+    c.process(x[:m])
+    o = orc.Cascade(n, 1)
+    o.set_detrend(3)
+    o.set_avg(999, 2 ** 32 - 2)
+    o.process(xs)
+    p, br = c.psd(MergeOpts())
+    po, bo = o.psd()
+    out["preset_max_rel_vs_cpu_30e6"] = float(np.max(np.abs(p - po)[2:] / np.maximum(po[2:], 1e-30)))
+    out["preset_counts_equal"] = [k.count for k in br] == [k.count for k in bo]
+    return out
+
+
+def config5(dev, total, n_local, check, preset=False):
     import torch.distributed as dist
     from stabilizer_stream_b200 import MergeOpts, PsdCascade, multi
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     d = dist if world > 1 else None
     n = 4096
+    from stabilizer_stream_b200 import AvgOpts, Detrend
+    avg = AvgOpts(limit=999, count=2 ** 32 - 2) if preset else None
     c = PsdCascade(n, device=dev.index)
+    if preset:
+        c.set_detrend(Detrend.MEAN)
     # the rank's share of the capture is generated into HBM first (untimed): feed range of the plan
     plan = multi.plan_time_chunks(total, world, n, 1, n_local)[rank]
     lo, hi = plan["feed_lo"], plan["feed_hi"]
@@ -154,7 +206,7 @@ def config5(dev, total, n_local, check):
         sink(xs)
 
     tim = {}
-    root = multi.time_chunked_psd(c, feed, total, n, d, 1, n_local, str(dev), tim)
+    root = multi.time_chunked_psd(c, feed, total, n, d, 1, n_local, str(dev), tim, avg)
     torch.cuda.synchronize()
     if d is not None:
         d.barrier()
@@ -163,15 +215,18 @@ def config5(dev, total, n_local, check):
         return None
     p, b = root.psd(MergeOpts())
     counts = [k.count for k in reversed(b)]
-    want = [s[1] for s in multi.stream_state(total, n, n // 2, multi.DRAIN[1])]
+    want = [min(s[1], multi.stage_avg(avg, i) + 1) for i, s in enumerate(multi.stream_state(total, n, n // 2, multi.DRAIN[1]))]
     flat = all(bool(np.all(np.abs(p[k.start:k.start + len(k.bins)] * 0.5 - 1.0) < 10.0 / np.sqrt(k.count)))
                for k in b if k.include and k.count >= 20)
-    out = {"config": 5, "samples": total, "world": world, "n_local": n_local, "stage_counts": counts,
+    out = {"config": 5, "preset": bool(preset), "samples": total, "world": world, "n_local": n_local, "stage_counts": counts,
            "counts_match_closed_form": counts == want, "flat_10sigma": flat, "wall_s": dt,
            "MSps": total / dt / 1e6, "phases_s_rank0": tim, "halo_overhead": (hi - lo) * world / total - 1 if world > 1 else 0.0,
            "bins": int(p.size)}
     if check and world > 1:
         seq = PsdCascade(n, device=dev.index)
+        if preset:
+            seq.set_detrend(Detrend.MEAN)
+            seq.set_avg(avg)
         feed_stream(0, total, seq.process, dev)
         ps, bs = seq.psd(MergeOpts())
         out["max_rel_diff_vs_sequential"] = float(np.max(np.abs(p - ps) / np.maximum(ps, 1e-30)))
@@ -191,6 +246,7 @@ def main():
     ap.add_argument("--total", type=float, default=4.8e9)
     ap.add_argument("--n-local", type=int, default=5)
     ap.add_argument("--check", action="store_true")
+    ap.add_argument("--preset", action="store_true")
     a = ap.parse_args()
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
@@ -198,7 +254,8 @@ def main():
     if int(os.environ.get("WORLD_SIZE", "1")) > 1:
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=dev)
-    r = {1: lambda: config1(dev), 3: lambda: config3(dev), 5: lambda: config5(dev, int(a.total), a.n_local, a.check)}[a.config]()
+    r = {1: lambda: config1(dev), 2: lambda: config2(dev), 3: lambda: config3(dev),
+         5: lambda: config5(dev, int(a.total), a.n_local, a.check, a.preset)}[a.config]()
     if r is not None:
         print(json.dumps(r))
     if int(os.environ.get("WORLD_SIZE", "1")) > 1:
