@@ -260,12 +260,22 @@ def finish_on_root(root, reduced_counts, tails, total, n, hbf, n_local, avg=None
         a = stage_avg(avg, i)
         root.set_stream_state(i, st[i][0], st[i][1] if a == 0xFFFFFFFF else min(st[i][1], a + 1))
     pos = 0
+    parts = []
     for first, tail in tails:
         size = int(tail.numel()) if hasattr(tail, "numel") else int(tail.size)
         assert first == pos or size == 0, "tail slices are not contiguous: %d != %d" % (first, pos)
         if size:
-            root.process_stage(n_local, tail)
+            parts.append(tail)
             pos = first + size
+    if parts:
+        # the slices are consecutive pieces of one stream: feed them in one call (one set of launches for
+        # the deep stages instead of one per rank)
+        if len(parts) > 1 and all(hasattr(t, "numel") for t in parts):
+            import torch
+            parts = [torch.cat(parts)]
+            torch.cuda.synchronize()  # made on torch's stream, read on the library's deep stream
+        for t in parts:
+            root.process_stage(n_local, t)
     if len(st) > n_local:
         assert pos == st[n_local][0], "tail stream length %d != %d" % (pos, st[n_local][0])
     return root

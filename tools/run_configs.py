@@ -186,15 +186,13 @@ def config5(dev, total, n_local, check, preset=False):
     feed_stream(lo, hi, lambda t: parts.append(t.clone()), dev)
     xs = torch.cat(parts)
     del parts
-    # warm-up pass of the whole pipeline on a short stream: NCCL connections (reduce, gather), library
-    # buffers and kernels are set up outside the timed region
-    wtotal = 400_000_000
-    multi.time_chunked_psd(PsdCascade(n, device=dev.index),
-                           lambda a, b, sink: sink((torch.rand(b - a, device=dev) - 0.5) * (12 ** 0.5)),
-                           wtotal, n, d, 1, min(n_local, 4), str(dev))
-    c.process(xs[:min(xs.numel(), (1 << 28) + (1 << 22))])   # one full-size batch: the handle's buffers reach their final size
+    # warm-up: one untimed pass of the whole pipeline on the same handle and stream (NCCL connections, the
+    # handle's stage / tail buffers at their final size, kernels loaded), then reset() -- which keeps buffers
+    multi.time_chunked_psd(c, lambda a, b, sink: sink(xs), total, n, d, 1, n_local, str(dev), None, avg)
     c.sync()
-    c.reset()                                                # keeps the buffers
+    c.reset()
+    if preset:
+        c.set_detrend(Detrend.MEAN)
     if d is not None:
         d.barrier()
     torch.cuda.synchronize()
