@@ -281,6 +281,45 @@ def finish_on_root(root, reduced_counts, tails, total, n, hbf, n_local, avg=None
     return root
 
 
+def exchange_layout(total, world, n, hbf, n_local, stride):
+    """Layout of the single reduction buffer of the time-chunked readout (float64 words):
+    [n_local accumulator rows of `stride`] [world tail slots of `slot`] [n_local counts] [world x (first, length)]"""
+    slot = (stream_state(total, n, n // 2, DRAIN[hbf]) + [(0, 0, 0)] * 16)[n_local][0] // world + 64
+    nacc = n_local * stride
+    meta = nacc + world * slot
+    return dict(slot=slot, nacc=nacc, meta=meta, size=meta + n_local + 2 * world, stride=stride)
+
+
+def pack_exchange(lay, rank, world, n_local, acc_rows, factors, counts, first, tail32, tlen, device):
+    """This rank's contribution: its rows (times the EWMA factors) and counts are summed by the reduction,
+    its tail slice and (first, length) sit in slots nobody else writes."""
+    import torch
+    buf = torch.zeros(lay["size"], dtype=torch.float64, device=device)
+    stride = lay["stride"]
+    buf[:lay["nacc"]] = acc_rows[:n_local].reshape(-1)
+    for i, f in enumerate(factors):  # EWMA: weight of everything that follows this rank's chunk
+        if f != 1.0:
+            buf[i * stride:(i + 1) * stride] *= f
+    base = lay["nacc"] + rank * lay["slot"]
+    buf[base:base + tlen] = tail32[:tlen]
+    book = [0.0] * (n_local + 2 * world)
+    book[:n_local] = [float(c) for c in counts]
+    book[n_local + 2 * rank] = float(first)
+    book[n_local + 2 * rank + 1] = float(tlen)
+    buf[lay["meta"]:] = torch.tensor(book, dtype=torch.float64).to(device, non_blocking=True)
+    return buf
+
+
+def unpack_exchange(lay, world, n_local, buf):
+    """Root side, after the sum reduction: (rows [n_local, stride] float32, counts, [(first, tail float32)])"""
+    book = [int(round(v)) for v in buf[lay["meta"]:].tolist()]  # the one device->host readback (synchronises)
+    rows = buf[:lay["nacc"]].reshape(n_local, lay["stride"]).float()
+    all32 = buf[lay["nacc"]:lay["meta"]].float()
+    slot = lay["slot"]
+    tails = [(book[n_local + 2 * r], all32[r * slot:r * slot + book[n_local + 2 * r + 1]]) for r in range(world)]
+    return rows, book[:n_local], tails
+
+
 def time_chunked_psd(cascade, feed, total, n, dist=None, hbf=1, n_local=3, device="cuda", timings=None, avg=None):
     """Distributed driver of the time-chunked mode: every rank calls this with a FRESH cascade and a
     callable feed(lo, hi, sink) that pushes stream samples [lo, hi) into sink(x) in order (any block
@@ -324,38 +363,22 @@ def time_chunked_psd(cascade, feed, total, n, dist=None, hbf=1, n_local=3, devic
         # rank's slice of the stage-n_local stream travel in one buffer; rows and counts are summed, the
         # slices land in disjoint slots (everybody else contributes zeros there).  Everything stays on
         # the device; the root reads back only the 2 * world + n_local bookkeeping numbers.
-        slot = (stream_state(total, n, n // 2, DRAIN[hbf]) + [(0, 0, 0)] * 16)[n_local][0] // world + 64
-        tail32 = torch.empty(slot, dtype=torch.float32, device=device)
+        acc, counts = cascade_partials_tensor(cascade)
+        lay = exchange_layout(total, world, n, hbf, n_local, acc.shape[1])
+        tail32 = torch.empty(lay["slot"], dtype=torch.float32, device=device)
         first, tlen = cascade.take_tail_device(plan["tail_lo"], tail_hi, tail32)
         lap("process+tail")
-        acc, counts = cascade_partials_tensor(cascade)
         counts = (counts + [0] * 16)[:n_local]
-        stride = acc.shape[1]
-        nacc = n_local * stride
-        meta = nacc + world * slot
-        buf = torch.zeros(meta + n_local + 2 * world, dtype=torch.float64, device=device)
-        buf[:nacc] = acc[:n_local].reshape(-1)
-        for i, f in enumerate(factors):  # EWMA: weight of everything that follows this rank's chunk
-            if f != 1.0:
-                buf[i * stride:(i + 1) * stride] *= f
-        buf[nacc + rank * slot:nacc + rank * slot + tlen] = tail32[:tlen]
-        book = [0.0] * (n_local + 2 * world)
-        book[:n_local] = [float(c) for c in counts]
-        book[n_local + 2 * rank] = float(first)
-        book[n_local + 2 * rank + 1] = float(tlen)
-        buf[meta:] = torch.tensor(book, dtype=torch.float64).to(device, non_blocking=True)
+        buf = pack_exchange(lay, rank, world, n_local, acc, factors, counts, first, tail32, tlen, device)
         dist.reduce(buf, dst=0, op=dist.ReduceOp.SUM)
         if rank != 0:
             torch.cuda.synchronize()
             lap("reduce")
             return None
-        book = [int(round(v)) for v in buf[meta:].tolist()]  # the one device->host readback (synchronises)
+        rows, counts, tails = unpack_exchange(lay, world, n_local, buf)
         lap("reduce")
-        acc[:n_local] = buf[:nacc].reshape(n_local, stride).float()
-        counts = book[:n_local]
-        all32 = buf[nacc:meta].float()
+        acc[:n_local] = rows
         torch.cuda.synchronize()  # torch's stream wrote library memory / made the tensors the library reads
-        tails = [(book[n_local + 2 * r], all32[r * slot:r * slot + book[n_local + 2 * r + 1]]) for r in range(world)]
     root = finish_on_root(cascade, counts, tails, total, n, hbf, n_local, avg)
     if world > 1:
         root.sync()  # the gathered slices are torch temporaries read asynchronously on the library's deep stream

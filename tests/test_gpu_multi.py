@@ -38,3 +38,25 @@ def test_stage0_partials_sum_to_full_spectrum(oracle):
     assert top.decimation == 1 and top.count == nseg
     want = full.spectrum() / full.gain()
     np.testing.assert_allclose(p[top.start:top.start + len(top.bins)], want, rtol=1e-4)
+
+
+@pytest.mark.parametrize("preset", [False, True])
+def test_time_chunked_over_nccl_two_ranks(preset):
+    """the real thing: two processes, two GPUs, NCCL reduction (tools/run_configs.py --config 5 --check);
+    skipped on a single-GPU box"""
+    import json
+    import os
+    import subprocess
+    import sys
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+           "--master-port", "29577", os.path.join(root, "tools", "run_configs.py"), "--config", "5", "--total", "6e8",
+           "--n-local", "4", "--check"] + (["--preset"] if preset else [])
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, r.stderr[-2000:]
+    out = json.loads([l for l in r.stdout.splitlines() if l.startswith("{")][-1])
+    assert out["world"] == 2 and out["counts_match_closed_form"] and out["breaks_equal"]
+    assert out["max_rel_diff_vs_sequential"] < 5e-5

@@ -65,6 +65,28 @@ def _worker(rank, world, port, out):
         full.process(x)
         assert counts == [full.count()] == [nseg]
         np.testing.assert_allclose(acc[0, :n // 2 + 1].numpy(), full.spectrum(), rtol=2e-5)
+        # ---- the single readout collective of the time-chunked mode: rows + counts summed, tail slices and
+        # their positions carried in disjoint slots (pack_exchange / unpack_exchange over a gloo reduce) ----
+        total, n_local, stride = 3_000_017, 3, 260
+        lay = multi.exchange_layout(total, world, n, 1, n_local, stride)
+        stream = uniform_noise(2 * lay["slot"] - 100, 5)          # the "stage-3 stream": two consecutive slices
+        cut = lay["slot"] - 37
+        first, piece = (0, stream[:cut]) if rank == 0 else (cut, stream[cut:])
+        rows = torch.from_numpy(uniform_noise(16 * stride, 20 + rank).reshape(16, stride) ** 2)
+        factors = [1.0, 0.5, 1.0] if rank == 0 else [1.0, 1.0, 1.0]
+        counts = [1000 + rank, 120 + rank, 2 ** 30 + 15 + rank]    # beyond f32 integer range on purpose
+        buf = multi.pack_exchange(lay, rank, world, n_local, rows, factors, counts, first,
+                                  torch.from_numpy(piece.copy()), piece.size, torch.device("cpu"))
+        dist.reduce(buf, dst=0, op=dist.ReduceOp.SUM)
+        if rank == 0:
+            got_rows, got_counts, tails = multi.unpack_exchange(lay, world, n_local, buf)
+            r0 = uniform_noise(16 * stride, 20).reshape(16, stride) ** 2
+            r1 = uniform_noise(16 * stride, 21).reshape(16, stride) ** 2
+            want = r0[:3].astype(np.float64) * np.array([1.0, 0.5, 1.0])[:, None] + r1[:3]
+            np.testing.assert_allclose(got_rows.numpy(), want, rtol=1e-6)
+            assert got_counts == [2001, 241, 2 ** 31 + 31]
+            assert [t[0] for t in tails] == [0, cut]
+            assert np.array_equal(np.concatenate([t[1].numpy() for t in tails]), stream)
         out.put((rank, "ok"))
     except Exception as e:  # noqa: BLE001
         out.put((rank, repr(e)))
