@@ -220,6 +220,7 @@ Cascade::~Cascade()
     if (stream_)
         cudaStreamSynchronize(stream_);
     if (deep_stream_) cudaStreamSynchronize(deep_stream_);
+    if (psd_stream_) cudaStreamSynchronize(psd_stream_);
     free_stages(false);
     cudaFree(d_win_);
     cudaFree(d_twM_);
@@ -239,6 +240,8 @@ Cascade::~Cascade()
     }
     if (ev_stage0_) cudaEventDestroy(ev_stage0_);
     if (ev_deep_) cudaEventDestroy(ev_deep_);
+    if (ev_psd_join_) cudaEventDestroy(ev_psd_join_);
+    if (psd_stream_) cudaStreamDestroy(psd_stream_);
     if (deep_stream_) cudaStreamDestroy(deep_stream_);
     if (copy_stream_) cudaStreamDestroy(copy_stream_);
     if (own_stream_ && stream_) cudaStreamDestroy(stream_);
@@ -322,6 +325,14 @@ int Cascade::init(const sspsd_config& cfg, uint32_t max_stages)
         SSPSD_CUDA(cudaStreamCreateWithPriority(&deep_stream_, cudaStreamNonBlocking, hi_prio));
         SSPSD_CUDA(cudaEventCreateWithFlags(&ev_stage0_, cudaEventDisableTiming));
         SSPSD_CUDA(cudaEventCreateWithFlags(&ev_deep_, cudaEventDisableTiming));
+        // A deep stage's PSD kernel and its decimator only share their input, so the PSD kernels get a
+        // stream of their own: the dependent chain a readout has to wait for is then decimator ->
+        // decimator -> ... instead of PSD -> decimator -> carry copy per stage.
+        const char* ps = getenv("SSPSD_PSD_STREAM");
+        if (!ps || atoi(ps) != 0) {
+            SSPSD_CUDA(cudaStreamCreateWithPriority(&psd_stream_, cudaStreamNonBlocking, hi_prio));
+            SSPSD_CUDA(cudaEventCreateWithFlags(&ev_psd_join_, cudaEventDisableTiming));
+        }
     }
     for (int i = 0; i < 2; ++i) {
         SSPSD_CUDA(cudaEventCreateWithFlags(&ev_copied_[i], cudaEventDisableTiming));
@@ -387,10 +398,15 @@ int Cascade::add_stage()
         st.fresh_cap = old.fresh_cap;
         st.ev_read[0] = old.ev_read[0];
         st.ev_read[1] = old.ev_read[1];
+        st.ev_in = old.ev_in;
+        st.ev_psd[0] = old.ev_psd[0];
+        st.ev_psd[1] = old.ev_psd[1];
     } else {
         SSPSD_CUDA(cudaMalloc(&st.carry[0], cap * sizeof(float)));
         SSPSD_CUDA(cudaMalloc(&st.carry[1], cap * sizeof(float)));
         for (int b = 0; b < 2; ++b) SSPSD_CUDA(cudaEventCreateWithFlags(&st.ev_read[b], cudaEventDisableTiming));
+        for (int b = 0; b < 2; ++b) SSPSD_CUDA(cudaEventCreateWithFlags(&st.ev_psd[b], cudaEventDisableTiming));
+        SSPSD_CUDA(cudaEventCreateWithFlags(&st.ev_in, cudaEventDisableTiming));
     }
     st.avg = single_stage_avg_set_ ? single_stage_avg_ : stage_avg(stages_.size());
     // zero history for g < 0: the decimator starts from HbfDec8::default() (psd.rs:141)
@@ -412,6 +428,7 @@ int Cascade::ensure_fresh(StageState& st, size_t need)
     // tail, written by the previous batch's carry_copy_kernel) has to survive the reallocation
     SSPSD_CUDA(cudaStreamSynchronize(stream_));
     if (deep_stream_) SSPSD_CUDA(cudaStreamSynchronize(deep_stream_));
+    if (psd_stream_) SSPSD_CUDA(cudaStreamSynchronize(psd_stream_));
     size_t cap = std::max(need + 64, st.fresh_cap * 2);
     for (int b = 0; b < 2; ++b) {
         float* nb = nullptr;
@@ -452,9 +469,9 @@ int Cascade::launch_psd(size_t i, const StreamSrc& src, uint64_t k0, uint64_t ns
         p.g_first = g_first;
         p.g_s = g_s;
         int grid = (int)((nseg + p.T - 1) / p.T);
-        prof_begin(i == 0 ? SSPSD_PROF_PSD_STAGE0 : SSPSD_PROF_PSD_DEEP, nseg * (uint64_t)hop_, stage_stream(i));
-        psd_stage_kernel_ring<<<grid, R16::NT, stage_ring_smem_bytes(p.T), stage_stream(i)>>>(p);
-        prof_end(stage_stream(i));
+        prof_begin(i == 0 ? SSPSD_PROF_PSD_STAGE0 : SSPSD_PROF_PSD_DEEP, nseg * (uint64_t)hop_, psd_stream(i));
+        psd_stage_kernel_ring<<<grid, R16::NT, stage_ring_smem_bytes(p.T), psd_stream(i)>>>(p);
+        prof_end(psd_stream(i));
         return cuda_ok(cudaGetLastError(), "psd_stage_kernel_ring launch") ? SSPSD_OK : SSPSD_ECUDA;
     }
     const bool tiled_r16 = log2n_ == 12 && use_r16();
@@ -480,9 +497,9 @@ int Cascade::launch_psd(size_t i, const StreamSrc& src, uint64_t k0, uint64_t ns
     long long ntiles = ((long long)nseg + p.T - 1) / p.T;
     p.tpc = tiled_r16 ? 1 : (int)std::max<long long>(1, (ntiles + 2ll * num_sms_ - 1) / (2ll * num_sms_));
     int grid = (int)((ntiles + p.tpc - 1) / p.tpc);
-    prof_begin(i == 0 ? SSPSD_PROF_PSD_STAGE0 : SSPSD_PROF_PSD_DEEP, nseg * (uint64_t)hop_, stage_stream(i));
-    int rc = launch_stage((int)log2n_, p, grid, stage_stream(i));
-    prof_end(stage_stream(i));
+    prof_begin(i == 0 ? SSPSD_PROF_PSD_STAGE0 : SSPSD_PROF_PSD_DEEP, nseg * (uint64_t)hop_, psd_stream(i));
+    int rc = launch_stage((int)log2n_, p, grid, psd_stream(i));
+    prof_end(psd_stream(i));
     return rc;
 }
 
@@ -517,11 +534,19 @@ int Cascade::run_stage(size_t i, const float* fresh, long long split, uint64_t n
 {
     StageState& st = stages_[i];
     cudaStream_t ss = stage_stream(i);
+    cudaStream_t ps = psd_stream(i);  // == ss unless the stage's PSD kernel runs beside the decimation chain
     const uint64_t L1 = st.L + n_new;
     const uint64_t craw0 = st.craw;
     const uint64_t craw1 = L1 < n_ ? 0 : 1 + (L1 - n_) / hop_;
     const StreamSrc src{st.carry[st.cur], fresh, st.carry_start, split};
     int rc;
+    bool psd_launched = false;
+    if (ps != ss && craw1 > craw0) {
+        // everything queued on ss so far (previous decimator, carry copy of the last batch) made this
+        // stage's input: the PSD stream may read it from here on
+        SSPSD_CUDA(cudaEventRecord(st.ev_in, ss));
+        SSPSD_CUDA(cudaStreamWaitEvent(ps, st.ev_in, 0));
+    }
 
     if (windowed_ && i < n_local_ && craw1 > craw0) {
         // time-chunk mode: accumulate only the fully valid segments this rank owns; their start position
@@ -543,14 +568,15 @@ int Cascade::run_stage(size_t i, const float* fresh, long long split, uint64_t n
                 EwmaPlan e = ewma_plan(cnt, st.avg, b - a);
                 if (e.total != 1.0f) {
                     int nb = (int)(n_ / 2 + 1);
-                    prof_begin(SSPSD_PROF_OTHER, 0, ss);
-                    scale_kernel<<<(nb + 255) / 256, 256, 0, ss>>>(d_acc_ + i * acc_stride_, nb, e.total);
-                    prof_end(ss);
+                    prof_begin(SSPSD_PROF_OTHER, 0, ps);
+                    scale_kernel<<<(nb + 255) / 256, 256, 0, ps>>>(d_acc_ + i * acc_stride_, nb, e.total);
+                    prof_end(ps);
                     SSPSD_CUDA(cudaGetLastError());
                 }
                 rc = launch_psd(i, src, a, b - a, e.jb, e.g_first, e.g_s);
             }
             if (rc) return rc;
+            psd_launched = true;
             st.count = (uint32_t)std::min<uint64_t>((uint64_t)st.count + (b - a), 0xffffffffull);
         }
     } else if (craw1 > craw0) {
@@ -558,14 +584,20 @@ int Cascade::run_stage(size_t i, const float* fresh, long long split, uint64_t n
         EwmaPlan e = ewma_plan(st.count, st.avg, S);
         if (e.total != 1.0f) {
             int nb = (int)(n_ / 2 + 1);
-            prof_begin(SSPSD_PROF_OTHER, 0, ss);
-            scale_kernel<<<(nb + 255) / 256, 256, 0, ss>>>(d_acc_ + i * acc_stride_, nb, e.total);
-            prof_end(ss);
+            prof_begin(SSPSD_PROF_OTHER, 0, ps);
+            scale_kernel<<<(nb + 255) / 256, 256, 0, ps>>>(d_acc_ + i * acc_stride_, nb, e.total);
+            prof_end(ps);
             SSPSD_CUDA(cudaGetLastError());
         }
         rc = launch_psd(i, src, craw0, S, e.jb, e.g_first, e.g_s);
         if (rc) return rc;
         st.count = e.count_after;
+        psd_launched = true;
+    }
+    if (ps != ss && psd_launched) {
+        // the PSD kernel reads carry[cur] and fresh[fb]: whoever overwrites them next waits for this
+        SSPSD_CUDA(cudaEventRecord(st.ev_psd[st.fb], ps));
+        psd_dirty_ = true;
     }
 
     const uint64_t D0 = decimated(st);
@@ -623,6 +655,9 @@ int Cascade::run_stage(size_t i, const float* fresh, long long split, uint64_t n
                 // the next stage may still be reading this buffer from two batches ago (other stream)
                 if (nx.ev_read_pending[b] && stage_stream(i) != stage_stream(i + 1)) {
                     SSPSD_CUDA(cudaStreamWaitEvent(ss, nx.ev_read[b], 0));
+                    // ... and so may its PSD kernel (on the deep stream itself this is implied: that stream
+                    // waits for ev_psd before every carry copy, which precedes this launch in stream order)
+                    if (psd_stream(i + 1) != stage_stream(i + 1)) SSPSD_CUDA(cudaStreamWaitEvent(ss, nx.ev_psd[b], 0));
                     nx.ev_read_pending[b] = false;
                 }
                 rc = launch_decim(i, src, m0, m1, nx.fresh[b], nsplit);
@@ -651,6 +686,9 @@ int Cascade::run_stage(size_t i, const float* fresh, long long split, uint64_t n
                 head_dst = s2.fresh[s2.fb ^ 1];
             }
         }
+        // the copy overwrites carry[cur ^ 1] and the head of fresh[fb ^ 1], which the previous batch's PSD
+        // kernel read (a wait on an event that was never recorded returns at once)
+        if (ps != ss) SSPSD_CUDA(cudaStreamWaitEvent(ss, s2.ev_psd[s2.fb ^ 1], 0));
         prof_begin(SSPSD_PROF_OTHER, 0, ss);
         carry_copy_kernel<<<std::max(1, std::min(64, (n + 255) / 256)), 256, 0, ss>>>(src, cs, n, s2.carry[s2.cur ^ 1],
                                                                                      head_dst, head_n);
@@ -680,6 +718,11 @@ int Cascade::run_stage(size_t i, const float* fresh, long long split, uint64_t n
 
 int Cascade::join_streams()
 {
+    if (psd_stream_ && psd_dirty_) {
+        SSPSD_CUDA(cudaEventRecord(ev_psd_join_, psd_stream_));
+        SSPSD_CUDA(cudaStreamWaitEvent(stream_, ev_psd_join_, 0));
+        psd_dirty_ = false;
+    }
     if (deep_stream_ && deep_dirty_) {
         SSPSD_CUDA(cudaEventRecord(ev_deep_, deep_stream_));
         SSPSD_CUDA(cudaStreamWaitEvent(stream_, ev_deep_, 0));
@@ -702,8 +745,11 @@ void Cascade::free_stages(bool keep_buffers)
             cudaFree(st.carry[1]);
             cudaFree(st.fresh[0]);
             cudaFree(st.fresh[1]);
-            for (int b = 0; b < 2; ++b)
+            for (int b = 0; b < 2; ++b) {
                 if (st.ev_read[b]) cudaEventDestroy(st.ev_read[b]);
+                if (st.ev_psd[b]) cudaEventDestroy(st.ev_psd[b]);
+            }
+            if (st.ev_in) cudaEventDestroy(st.ev_in);
         }
         v->clear();
     }
@@ -987,8 +1033,10 @@ int Cascade::reset()
     SSPSD_CUDA(cudaStreamSynchronize(stream_));
     SSPSD_CUDA(cudaStreamSynchronize(copy_stream_));
     if (deep_stream_) SSPSD_CUDA(cudaStreamSynchronize(deep_stream_));
+    if (psd_stream_) SSPSD_CUDA(cudaStreamSynchronize(psd_stream_));
     free_stages(true);
     deep_dirty_ = false;
+    psd_dirty_ = false;
     seek_pos_ = 0;
     windowed_ = false;
     tail_len_ = 0;
@@ -1041,6 +1089,7 @@ int Cascade::clone_from(Cascade& o)
                                cudaMemcpyDeviceToDevice, stream_));
     SSPSD_CUDA(cudaStreamSynchronize(stream_));
     if (deep_stream_) SSPSD_CUDA(cudaStreamSynchronize(deep_stream_));
+    if (psd_stream_) SSPSD_CUDA(cudaStreamSynchronize(psd_stream_));
     return SSPSD_OK;
 }
 

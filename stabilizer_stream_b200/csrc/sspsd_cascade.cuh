@@ -49,6 +49,9 @@ struct StageState {
     size_t fresh_cap = 0;
     cudaEvent_t ev_read[2] = {nullptr, nullptr};  // recorded when this stage has finished reading fresh[b]
     bool ev_read_pending[2] = {false, false};
+    // stages on the deep stream run their PSD kernel on a third stream beside the decimation chain:
+    cudaEvent_t ev_in = nullptr;                  // deep stream: this batch's input of the stage is complete
+    cudaEvent_t ev_psd[2] = {nullptr, nullptr};   // PSD stream: the PSD kernel has finished reading fresh[b] + carry
 };
 
 class Cascade {
@@ -99,6 +102,8 @@ private:
     int launch_decim(size_t i, const StreamSrc& src, uint64_t m0, uint64_t m1, float* out_fresh,
                      long long out_split);
     cudaStream_t stage_stream(size_t i) const { return (i < deep_from_ || !deep_stream_) ? stream_ : deep_stream_; }
+    // stream of stage i's PSD kernel (and its EWMA pre-scale): beside the decimation chain for the deep stages
+    cudaStream_t psd_stream(size_t i) const { return (i >= deep_from_ && psd_stream_) ? psd_stream_ : stage_stream(i); }
     int join_streams();  // make stream_ wait for everything queued on deep_stream_
     int ensure_fresh(StageState& st, size_t need);
     int ensure_in_buffers(size_t need);
@@ -148,8 +153,9 @@ private:
     bool own_stream_ = false;
     cudaStream_t copy_stream_ = nullptr;
     cudaStream_t deep_stream_ = nullptr;  // stages >= 1 run here, overlapping the next batch's stage 0
-    cudaEvent_t ev_stage0_ = nullptr, ev_deep_ = nullptr;
-    bool deep_dirty_ = false;
+    cudaStream_t psd_stream_ = nullptr;   // PSD kernels of stages >= deep_from_ (SSPSD_PSD_STREAM=0 disables)
+    cudaEvent_t ev_stage0_ = nullptr, ev_deep_ = nullptr, ev_psd_join_ = nullptr;
+    bool deep_dirty_ = false, psd_dirty_ = false;
     size_t deep_from_ = 1;  // first stage that runs on deep_stream_
     cudaEvent_t ev_copied_[2] = {nullptr, nullptr}, ev_free_[2] = {nullptr, nullptr};
     cudaEvent_t ev_stage_[2] = {nullptr, nullptr};
