@@ -62,6 +62,7 @@ pub struct DecodeInfo {
 enum CCascade {}
 enum CDecoder {}
 enum CSource {}
+enum CReceiver {}
 
 extern "C" {
     fn sspsd_last_error() -> *const c_char;
@@ -84,6 +85,11 @@ extern "C" {
                            out: *mut *mut CSource) -> i32;
     fn sspsd_source_destroy(s: *mut CSource);
     fn sspsd_cascade_process_source(h: *mut CCascade, s: *mut CSource, n: usize) -> i32;
+    fn sspsd_receiver_create(ip: *const c_char, port: u16, slot_bytes: u32, n_slots: u32, flags: i32,
+                             out: *mut *mut CReceiver) -> i32;
+    fn sspsd_receiver_destroy(r: *mut CReceiver);
+    fn sspsd_receiver_pump(r: *mut CReceiver, d: *mut CDecoder, cascades: *const *mut CCascade, n: u32, max_frames: u32,
+                           timeout_ms: i32, loss: *mut CLoss, info: *mut DecodeInfo) -> i32;
 }
 
 fn check(status: i32) {
@@ -234,5 +240,37 @@ impl SyntheticSource {
 impl Drop for SyntheticSource {
     fn drop(&mut self) {
         unsafe { sspsd_source_destroy(self.s) }
+    }
+}
+
+/// `Data::Udp` (src/source.rs:81-93, 159-165): datagrams are collected with recvmmsg into page-locked
+/// slots and decoded per batch instead of `socket.read` + `Frame::from_bytes` per packet.
+pub struct UdpReceiver {
+    r: *mut CReceiver,
+}
+unsafe impl Send for UdpReceiver {}
+
+impl UdpReceiver {
+    /// `SourceOpts::{ip, port}` (source.rs:17-23)
+    pub fn bind(ip: std::net::Ipv4Addr, port: u16) -> Self {
+        let ip = std::ffi::CString::new(ip.to_string()).unwrap();
+        let mut r = ptr::null_mut();
+        unsafe { check(sspsd_receiver_create(ip.as_ptr(), port, 2048, 1024, 0, &mut r)) };
+        Self { r }
+    }
+    /// One batch of datagrams -> decode -> loss -> one cascade per trace.  `Ok(info)` with
+    /// `frames_ok == 0` after a second without traffic (the reference's read timeout, source.rs:83).
+    pub fn pump<const N: usize>(&mut self, dec: &mut FrameDecoder, cascades: &mut [PsdCascade<N>], loss: &mut CLoss)
+                                -> Result<DecodeInfo, i32> {
+        let hs: Vec<*mut CCascade> = cascades.iter().map(|c| c.h).collect();
+        let mut info = DecodeInfo::default();
+        let st = unsafe { sspsd_receiver_pump(self.r, dec.d, hs.as_ptr(), hs.len() as u32, 1024, 1000, loss, &mut info) };
+        if st == 0 { Ok(info) } else { Err(st) }
+    }
+}
+
+impl Drop for UdpReceiver {
+    fn drop(&mut self) {
+        unsafe { sspsd_receiver_destroy(self.r) }
     }
 }
