@@ -134,29 +134,44 @@ struct Plan {
 // padded shared-memory position of complex element i (4 floats of padding per 32 elements)
 __device__ __forceinline__ int ws_pos(int i) { return i + ((i >> 5) << 2); }
 
+// ---------------------------------------------------------------------------------------------
+// Complex arithmetic on packed FP32 pairs.  sm_100 has FADD2 / FMUL2 / FFMA2: one instruction, one
+// issue slot, both halves of a 64-bit register pair, with per-operand swizzle (LO_HI), per-half
+// negation and 32-bit broadcast modifiers, so a complex value (re, im) adds in ONE instruction,
+// multiplies in TWO, and a multiplication by +-i is free (it folds into the consumer's operand
+// modifiers).  The PSD kernels are bound by instruction issue (profiles/r01_ncu_summary.md), and
+// three quarters of their instructions were scalar FADD/FMUL/FFMA on exactly such pairs.
+// The FP32 pipe does the same number of lane operations either way (tools/microbench/ffma2.cu).
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ float2 cadd(float2 a, float2 b) { return __fadd2_rn(a, b); }
+__device__ __forceinline__ float2 csub(float2 a, float2 b) { return __fadd2_rn(a, make_float2(-b.x, -b.y)); }
+// a - i b  and  a + i b
+__device__ __forceinline__ float2 cadd_mi(float2 a, float2 b) { return __fadd2_rn(a, make_float2(b.y, -b.x)); }
+__device__ __forceinline__ float2 cadd_pi(float2 a, float2 b) { return __fadd2_rn(a, make_float2(-b.y, b.x)); }
+
 __device__ __forceinline__ float2 cmul(float2 a, float2 b)
 {
-    return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
+    // (a.x b.x - a.y b.y, a.x b.y + a.y b.x) = b.x (a.x, a.y) + b.y (-a.y, a.x): the pair operand takes the
+    // swizzle + half negation (FFMA2 -Ra.LO_HI.NP), b's halves are 32-bit broadcasts (or immediates)
+    float2 t = __fmul2_rn(a, make_float2(b.x, b.x));
+    return __ffma2_rn(make_float2(-a.y, a.x), make_float2(b.y, b.y), t);
 }
 
 // in-place forward DFTs, v[k] = sum_t v[t] exp(-2 pi i t k / R)
 __device__ __forceinline__ void dft2(float2& a, float2& b)
 {
     float2 t = a;
-    a = make_float2(t.x + b.x, t.y + b.y);
-    b = make_float2(t.x - b.x, t.y - b.y);
+    a = cadd(t, b);
+    b = csub(t, b);
 }
 
 __device__ __forceinline__ void dft4(float2& c0, float2& c1, float2& c2, float2& c3)
 {
-    float2 e0 = make_float2(c0.x + c2.x, c0.y + c2.y);
-    float2 e1 = make_float2(c0.x - c2.x, c0.y - c2.y);
-    float2 f0 = make_float2(c1.x + c3.x, c1.y + c3.y);
-    float2 f1 = make_float2(c1.y - c3.y, -(c1.x - c3.x)); // -i (c1 - c3)
-    c0 = make_float2(e0.x + f0.x, e0.y + f0.y);
-    c2 = make_float2(e0.x - f0.x, e0.y - f0.y);
-    c1 = make_float2(e1.x + f1.x, e1.y + f1.y);
-    c3 = make_float2(e1.x - f1.x, e1.y - f1.y);
+    float2 e0 = cadd(c0, c2), e1 = csub(c0, c2), f0 = cadd(c1, c3), d = csub(c1, c3);
+    c0 = cadd(e0, f0);
+    c2 = csub(e0, f0);
+    c1 = cadd_mi(e1, d);  // e1 - i (c1 - c3)
+    c3 = cadd_pi(e1, d);
 }
 
 template <int R>
@@ -169,22 +184,53 @@ __device__ __forceinline__ void butterfly(float2 (&v)[R])
     } else {
         static_assert(R == 8, "radix");
         constexpr float h = 0.70710678118654752440f;
-        float2 a0 = make_float2(v[0].x + v[4].x, v[0].y + v[4].y);
-        float2 a1 = make_float2(v[1].x + v[5].x, v[1].y + v[5].y);
-        float2 a2 = make_float2(v[2].x + v[6].x, v[2].y + v[6].y);
-        float2 a3 = make_float2(v[3].x + v[7].x, v[3].y + v[7].y);
-        float2 b0 = make_float2(v[0].x - v[4].x, v[0].y - v[4].y);
-        float2 d1 = make_float2(v[1].x - v[5].x, v[1].y - v[5].y);
-        float2 d2 = make_float2(v[2].x - v[6].x, v[2].y - v[6].y);
-        float2 d3 = make_float2(v[3].x - v[7].x, v[3].y - v[7].y);
-        float2 b1 = make_float2(h * (d1.x + d1.y), h * (d1.y - d1.x));  // * (1 - i)/sqrt2
-        float2 b2 = make_float2(d2.y, -d2.x);                            // * -i
-        float2 b3 = make_float2(h * (d3.y - d3.x), -h * (d3.x + d3.y)); // * (-1 - i)/sqrt2
+        float2 a0 = cadd(v[0], v[4]), a1 = cadd(v[1], v[5]), a2 = cadd(v[2], v[6]), a3 = cadd(v[3], v[7]);
+        float2 b0 = csub(v[0], v[4]), d1 = csub(v[1], v[5]), d2 = csub(v[2], v[6]), d3 = csub(v[3], v[7]);
+        float2 b1 = cmul(d1, make_float2(h, -h));    // * (1 - i)/sqrt2
+        float2 b3 = cmul(d3, make_float2(-h, -h));   // * (-1 - i)/sqrt2
         dft4(a0, a1, a2, a3);
-        dft4(b0, b1, b2, b3);
+        // dft4 of (b0, b1, -i d2, b3) with the -i folded into the operand modifiers
+        float2 e0 = cadd_mi(b0, d2), e1 = cadd_pi(b0, d2), f0 = cadd(b1, b3), d = csub(b1, b3);
         v[0] = a0; v[2] = a1; v[4] = a2; v[6] = a3;
-        v[1] = b0; v[3] = b1; v[5] = b2; v[7] = b3;
+        v[1] = cadd(e0, f0);
+        v[5] = csub(e0, f0);
+        v[3] = cadd_mi(e1, d);
+        v[7] = cadd_pi(e1, d);
     }
+}
+
+// Radix-8 forward DFT of 8 contiguous points that arrive as separate re / im planes (two LDS.128 per
+// plane).  The planes are consumed as packed pairs of NEIGHBOURING points ((re0,re1), (re2,re3), ...),
+// which needs no register shuffling: the distance-4 stage and the even half's distance-2 stage are
+// element-wise packed operations; everything that mixes the halves of a pair (the distance-1 stage, the
+// odd half with its W8 twiddles) is scalar and reads the halves in place.  The 1/sqrt2 of W8 and W8^3
+// is applied by the FFMAs of the last stage.
+__device__ __forceinline__ void dft8_planes(float4 r0, float4 r1, float4 i0, float4 i1, float2 (&z)[8])
+{
+    constexpr float h = 0.70710678118654752440f;
+    const float2 zr01 = make_float2(r0.x, r0.y), zr23 = make_float2(r0.z, r0.w), zr45 = make_float2(r1.x, r1.y),
+                 zr67 = make_float2(r1.z, r1.w);
+    const float2 zi01 = make_float2(i0.x, i0.y), zi23 = make_float2(i0.z, i0.w), zi45 = make_float2(i1.x, i1.y),
+                 zi67 = make_float2(i1.z, i1.w);
+    // distance 4: a_t = z_t + z_{t+4}, d_t = z_t - z_{t+4}
+    const float2 ar01 = cadd(zr01, zr45), ar23 = cadd(zr23, zr67), ai01 = cadd(zi01, zi45), ai23 = cadd(zi23, zi67);
+    const float2 dr01 = csub(zr01, zr45), dr23 = csub(zr23, zr67), di01 = csub(zi01, zi45), di23 = csub(zi23, zi67);
+    // even outputs: DFT4 of a.  distance 2 packed: c_t = a_t + a_{t+2}, e_t = a_t - a_{t+2}; distance 1 scalar
+    const float2 cr = cadd(ar01, ar23), ci = cadd(ai01, ai23), er = csub(ar01, ar23), ei = csub(ai01, ai23);
+    z[0] = make_float2(cr.x + cr.y, ci.x + ci.y);
+    z[4] = make_float2(cr.x - cr.y, ci.x - ci.y);
+    z[2] = make_float2(er.x + ei.y, ei.x - er.y);  // e0 - i e1
+    z[6] = make_float2(er.x - ei.y, ei.x + er.y);
+    // odd outputs: DFT4 of (d0, d1 W8, -i d2, d3 W8^3) with W8 = h (1 - i), W8^3 = h (-1 - i)
+    const float f0r = dr01.x + di23.x, f0i = di01.x - dr23.x;   // d0 + (-i d2)
+    const float g0r = dr01.x - di23.x, g0i = di01.x + dr23.x;   // d0 - (-i d2)
+    const float p = dr01.y + di01.y, q = di01.y - dr01.y;       // d1 (1 - i)
+    const float r = di23.y - dr23.y, s = di23.y + dr23.y;       // d3 (-1 - i) = (r, -s)
+    const float f1r = p + r, f1i = q - s, g1r = p - r, g1i = q + s;
+    z[1] = make_float2(fmaf(h, f1r, f0r), fmaf(h, f1i, f0i));
+    z[5] = make_float2(fmaf(-h, f1r, f0r), fmaf(-h, f1i, f0i));
+    z[3] = make_float2(fmaf(h, g1i, g0r), fmaf(-h, g1r, g0i));  // g0 - i h g1
+    z[7] = make_float2(fmaf(-h, g1i, g0r), fmaf(h, g1r, g0i));
 }
 
 }  // namespace sspsd

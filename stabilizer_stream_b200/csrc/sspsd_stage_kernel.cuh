@@ -49,13 +49,13 @@ __device__ __forceinline__ void group_sync(int group)
 //   X[k] = (A2 + W B2)/2,  X[M-k] = conj(A2 - W B2)/2,  A2 = Zk + conj(Zm),  B2 = -i (Zk - conj(Zm))
 __device__ __forceinline__ void split_power(float2 zk, float2 zm, float2 w, float& pk, float& pm)
 {
-    float2 a2 = make_float2(zk.x + zm.x, zk.y - zm.y);
-    float2 b2 = make_float2(zk.y + zm.y, zm.x - zk.x);
-    float2 wb = cmul(w, b2);
-    float sr = a2.x + wb.x, si = a2.y + wb.y;
-    float dr = a2.x - wb.x, di = a2.y - wb.y;
-    pk = sr * sr + si * si;
-    pm = dr * dr + di * di;
+    float2 a2 = __fadd2_rn(zk, make_float2(zm.x, -zm.y));   // Zk + conj(Zm)
+    float2 d = __fadd2_rn(zk, make_float2(-zm.x, zm.y));    // Zk - conj(Zm)
+    // W * (-i d) = w.x (d.y, -d.x) + w.y (d.x, d.y)
+    float2 wb = __ffma2_rn(d, make_float2(w.y, w.y), __fmul2_rn(make_float2(d.y, -d.x), make_float2(w.x, w.x)));
+    float2 s = cadd(a2, wb), t = csub(a2, wb);
+    pk = fmaf(s.y, s.y, s.x * s.x);
+    pm = fmaf(t.y, t.y, t.x * t.x);
 }
 
 template <int LOG2N, int PASS>

@@ -29,10 +29,7 @@ struct R16 {
 
 __device__ __forceinline__ int r16_pos(int i) { return i + ((i >> 5) << 2) + ((i >> 7) << 3); }
 
-__device__ __forceinline__ float2 cmulc(float2 a, float cr, float ci)
-{
-    return make_float2(a.x * cr - a.y * ci, a.x * ci + a.y * cr);
-}
+__device__ __forceinline__ float2 cmulc(float2 a, float cr, float ci) { return cmul(a, make_float2(cr, ci)); }
 
 // in-place 16-point forward DFT: v[k] = sum_n v[n] exp(-2 pi i n k / 16)
 __device__ __forceinline__ void dft16(float2 (&v)[16])
@@ -42,19 +39,27 @@ __device__ __forceinline__ void dft16(float2 (&v)[16])
     // inner DFT4 over m for each a: inputs v[a + 4m] -> Y_a[b] stored at v[a + 4b]
 #pragma unroll
     for (int a = 0; a < 4; ++a) dft4(v[a], v[a + 4], v[a + 8], v[a + 12]);
-    // twiddle Y_a[b] *= W16^(a b)
-    v[1 + 4] = cmulc(v[1 + 4], c1, -s1);                                   // W^1
-    v[1 + 8] = make_float2(h * (v[9].x + v[9].y), h * (v[9].y - v[9].x));  // W^2
-    v[1 + 12] = cmulc(v[1 + 12], s1, -c1);                                 // W^3
-    v[2 + 4] = make_float2(h * (v[6].x + v[6].y), h * (v[6].y - v[6].x));  // W^2
-    v[2 + 8] = make_float2(v[10].y, -v[10].x);                             // W^4 = -i
-    v[2 + 12] = make_float2(h * (v[14].y - v[14].x), -h * (v[14].x + v[14].y));  // W^6
-    v[3 + 4] = cmulc(v[3 + 4], s1, -c1);                                   // W^3
-    v[3 + 8] = make_float2(h * (v[11].y - v[11].x), -h * (v[11].x + v[11].y));  // W^6
-    v[3 + 12] = cmulc(v[3 + 12], -c1, s1);                                 // W^9
+    // twiddle Y_a[b] *= W16^(a b)   (W^4 = -i is folded into the outer DFT4 of b = 2 below)
+    v[1 + 4] = cmulc(v[1 + 4], c1, -s1);    // W^1
+    v[1 + 8] = cmulc(v[1 + 8], h, -h);      // W^2
+    v[1 + 12] = cmulc(v[1 + 12], s1, -c1);  // W^3
+    v[2 + 4] = cmulc(v[2 + 4], h, -h);      // W^2
+    v[2 + 12] = cmulc(v[2 + 12], -h, -h);   // W^6
+    v[3 + 4] = cmulc(v[3 + 4], s1, -c1);    // W^3
+    v[3 + 8] = cmulc(v[3 + 8], -h, -h);     // W^6
+    v[3 + 12] = cmulc(v[3 + 12], -c1, s1);  // W^9
     // outer DFT4 over a for each b: inputs v[a + 4b] -> X[b + 4c] stored at v[c + 4b]
-#pragma unroll
-    for (int b = 0; b < 4; ++b) dft4(v[4 * b], v[4 * b + 1], v[4 * b + 2], v[4 * b + 3]);
+    dft4(v[0], v[1], v[2], v[3]);
+    dft4(v[4], v[5], v[6], v[7]);
+    {
+        // b = 2: inputs (v8, v9, -i v10, v11)
+        float2 e0 = cadd_mi(v[8], v[10]), e1 = cadd_pi(v[8], v[10]), f0 = cadd(v[9], v[11]), d = csub(v[9], v[11]);
+        v[8] = cadd(e0, f0);
+        v[10] = csub(e0, f0);
+        v[9] = cadd_mi(e1, d);
+        v[11] = cadd_pi(e1, d);
+    }
+    dft4(v[12], v[13], v[14], v[15]);
     // v[c + 4b] holds X[b + 4c]: transpose the 4x4 index to natural order
 #pragma unroll
     for (int b = 0; b < 4; ++b)
@@ -232,14 +237,9 @@ __global__ void __launch_bounds__(R16::NT, 2) psd_stage_kernel_r16(const StagePa
         float4 bi0 = *reinterpret_cast<const float4*>(wim + posB), bi1 = *reinterpret_cast<const float4*>(wim + posB + 4);
         group_sync<TPS, NT>(group);  // workspace may be overwritten by the next segment from here on
 
-        float2 za[8] = {make_float2(ar0.x, ai0.x), make_float2(ar0.y, ai0.y), make_float2(ar0.z, ai0.z),
-                        make_float2(ar0.w, ai0.w), make_float2(ar1.x, ai1.x), make_float2(ar1.y, ai1.y),
-                        make_float2(ar1.z, ai1.z), make_float2(ar1.w, ai1.w)};
-        float2 zb[8] = {make_float2(br0.x, bi0.x), make_float2(br0.y, bi0.y), make_float2(br0.z, bi0.z),
-                        make_float2(br0.w, bi0.w), make_float2(br1.x, bi1.x), make_float2(br1.y, bi1.y),
-                        make_float2(br1.z, bi1.z), make_float2(br1.w, bi1.w)};
-        butterfly<8>(za);
-        butterfly<8>(zb);
+        float2 za[8], zb[8];
+        dft8_planes(ar0, ar1, ai0, ai1, za);
+        dft8_planes(br0, br1, bi0, bi1, zb);
 
         constexpr float h = 0.70710678118654752440f;
         constexpr float c1 = 0.92387953251128675613f, s1 = 0.38268343236508977173f;

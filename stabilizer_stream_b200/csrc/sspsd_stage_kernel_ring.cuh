@@ -31,7 +31,8 @@ __global__ void __launch_bounds__(R16::NT, 2) psd_stage_kernel_ring(const StageP
     constexpr int RING = RingCfg::RING;
     extern __shared__ __align__(16) float smem[];
     float* ring = smem;                      // RING * HOP
-    float* wsb = ring + RING * HOP;          // G * 2 * WS
+    float2* wtab = reinterpret_cast<float2*>(ring + RING * HOP);  // the window as N/2 pairs (16 KiB)
+    float* wsb = ring + RING * HOP + N;      // G * 2 * WS
     float* wgt = wsb + G * 2 * WS;           // p.T entries (segments per CTA)
     float* red = wgt + ((p.T + 3) & ~3);     // G * 4
     uint64_t* bars = reinterpret_cast<uint64_t*>(red + 8);  // RING mbarriers (8-byte aligned: all counts above are even)
@@ -66,13 +67,9 @@ __global__ void __launch_bounds__(R16::NT, 2) psd_stage_kernel_ring(const StageP
     }
 
     // ---- segment-invariant per-thread constants (as in the tiled radix-16 kernel) ----
-    float wv[32];
-#pragma unroll
-    for (int t = 0; t < 16; ++t) {
-        float2 w2 = __ldg(reinterpret_cast<const float2*>(p.win) + (j + t * TPS));
-        wv[2 * t] = w2.x;
-        wv[2 * t + 1] = w2.y;
-    }
+    // the window lives in shared memory (one LDS.64 per point and segment): the packed arithmetic needs
+    // aligned register pairs, and 32 registers of window values no longer fit beside it
+    for (int i = tid; i < N / 2; i += NT) wtab[i] = __ldg(reinterpret_cast<const float2*>(p.win) + i);
     const float2 a1 = __ldg(&p.twM[j]), a2 = __ldg(&p.twM[2 * j]), a4 = __ldg(&p.twM[4 * j]), a8 = __ldg(&p.twM[8 * j]);
     const int o = j & 7;
     const float2 b1 = __ldg(&p.twM[16 * o]), b2 = __ldg(&p.twM[32 * o]), b4 = __ldg(&p.twM[64 * o]),
@@ -120,7 +117,7 @@ __global__ void __launch_bounds__(R16::NT, 2) psd_stage_kernel_ring(const StageP
         if (p.detrend == 1) {
             float off = sB[0];  // x[N/2]
 #pragma unroll
-            for (int t = 0; t < 16; ++t) { v[t].x -= off; v[t].y -= off; }
+            for (int t = 0; t < 16; ++t) v[t] = __fadd2_rn(v[t], make_float2(-off, -off));
         } else if (p.detrend == 2) {
             float x0 = sA[0];
             float slope = (sB[HOP - 1] - x0) / (float)(N - 1);
@@ -144,10 +141,10 @@ __global__ void __launch_bounds__(R16::NT, 2) psd_stage_kernel_ring(const StageP
             for (int w = 0; w < WPG; ++w) sum += red[group * WPG + w];
             float off = sum * (1.0f / (float)N);
 #pragma unroll
-            for (int t = 0; t < 16; ++t) { v[t].x -= off; v[t].y -= off; }
+            for (int t = 0; t < 16; ++t) v[t] = __fadd2_rn(v[t], make_float2(-off, -off));
         }
 #pragma unroll
-        for (int t = 0; t < 16; ++t) { v[t].x *= wv[2 * t]; v[t].y *= wv[2 * t + 1]; }
+        for (int t = 0; t < 16; ++t) v[t] = __fmul2_rn(v[t], wtab[j + t * TPS]);
 
         dft16(v);
         twiddle16(v, a1, a2, a4, a8);
@@ -191,14 +188,9 @@ __global__ void __launch_bounds__(R16::NT, 2) psd_stage_kernel_ring(const StageP
             }
         }
 
-        float2 za[8] = {make_float2(ar0.x, ai0.x), make_float2(ar0.y, ai0.y), make_float2(ar0.z, ai0.z),
-                        make_float2(ar0.w, ai0.w), make_float2(ar1.x, ai1.x), make_float2(ar1.y, ai1.y),
-                        make_float2(ar1.z, ai1.z), make_float2(ar1.w, ai1.w)};
-        float2 zb[8] = {make_float2(br0.x, bi0.x), make_float2(br0.y, bi0.y), make_float2(br0.z, bi0.z),
-                        make_float2(br0.w, bi0.w), make_float2(br1.x, bi1.x), make_float2(br1.y, bi1.y),
-                        make_float2(br1.z, bi1.z), make_float2(br1.w, bi1.w)};
-        butterfly<8>(za);
-        butterfly<8>(zb);
+        float2 za[8], zb[8];
+        dft8_planes(ar0, ar1, ai0, ai1, za);
+        dft8_planes(br0, br1, bi0, bi1, zb);
 
         constexpr float h = 0.70710678118654752440f;
         constexpr float c1 = 0.92387953251128675613f, s1 = 0.38268343236508977173f;
@@ -259,7 +251,7 @@ __global__ void __launch_bounds__(R16::NT, 2) psd_stage_kernel_ring(const StageP
 
 inline size_t stage_ring_smem_bytes(int segs_per_cta)
 {
-    size_t fl = (size_t)RingCfg::RING * (R16::N / 2) + (size_t)R16::G * 2 * R16::WS + ((segs_per_cta + 3) & ~3) + 8;
+    size_t fl = (size_t)RingCfg::RING * (R16::N / 2) + R16::N + (size_t)R16::G * 2 * R16::WS + ((segs_per_cta + 3) & ~3) + 8;
     return fl * sizeof(float) + RingCfg::RING * sizeof(uint64_t) + 16;
 }
 
