@@ -233,4 +233,16 @@ __device__ __forceinline__ void dft8_planes(float4 r0, float4 r1, float4 i0, flo
     z[7] = make_float2(fmaf(-h, g1i, g0r), fmaf(h, g1r, g0i));
 }
 
+// Radix-4 forward DFT of 4 contiguous points given as one LDS.128 per plane (same idea as dft8_planes)
+__device__ __forceinline__ void dft4_planes(float4 r, float4 i, float2 (&z)[4])
+{
+    const float2 zr01 = make_float2(r.x, r.y), zr23 = make_float2(r.z, r.w);
+    const float2 zi01 = make_float2(i.x, i.y), zi23 = make_float2(i.z, i.w);
+    const float2 cr = cadd(zr01, zr23), ci = cadd(zi01, zi23), er = csub(zr01, zr23), ei = csub(zi01, zi23);
+    z[0] = make_float2(cr.x + cr.y, ci.x + ci.y);
+    z[2] = make_float2(cr.x - cr.y, ci.x - ci.y);
+    z[1] = make_float2(er.x + ei.y, ei.x - er.y);  // e0 - i e1
+    z[3] = make_float2(er.x - ei.y, ei.x + er.y);
+}
+
 }  // namespace sspsd

@@ -179,13 +179,9 @@ psd_stage_kernel(const StageParams p)
     }
 
     // ---- segment-invariant per-thread constants ----
-    float wv[16];
+    float2 wv[8];
 #pragma unroll
-    for (int t = 0; t < 8; ++t) {
-        float2 w2 = __ldg(reinterpret_cast<const float2*>(p.win) + (j + t * TPS));
-        wv[2 * t] = w2.x;
-        wv[2 * t + 1] = w2.y;
-    }
+    for (int t = 0; t < 8; ++t) wv[t] = __ldg(reinterpret_cast<const float2*>(p.win) + (j + t * TPS));
     float2 tw[PL::P - 1][7];
     load_pass_twiddles<LOG2N, 0>(tw, p.twM, j);
 
@@ -254,7 +250,7 @@ psd_stage_kernel(const StageParams p)
         if (p.detrend == 1) { // Midpoint, psd.rs:87-93
             float off = seg[N / 2];
 #pragma unroll
-            for (int t = 0; t < 8; ++t) { v[t].x -= off; v[t].y -= off; }
+            for (int t = 0; t < 8; ++t) v[t] = __fadd2_rn(v[t], make_float2(-off, -off));
         } else if (p.detrend == 2) { // Span, psd.rs:94-102
             float x0 = seg[0];
             float slope = (seg[N - 1] - x0) / (float)(N - 1);
@@ -283,10 +279,10 @@ psd_stage_kernel(const StageParams p)
             }
             float off = sum * (1.0f / (float)N);
 #pragma unroll
-            for (int t = 0; t < 8; ++t) { v[t].x -= off; v[t].y -= off; }
+            for (int t = 0; t < 8; ++t) v[t] = __fadd2_rn(v[t], make_float2(-off, -off));
         }
 #pragma unroll
-        for (int t = 0; t < 8; ++t) { v[t].x *= wv[2 * t]; v[t].y *= wv[2 * t + 1]; }
+        for (int t = 0; t < 8; ++t) v[t] = __fmul2_rn(v[t], wv[t]);
 
         butterfly<8>(v);
         {
@@ -312,10 +308,9 @@ psd_stage_kernel(const StageParams p)
         // all reads of this segment's workspace are done once every thread passes this barrier
         group_sync<TPS, NT>(group);
 
-        float2 za[4] = {make_float2(ar.x, ai.x), make_float2(ar.y, ai.y), make_float2(ar.z, ai.z), make_float2(ar.w, ai.w)};
-        float2 zb[4] = {make_float2(br.x, bi.x), make_float2(br.y, bi.y), make_float2(br.z, bi.z), make_float2(br.w, bi.w)};
-        butterfly<4>(za);
-        butterfly<4>(zb);
+        float2 za[4], zb[4];
+        dft4_planes(ar, ai, za);
+        dft4_planes(br, bi, zb);
         float pk, pm;
         if (j != 0) {
 #pragma unroll
