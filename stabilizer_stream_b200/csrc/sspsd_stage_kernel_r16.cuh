@@ -123,13 +123,9 @@ __global__ void __launch_bounds__(R16::NT, 2) psd_stage_kernel_r16(const StagePa
     }
 
     // ---- segment-invariant per-thread constants ----
-    float wv[32];
-#pragma unroll
-    for (int t = 0; t < 16; ++t) {
-        float2 w2 = __ldg(reinterpret_cast<const float2*>(p.win) + (j + t * TPS));
-        wv[2 * t] = w2.x;
-        wv[2 * t + 1] = w2.y;
-    }
+    // the window is re-read through L1 for every segment (16 LDG.64): with the arithmetic on aligned
+    // register pairs, 32 registers of window values no longer fit without spilling
+    const float2* __restrict__ win2 = reinterpret_cast<const float2*>(p.win) + j;
     // pass-0 twiddles W_M^(j t): bases t = 1, 2, 4, 8
     const float2 a1 = __ldg(&p.twM[j]), a2 = __ldg(&p.twM[2 * j]), a4 = __ldg(&p.twM[4 * j]), a8 = __ldg(&p.twM[8 * j]);
     // pass-1 twiddles W_128^(o t) = W_M^(16 o t), o = j % 8
@@ -174,7 +170,7 @@ __global__ void __launch_bounds__(R16::NT, 2) psd_stage_kernel_r16(const StagePa
         if (p.detrend == 1) {
             float off = seg[N / 2];
 #pragma unroll
-            for (int t = 0; t < 16; ++t) { v[t].x -= off; v[t].y -= off; }
+            for (int t = 0; t < 16; ++t) v[t] = __fadd2_rn(v[t], make_float2(-off, -off));
         } else if (p.detrend == 2) {
             float x0 = seg[0];
             float slope = (seg[N - 1] - x0) / (float)(N - 1);
@@ -198,10 +194,10 @@ __global__ void __launch_bounds__(R16::NT, 2) psd_stage_kernel_r16(const StagePa
             for (int w = 0; w < WPG; ++w) sum += red[group * WPG + w];
             float off = sum * (1.0f / (float)N);
 #pragma unroll
-            for (int t = 0; t < 16; ++t) { v[t].x -= off; v[t].y -= off; }
+            for (int t = 0; t < 16; ++t) v[t] = __fadd2_rn(v[t], make_float2(-off, -off));
         }
 #pragma unroll
-        for (int t = 0; t < 16; ++t) { v[t].x *= wv[2 * t]; v[t].y *= wv[2 * t + 1]; }
+        for (int t = 0; t < 16; ++t) v[t] = __fmul2_rn(v[t], __ldg(win2 + t * TPS));
 
         dft16(v);
         twiddle16(v, a1, a2, a4, a8);
