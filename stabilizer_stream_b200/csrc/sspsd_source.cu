@@ -91,7 +91,9 @@ public:
     {
         if (n > buf_cap_) {
             SSPSD_CUDA(cudaSetDevice(device_));
+            // the old buffer may still be read by the cascade the last call fed (its stream, not ours)
             SSPSD_CUDA(cudaStreamSynchronize(stream_));
+            if (last_stream_) SSPSD_CUDA(cudaStreamSynchronize(last_stream_));
             SSPSD_CUDA(cudaFree(d_buf_));
             d_buf_ = nullptr;
             buf_cap_ = 0;
