@@ -86,14 +86,11 @@ def config3(dev):
         c.set_detrend(Detrend.MIDPOINT)
     dec = FrameDecoder()
     loss = Loss()
-    dec.process_frames(cas, fr, flen, Loss())   # warm-up at full size: decoder and cascade buffers get allocated
+    dec.process_frames(cas, fr, flen, Loss())   # warm-up at full size: decoder and cascade buffers reach their final size
     for c in cas:
         c.sync()
-    cas = [PsdCascade(n) for _ in range(4)]
-    for c in cas:
+        c.reset()                                # keeps the buffers (the GUI's Cmd::Reset)
         c.set_detrend(Detrend.MIDPOINT)
-        c.process(torch.zeros(8 * n, device=dev))   # allocate stage buffers, then start over
-        c.reset()
     torch.cuda.synchronize()
     t0 = time.perf_counter()
     info = dec.process_frames(cas, fr, flen, loss)
