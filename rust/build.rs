@@ -7,7 +7,7 @@ fn main() {
     let root = PathBuf::from(env::var("SSPSD_ROOT").unwrap_or_else(|_| "../stabilizer_stream_b200".into()));
     let out = PathBuf::from(env::var("OUT_DIR").unwrap());
     let lib = out.join("libsspsd.a");
-    let objs: Vec<PathBuf> = ["sspsd_cascade", "sspsd_api"]
+    let objs: Vec<PathBuf> = ["sspsd_cascade", "sspsd_api", "sspsd_source", "sspsd_receiver"]
         .iter()
         .map(|name| {
             let obj = out.join(format!("{name}.o"));
