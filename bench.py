@@ -33,6 +33,10 @@ BYTES_PER_SAMPLE = 4.0  # algorithmic: every raw f32 sample must cross HBM once 
 # measured DRAM traffic of the stage-0 PSD kernel: dram__bytes_read.sum + dram__bytes_write.sum = 270.94 MB +
 # 3.97 MB for a 2^26-sample launch (ncu --set full, profiles/r01_ncu_stage0_ring_metrics.csv)
 TRAFFIC_BYTES_PER_SAMPLE = (270.938624e6 + 3.97184e6) / (1 << 26)
+# FP32 lane operations the stage-0 PSD kernel executes per input sample (ncu instruction mix of the final kernel,
+# profiles/r01_ncu_ring_packed_instruction_mix.csv: 2 x 43.41 M packed + 15.44 M scalar FP warp instructions for
+# 2^26 samples): the roof that actually bounds it -- explanatory, next to the contract's HBM roofline
+FP32_LANE_OPS_PER_SAMPLE = (2 * 43.41e6 + 15.44e6) * 32 / (1 << 26)
 WORKLOAD = "PsdCascade N=4096 Hann 50% overlap, div-8 half-band per stage, 200e6-sample f32 stream per channel"
 
 
@@ -266,6 +270,10 @@ def run_ours(args):
             "peak_kind": peak_kind, "unit": "GB/s", "frac": achieved / peak,
             "traffic": TRAFFIC_BYTES_PER_SAMPLE * k_units / max(k_launches, 1),
             "traffic_source": "ncu --set full, profiles/r01_ncu_stage0_ring_metrics.csv, scaled per sample",
+            "fp32_pipe": {"lane_ops_per_sample": FP32_LANE_OPS_PER_SAMPLE,
+                          "achieved_Tops": FP32_LANE_OPS_PER_SAMPLE * k_units / (k_ms * 1e-3) / 1e12 if k_ms > 0 else 0.0,
+                          "peak_Tops": 148 * 128 * (clocks.get("sm_max_mhz") or 1965.0) * 1e6 / 1e12,
+                          "note": "explanatory: the kernel is FP32 / latency bound, not HBM bound"},
             "launches": int(k_launches), "avg_launch_ms": (k_ms / k_launches) if k_launches else None,
             "algorithmic_bytes_per_launch": BYTES_PER_SAMPLE * k_units / max(k_launches, 1),
             "share_of_step": k_ms / ms,
