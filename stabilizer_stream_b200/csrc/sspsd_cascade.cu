@@ -153,7 +153,18 @@ int upload_taps_once(int device)
     if (device < 64 && done[device])
         return SSPSD_OK;
     static_assert(sizeof(sspsd_hbf_taps) == sizeof(float) * SSPSD_HBF_NPRESET * 3 * SSPSD_HBF_MAXTAPS, "tap table");
-    SSPSD_CUDA(cudaMemcpyToSymbol(c_hbf_taps, sspsd_hbf_taps, sizeof(sspsd_hbf_taps)));
+    {
+        // rows padded to an even length (8-byte aligned pairs) + a copy shifted by one tap
+        static float t0[SSPSD_HBF_NPRESET][3][SSPSD_HBF_MAXTAPS + 1], t1[SSPSD_HBF_NPRESET][3][SSPSD_HBF_MAXTAPS + 1];
+        for (int p = 0; p < SSPSD_HBF_NPRESET; ++p)
+            for (int s = 0; s < 3; ++s)
+                for (int i = 0; i <= SSPSD_HBF_MAXTAPS; ++i) {
+                    t0[p][s][i] = i < SSPSD_HBF_MAXTAPS ? sspsd_hbf_taps[p][s][i] : 0.f;
+                    t1[p][s][i] = i + 1 < SSPSD_HBF_MAXTAPS ? sspsd_hbf_taps[p][s][i + 1] : 0.f;
+                }
+        SSPSD_CUDA(cudaMemcpyToSymbol(c_hbf_taps, t0, sizeof(t0)));
+        SSPSD_CUDA(cudaMemcpyToSymbol(c_hbf_taps_sh, t1, sizeof(t1)));
+    }
     SSPSD_CUDA(cudaFuncSetAttribute(decim8_kernel<5, 10, 23, SSPSD_HBF_140>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                     (int)(DecGeom<5, 10, 23>::SMEM_FLOATS * sizeof(float))));
     SSPSD_CUDA(cudaFuncSetAttribute(decim8_kernel<3, 6, 15, SSPSD_HBF_98>, cudaFuncAttributeMaxDynamicSharedMemorySize,

@@ -21,7 +21,9 @@
 
 namespace sspsd {
 
-__constant__ float c_hbf_taps[SSPSD_HBF_NPRESET][3][SSPSD_HBF_MAXTAPS];
+__constant__ __align__(8) float c_hbf_taps[SSPSD_HBF_NPRESET][3][SSPSD_HBF_MAXTAPS + 1];
+// the same taps shifted by one position, so that the pairs (t1,t2), (t3,t4), ... are 8-byte aligned too
+__constant__ __align__(8) float c_hbf_taps_sh[SSPSD_HBF_NPRESET][3][SSPSD_HBF_MAXTAPS + 1];
 
 constexpr int DEC_OB = 960;   // outputs per CTA (7680 input samples + 488 of halo)
 constexpr int DEC_P = 8;      // consecutive outputs per thread
@@ -70,21 +72,42 @@ __device__ __forceinline__ void hbf_stage(const float* __restrict__ ine, const f
     for (int w = threadIdx.x; w < n_out / P; w += DEC_NT) {
         // plane index of window element i is P w + (REL0 - 2M + 1 + i): its phase and offset are compile
         // time constants, only `w` is per thread (unit stride across lanes)
-        float win[2 * M + P - 1];
+        // window of odd-plane samples as aligned register pairs (win[2m], win[2m+1])
+        constexpr int NW = 2 * M + P - 1;
+        float2 wp[(NW + 1) / 2];
 #pragma unroll
-        for (int i = 0; i < 2 * M + P - 1; ++i) {
+        for (int i = 0; i < NW; ++i) {
             const int c = REL0 - 2 * M + 1 + i;
-            win[i] = ino[(c & (P - 1)) * SI + (c >> LP) + w];
+            const float x = ino[(c & (P - 1)) * SI + (c >> LP) + w];
+            if (i & 1) wp[i >> 1].y = x; else wp[i >> 1].x = x;
         }
+        // Taps are paired so that both window operands of a packed add are aligned pairs: for even q the
+        // pairs (0,1), (2,3), ..., for odd q the pairs (1,2), (3,4), ...; tap i multiplies
+        // win[q+i] + win[q+2M-1-i], and the mirrored operand of a pair is the swapped pair (free swizzle).
+        // The two halves of the packed accumulator hold the even- and the odd-tap partial sums.
+        const float2* __restrict__ tp0 = reinterpret_cast<const float2*>(&c_hbf_taps[PRESET][SET][0]);
+        const float2* __restrict__ tp1 = reinterpret_cast<const float2*>(&c_hbf_taps_sh[PRESET][SET][0]);
         float y[P];
 #pragma unroll
         for (int q = 0; q < P; ++q) {
-            float acc = 0.f;
+            float2 acc = make_float2(0.f, 0.f);
+            constexpr int dummy = 0;
+            (void)dummy;
+            const int i0 = q & 1;  // first paired tap
 #pragma unroll
-            for (int i = 0; i < M; ++i)
-                acc = fmaf(win[q + i] + win[q + 2 * M - 1 - i], c_hbf_taps[PRESET][SET][i], acc);
+            for (int i = i0; i + 1 < M; i += 2) {
+                const float2 l = wp[(q + i) >> 1];
+                const float2 r = wp[(q + 2 * M - 2 - i) >> 1];
+                const float2 sum = __fadd2_rn(l, make_float2(r.y, r.x));
+                acc = __ffma2_rn(sum, (q & 1) ? tp1[(i - 1) >> 1] : tp0[i >> 1], acc);
+            }
+            float a = acc.x + acc.y;
+            auto winv = [&](int k) { return (k & 1) ? wp[k >> 1].y : wp[k >> 1].x; };
+            if (q & 1) a = fmaf(winv(q) + winv(q + 2 * M - 1), c_hbf_taps[PRESET][SET][0], a);  // tap 0
+            // the last tap is unpaired when the paired range [i0, M) has odd length
+            if (((M - i0) & 1) != 0) a = fmaf(winv(q + M - 1) + winv(q + M), c_hbf_taps[PRESET][SET][M - 1], a);
             const int ce = REL0 + q - M + 1;
-            y[q] = ine[(ce & (P - 1)) * SI + (ce >> LP) + w] + acc;
+            y[q] = ine[(ce & (P - 1)) * SI + (ce >> LP) + w] + a;
         }
         if constexpr (FINAL) {
             // gout points at the block's first output; only [rel_lo, rel_hi) of the block is stored
