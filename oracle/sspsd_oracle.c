@@ -15,6 +15,7 @@
 
 #include <assert.h>
 #include <math.h>
+#include <pthread.h>
 #include <stdlib.h>
 #include <string.h>
 
@@ -159,10 +160,20 @@ typedef struct {
     float *w1r, *w1i; /* W_n1^k */
     float *w2r, *w2i; /* W_n2^k */
     float *tr, *ti;   /* W_n^(k1*c), [n1][n2] */
-    float *ar, *ai, *br, *bi; /* work planes, n floats each */
 } fft_plan;
 
+/* Plans hold read-only tables only (built once under a mutex); every thread owns its work planes, so
+ * cascades may run on different threads concurrently (bench.py --impl reference, one channel per thread). */
 static fft_plan g_plans[32];
+static pthread_mutex_t g_plan_lock = PTHREAD_MUTEX_INITIALIZER;
+
+typedef struct {
+    int cap;
+    float *ar, *ai, *br, *bi; /* work planes of fft_soa, cap floats each */
+    int ccap;
+    float *cre, *cim;         /* split planes of orc_fft_forward */
+} fft_scratch;
+static __thread fft_scratch t_scratch;
 
 /* Planes are placed at distinct offsets modulo 4 KiB: the radix-4 passes stream 16 arrays whose
  * mutual distances are powers of two, which would otherwise all map to the same L1 sets. */
@@ -192,8 +203,10 @@ static fft_plan *fft_get_plan(int n)
         l++;
     assert((1 << l) == n && l < 32 && l >= 2);
     fft_plan *p = &g_plans[l];
+    if (__atomic_load_n(&p->n, __ATOMIC_ACQUIRE) == n)
+        return p;
+    pthread_mutex_lock(&g_plan_lock);
     if (p->n != n) {
-        p->n = n;
         p->n1 = 1 << ((l + 1) / 2);
         p->n2 = n / p->n1;
         make_roots(p->n1, &p->w1r, &p->w1i);
@@ -206,12 +219,23 @@ static fft_plan *fft_get_plan(int n)
                 p->tr[k1 * p->n2 + c] = (float)cos(a);
                 p->ti[k1 * p->n2 + c] = (float)sin(a);
             }
-        p->ar = alloc_plane((size_t)n, 2048);
-        p->ai = alloc_plane((size_t)n, 3072);
-        p->br = alloc_plane((size_t)n, 512);
-        p->bi = alloc_plane((size_t)n, 1536);
+        __atomic_store_n(&p->n, n, __ATOMIC_RELEASE); /* published last: tables are complete */
     }
+    pthread_mutex_unlock(&g_plan_lock);
     return p;
+}
+
+static fft_scratch *fft_get_scratch(int n)
+{
+    fft_scratch *s = &t_scratch;
+    if (n > s->cap) { /* planes are never freed (they are skewed pointers); grow-only, per thread */
+        s->ar = alloc_plane((size_t)n, 2048);
+        s->ai = alloc_plane((size_t)n, 3072);
+        s->br = alloc_plane((size_t)n, 512);
+        s->bi = alloc_plane((size_t)n, 1536);
+        s->cap = n;
+    }
+    return s;
 }
 
 static inline void r4_inner(const float *restrict ar, const float *restrict ai, const float *restrict br,
@@ -295,14 +319,15 @@ static int fft_batch(float *xr, float *xi, float *yr, float *yi, int n, int B, c
 static void fft_soa(float *re, float *im, int n)
 {
     fft_plan *pl = fft_get_plan(n);
+    fft_scratch *sc = fft_get_scratch(n);
     const int n1 = pl->n1, n2 = pl->n2;
-    float *xr = re, *xi = im, *yr = pl->ar, *yi = pl->ai;
+    float *xr = re, *xi = im, *yr = sc->ar, *yi = sc->ai;
     if (fft_batch(xr, xi, yr, yi, n1, n2, pl->w1r, pl->w1i)) {
-        xr = pl->ar;
-        xi = pl->ai;
+        xr = sc->ar;
+        xi = sc->ai;
     }
     /* twiddle (contiguous), then blocked transpose [n1][n2] -> [n2][n1] */
-    float *tr = pl->br, *ti = pl->bi;
+    float *tr = sc->br, *ti = sc->bi;
     {
         const float *restrict wr = pl->tr, *restrict wi = pl->ti;
         float *restrict ar = xr, *restrict ai = xi;
@@ -326,7 +351,7 @@ static void fft_soa(float *re, float *im, int n)
                 }
             }
         }
-    float *zr = (xr == re) ? pl->ar : re, *zi = (xr == re) ? pl->ai : im;
+    float *zr = (xr == re) ? sc->ar : re, *zi = (xr == re) ? sc->ai : im;
     if (fft_batch(tr, ti, zr, zi, n2, n1, pl->w2r, pl->w2i)) {
         if (zr != re) {
             memcpy(re, zr, sizeof(float) * (size_t)n);
@@ -347,13 +372,13 @@ void orc_fft_forward(float *c, int n)
         c[0] = ar + br; c[1] = ai + bi; c[2] = ar - br; c[3] = ai - bi;
         return;
     }
-    static float *re = NULL, *im = NULL;
-    static int cap = 0;
-    if (n > cap) { /* planes are never freed (they are skewed pointers); grow-only scratch */
-        re = alloc_plane((size_t)n, 0);
-        im = alloc_plane((size_t)n, 1024);
-        cap = n;
+    fft_scratch *sc = &t_scratch;
+    if (n > sc->ccap) {
+        sc->cre = alloc_plane((size_t)n, 0);
+        sc->cim = alloc_plane((size_t)n, 1024);
+        sc->ccap = n;
     }
+    float *re = sc->cre, *im = sc->cim;
     for (int i = 0; i < n; i++) {
         re[i] = c[2 * i];
         im[i] = c[2 * i + 1];
