@@ -8,7 +8,10 @@
  * Conventions
  *   - every function returns an int32 status (SSPSD_OK == 0); nothing unwinds or aborts across the
  *     boundary; sspsd_last_error() gives a thread-local human-readable message for the last failure;
- *   - all pointers are borrowed for the duration of the call only; the caller owns output buffers;
+ *   - host pointers are borrowed for the duration of the call only; SSPSD_MEM_DEVICE input is read
+ *     asynchronously, in place (zero copy), on the handle's stream: it must stay valid and unmodified in
+ *     stream order, i.e. until work queued on that stream after the call (an event recorded there, or
+ *     sspsd_cascade_sync()) has completed; the caller owns output buffers;
  *     variable-length outputs use "capacity in / length out" size_t* parameters and return
  *     SSPSD_ESHORT (with the needed length written) when the capacity is too small;
  *   - `mem` says where a buffer lives: SSPSD_MEM_HOST (pageable or pinned host memory) or
@@ -146,6 +149,8 @@ int32_t sspsd_cascade_psd(sspsd_cascade *h, const sspsd_merge_opts *opts, float 
                           sspsd_break *b, size_t *b_len);
 /* number of stages currently alive (self.stages.len()) */
 int32_t sspsd_cascade_num_stages(sspsd_cascade *h, uint32_t *n);
+/* the CUDA stream (cudaStream_t) all work of the handle is ordered on: cfg.stream, or the private stream */
+int32_t sspsd_cascade_stream(const sspsd_cascade *h, void **stream);
 /* launch everything staged from host-pointer process() calls */
 int32_t sspsd_cascade_flush(sspsd_cascade *h);
 /* flush + wait for the handle's stream */
@@ -228,6 +233,8 @@ typedef struct sspsd_stage sspsd_stage;
 /* Psd::new(fft, win), src/psd.rs:137-152 (the FFT plan is internal) */
 int32_t sspsd_stage_create(const sspsd_config *cfg, sspsd_stage **out);
 void sspsd_stage_destroy(sspsd_stage *h);
+/* the CUDA stream the stage's work is ordered on (see sspsd_cascade_stream) */
+int32_t sspsd_stage_stream(const sspsd_stage *h, void **stream);
 /* Psd::set_avg / set_detrend, src/psd.rs:154-160 */
 int32_t sspsd_stage_set_avg(sspsd_stage *h, uint32_t avg);
 int32_t sspsd_stage_set_detrend(sspsd_stage *h, int32_t detrend);
@@ -262,6 +269,8 @@ typedef struct {
 typedef struct sspsd_decoder sspsd_decoder;
 int32_t sspsd_decoder_create(int32_t device, void *stream, sspsd_decoder **out);
 void sspsd_decoder_destroy(sspsd_decoder *d);
+/* the CUDA stream the decoder's kernels run on; SSPSD_MEM_DEVICE frames must be complete in that stream's order */
+int32_t sspsd_decoder_stream(const sspsd_decoder *d, void **stream);
 
 typedef struct {
     uint32_t format;            /* Header.format of the batch (all frames of a call share it) */
@@ -361,6 +370,23 @@ typedef struct {
     uint64_t dc_cut;  /* default 2 */
 } sspsd_var;
 float sspsd_var_eval(const sspsd_var *v, const float *phase_psd, const float *frequencies, size_t n, float tau);
+
+/* ---------------------------------------------------------------------------------------------
+ * Trace::plot + struct Trapezoidal, src/bin/psd.rs:96-157 -- host helper on psd() output: trapezoidal
+ * integration over the irregular frequency grid of the merged spectrum (f32 running sums in the
+ * reference's order).  `integral` receives sqrt(sum of the trapezoids whose upper frequency fs*f lies in
+ * [integral_start, integral_end]); xy (may be NULL; n_points: capacity in points in, points out) receives
+ * the plot points [log10(f) + log10(fs), integrate ? sqrt(running integral) : 10 (log10(p) - log10(fs))]
+ * for every f that is a normal f32 (the DC bin is skipped, like `f.is_normal()` does).
+ * --------------------------------------------------------------------------------------------- */
+typedef struct {
+    float fs;             /* AcqOpts::fs, default 1.0 */
+    float integral_start; /* AcqOpts::integral_start, default 1e-6 */
+    float integral_end;   /* AcqOpts::integral_end, default 0.5 */
+    uint32_t integrate;   /* AcqOpts::integrate */
+} sspsd_plot_opts;
+int32_t sspsd_trace_plot(const sspsd_plot_opts *opts, const float *psd, const float *frequencies, size_t n,
+                         float *integral, double *xy, size_t *n_points);
 
 #ifdef __cplusplus
 }

@@ -33,7 +33,7 @@ def _host_key():
     except OSError:
         pass
     h = hashlib.sha1(flags.encode())
-    for name in ("sspsd_oracle.c", "sspsd_oracle.h", "hbf_taps.h", "Makefile"):
+    for name in ("sspsd_oracle.c", "model_f64.c", "sspsd_oracle.h", "hbf_taps.h", "Makefile"):
         with open(os.path.join(_HERE, name), "rb") as f:
             h.update(f.read())
     return h.hexdigest()[:12]
@@ -122,11 +122,19 @@ def lib():
         "orc_loss_ratio": (C.c_float, [C.POINTER(LossC)]),
         "orc_var_eval": (C.c_float, [C.c_int, C.c_int, C.c_float, C.c_size_t, _fp, _fp, C.c_size_t,
                                      C.c_float]),
+        "orc_trace_plot": (C.c_size_t, [C.c_float, C.c_float, C.c_float, C.c_int, _fp, _fp, C.c_size_t, _fp,
+                                        C.POINTER(C.c_double)]),
         "orc_philox4x32_10": (None, [C.POINTER(C.c_uint32), C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]),
         "orc_source_new": (vp, [C.c_int, C.c_int64, C.c_uint64]),
         "orc_source_free": (None, [vp]),
         "orc_source_get": (None, [vp, _fp, C.c_size_t]),
         "orc_dsm_input": (C.c_uint32, [C.c_uint64, C.c_uint32]),
+        "f64_cascade_new": (vp, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_uint32, C.c_uint32, C.c_int]),
+        "f64_cascade_free": (None, [vp]),
+        "f64_cascade_process": (None, [vp, _fp, C.c_size_t]),
+        "f64_cascade_num_stages": (C.c_int, [vp]),
+        "f64_cascade_stage": (None, [vp, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_uint64),
+                                     C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(L, name)
@@ -334,6 +342,17 @@ def var_eval(phase_psd, frequencies, tau, x_exp=-2, sinx_exp=4, clip=3.402823466
     return lib().orc_var_eval(x_exp, sinx_exp, clip, dc_cut, _ptr(p), _ptr(f), min(p.size, f.size), tau)
 
 
+def trace_plot(psd, frequencies, fs=1.0, integral_start=1e-6, integral_end=0.5, integrate=False):
+    """Trace::plot (bin/psd.rs:125-157) -> (sqrt of the band integral, plot points [n, 2] float64)"""
+    p, f = _f32(psd), _f32(frequencies)
+    n = min(p.size, f.size)
+    xy = np.zeros((max(n, 1), 2), np.float64)
+    integ = C.c_float()
+    m = lib().orc_trace_plot(fs, integral_start, integral_end, int(integrate), _ptr(p), _ptr(f), n, C.byref(integ),
+                             xy.ctypes.data_as(C.POINTER(C.c_double)))
+    return integ.value, xy[:m].copy()
+
+
 SOURCE_NOISE, SOURCE_DSM = 0, 1
 
 
@@ -366,3 +385,35 @@ class Source:
 
 def dsm_input(i, ftw):
     return lib().orc_dsm_input(i, ftw)
+
+
+class CascadeF64:
+    """Streaming float64 truth model (oracle/model_f64.c): same semantics as Cascade, f64 arithmetic,
+    independent code structure.  max_stages=1 models a single Psd<N> stage."""
+
+    def __init__(self, n, hbf=HBF_140, window=WINDOW_HANN, detrend=DETREND_NONE, avg_limit=0xFFFFFFFF,
+                 avg_count=0xFFFFFFFF, max_stages=0):
+        self.n = n
+        self._h = lib().f64_cascade_new(n, window, hbf, detrend, avg_limit, avg_count, max_stages)
+        if not self._h:
+            raise ValueError("unsupported configuration")
+
+    def process(self, x):
+        x = _f32(x)
+        lib().f64_cascade_process(self._h, _ptr(x), x.size)
+
+    def num_stages(self):
+        return lib().f64_cascade_num_stages(self._h)
+
+    def stage(self, i):
+        """(spectrum float64[N/2+1], effective count, segments, samples received)"""
+        sp = np.zeros(self.n // 2 + 1, np.float64)
+        cnt, craw, L = C.c_uint64(), C.c_uint64(), C.c_uint64()
+        lib().f64_cascade_stage(self._h, i, sp.ctypes.data_as(C.POINTER(C.c_double)), C.byref(cnt), C.byref(craw),
+                                C.byref(L))
+        return sp, cnt.value, craw.value, L.value
+
+    def __del__(self):
+        if getattr(self, "_h", None) and _lib is not None:
+            _lib.f64_cascade_free(self._h)
+            self._h = None

@@ -967,6 +967,36 @@ float orc_var_eval(int x_exp, int sinx_exp, float clip, size_t dc_cut, const flo
     return accu;
 }
 
+/* Trace::plot + Trapezoidal (bin/psd.rs:96-157).  Returns the number of plot points written to xy. */
+size_t orc_trace_plot(float fs, float integral_start, float integral_end, int integrate, const float *psd,
+                      const float *frequencies, size_t n, float *integral, double *xy)
+{
+    const float logfs = log10f(fs);                /* bin/psd.rs:126 */
+    float x0 = 0.0f, y0 = 0.0f, acc = 0.0f;        /* Trapezoidal::default(), bin/psd.rs:96-101 */
+    float pi = 0.0f;
+    size_t np = 0;
+    for (size_t i = 0; i < n; i++) {
+        float p = psd[i], f = frequencies[i];
+        float di = (p + y0) * 0.5f * (f - x0);     /* push, bin/psd.rs:104-110 */
+        x0 = f;
+        y0 = p;
+        acc += di;
+        float ff = fs * f;
+        if (integral_start <= ff && ff <= integral_end) /* RangeInclusive::contains, bin/psd.rs:136 */
+            pi += di;
+        if (fpclassify(f) == FP_NORMAL) {          /* f.is_normal(), bin/psd.rs:140 */
+            if (xy) {
+                xy[2 * np] = (double)(log10f(f) + logfs);
+                xy[2 * np + 1] = (double)(integrate ? sqrtf(acc) : 10.0f * (log10f(p) - logfs));
+            }
+            np++;
+        }
+    }
+    if (integral)
+        *integral = sqrtf(pi);                     /* bin/psd.rs:155 */
+    return np;
+}
+
 /* ------------------------------------------------------------------------------------------
  * Synthetic sources (source.rs:66-73, 104-134)
  * ------------------------------------------------------------------------------------------ */

@@ -119,6 +119,10 @@ float orc_loss_ratio(const orc_loss *l);                          /* loss.rs:29-
 float orc_var_eval(int x_exp, int sinx_exp, float clip, size_t dc_cut, const float *phase_psd,
                    const float *frequencies, size_t n, float tau);
 
+/* ---- Trace::plot + Trapezoidal (bin/psd.rs:96-157): trapezoidal integral over the merged spectrum ---- */
+size_t orc_trace_plot(float fs, float integral_start, float integral_end, int integrate, const float *psd,
+                      const float *frequencies, size_t n, float *integral, double *xy);
+
 /* ---- synthetic sources (source.rs:66-73, 104-134) ----
  * Noise: uniform (0,1) -> (x - 0.5) * sqrt(12), folded through |noise| first-order integrators
  * (noise < 0) or differentiators (noise > 0) with f32 state, exactly the fold at source.rs:110-114.

@@ -58,6 +58,11 @@ class DecodeInfoC(C.Structure):
                 ("frames_ok", C.c_uint64)]
 
 
+class PlotOptsC(C.Structure):
+    _fields_ = [("fs", C.c_float), ("integral_start", C.c_float), ("integral_end", C.c_float),
+                ("integrate", C.c_uint32)]
+
+
 class VarC(C.Structure):
     _fields_ = [("x_exp", C.c_int32), ("sinx_exp", C.c_int32), ("clip", C.c_float), ("_pad", C.c_uint32),
                 ("dc_cut", C.c_uint64)]
@@ -83,6 +88,7 @@ PROTOTYPES = {
     "sspsd_cascade_rbw": (_i32, [_vp, C.POINTER(C.c_float)]),
     "sspsd_cascade_psd": (_i32, [_vp, C.POINTER(MergeOptsC), _vp, _psz, C.POINTER(BreakC), _psz]),
     "sspsd_cascade_num_stages": (_i32, [_vp, C.POINTER(C.c_uint32)]),
+    "sspsd_cascade_stream": (_i32, [_vp, C.POINTER(_vp)]),
     "sspsd_cascade_flush": (_i32, [_vp]),
     "sspsd_cascade_sync": (_i32, [_vp]),
     "sspsd_break_frequencies": (_i32, [C.POINTER(BreakC), _sz, _vp, _psz]),
@@ -97,6 +103,7 @@ PROTOTYPES = {
     "sspsd_cascade_profile_read": (_i32, [_vp, C.POINTER(ProfileC)]),
     "sspsd_stage_create": (_i32, [C.POINTER(Config), C.POINTER(_vp)]),
     "sspsd_stage_destroy": (None, [_vp]),
+    "sspsd_stage_stream": (_i32, [_vp, C.POINTER(_vp)]),
     "sspsd_stage_set_avg": (_i32, [_vp, C.c_uint32]),
     "sspsd_stage_set_detrend": (_i32, [_vp, _i32]),
     "sspsd_stage_process_f32": (_i32, [_vp, _vp, _sz, _i32, _vp, _psz, _i32]),
@@ -106,6 +113,7 @@ PROTOTYPES = {
     "sspsd_stage_buf": (_i32, [_vp, _vp, _psz, _i32]),
     "sspsd_decoder_create": (_i32, [_i32, _vp, C.POINTER(_vp)]),
     "sspsd_decoder_destroy": (None, [_vp]),
+    "sspsd_decoder_stream": (_i32, [_vp, C.POINTER(_vp)]),
     "sspsd_decode_frames": (_i32, [_vp, _vp, _sz, _sz, _sz, _i32, C.POINTER(LossC), C.POINTER(_vp), _sz, _i32,
                                    C.POINTER(DecodeInfoC)]),
     "sspsd_cascade_process_frames": (_i32, [_vp, C.POINTER(_vp), C.c_uint32, _vp, _sz, _sz, _sz, _i32,
@@ -113,6 +121,7 @@ PROTOTYPES = {
     "sspsd_loss_update": (None, [C.POINTER(LossC), C.c_uint32, C.c_uint8]),
     "sspsd_loss_ratio": (C.c_float, [C.POINTER(LossC)]),
     "sspsd_var_eval": (C.c_float, [C.POINTER(VarC), _vp, _vp, _sz, C.c_float]),
+    "sspsd_trace_plot": (_i32, [C.POINTER(PlotOptsC), _vp, _vp, _sz, C.POINTER(C.c_float), _vp, _psz]),
     "sspsd_source_create": (_i32, [_i32, C.c_int64, C.c_uint64, _i32, _vp, C.POINTER(_vp)]),
     "sspsd_source_destroy": (None, [_vp]),
     "sspsd_source_reset": (_i32, [_vp]),

@@ -150,6 +150,13 @@ int32_t sspsd_cascade_num_stages(sspsd_cascade* h, uint32_t* n)
     return SSPSD_OK;
 }
 
+int32_t sspsd_cascade_stream(const sspsd_cascade* h, void** stream)
+{
+    if (!h || !stream) return SSPSD_EINVAL;
+    *stream = (void*)h->c.stream();
+    return SSPSD_OK;
+}
+
 int32_t sspsd_cascade_flush(sspsd_cascade* h) { return h ? h->c.flush() : SSPSD_EINVAL; }
 int32_t sspsd_cascade_sync(sspsd_cascade* h) { return h ? h->c.sync() : SSPSD_EINVAL; }
 
@@ -234,6 +241,13 @@ int32_t sspsd_stage_create(const sspsd_config* cfg, sspsd_stage** out)
 
 void sspsd_stage_destroy(sspsd_stage* h) { delete h; }
 
+int32_t sspsd_stage_stream(const sspsd_stage* h, void** stream)
+{
+    if (!h || !stream) return SSPSD_EINVAL;
+    *stream = (void*)h->c.stream();
+    return SSPSD_OK;
+}
+
 int32_t sspsd_stage_set_avg(sspsd_stage* h, uint32_t avg) { return h ? h->c.set_stage_avg(avg) : SSPSD_EINVAL; }
 int32_t sspsd_stage_set_detrend(sspsd_stage* h, int32_t d) { return h ? h->c.set_detrend(d) : SSPSD_EINVAL; }
 
@@ -310,6 +324,13 @@ int32_t sspsd_decoder_create(int32_t device, void* stream, sspsd_decoder** out)
         return SSPSD_ECUDA;
     }
     *out = d;
+    return SSPSD_OK;
+}
+
+int32_t sspsd_decoder_stream(const sspsd_decoder* d, void** stream)
+{
+    if (!d || !stream) return SSPSD_EINVAL;
+    *stream = (void*)d->stream;
     return SSPSD_OK;
 }
 
@@ -491,13 +512,22 @@ int32_t sspsd_decode_frames(sspsd_decoder* d, const uint8_t* frames, size_t n_fr
     if (rc) return rc;
     const sspsd::DecodeResult r = *d->h_res;
     const unsigned int div = r.format == SSPSD_FORMAT_ADCDAC ? 8 : 1;
+    if (want && traces_mem != SSPSD_MEM_DEVICE && r.first_bad > 0 &&
+        (size_t)r.first_bad * r.batches * div > trace_cap) {
+        // capacity-in / length-out retry: report the needed length and leave `loss` untouched, so that the
+        // retried call accounts for the batch exactly once (Loss stays bit-exact against loss.rs)
+        if (info) {
+            std::memset(info, 0, sizeof(*info));
+            info->format = r.format;
+            info->n_traces = r.format == SSPSD_FORMAT_MPLL ? 3 : 4;
+            info->samples_per_trace = (uint64_t)r.first_bad * r.batches * div;
+        }
+        set_error("trace capacity too small");
+        return SSPSD_ESHORT;
+    }
     apply_result(r, n_frames, loss, info, div);
     if (want && traces_mem != SSPSD_MEM_DEVICE && r.first_bad > 0) {
         const size_t ns = (size_t)r.first_bad * r.batches * div;
-        if (ns > trace_cap) {
-            set_error("trace capacity too small");
-            return SSPSD_ESHORT;
-        }
         const int ntr = r.format == SSPSD_FORMAT_MPLL ? 3 : 4;
         for (int t = 0; t < ntr; ++t)
             if (traces[t])
@@ -589,6 +619,49 @@ float sspsd_loss_ratio(const sspsd_loss* l)
     // loss.rs:29-30
     if (!l) return 0.f;
     return (float)l->dropped / (float)(l->received + l->dropped);
+}
+
+int32_t sspsd_trace_plot(const sspsd_plot_opts* o, const float* psd, const float* frequencies, size_t n,
+                         float* integral, double* xy, size_t* n_points)
+{
+    // Trace::plot + Trapezoidal, bin/psd.rs:96-157 (f32 running sums in the reference's order)
+    sspsd_plot_opts d{1.0f, 1e-6f, 0.5f, 0};  // AcqOpts defaults, bin/psd.rs:37-38, 63-69
+    if (o) d = *o;
+    if (!n_points || (n && (!psd || !frequencies))) {
+        set_error("null argument");
+        return SSPSD_EINVAL;
+    }
+    size_t need = 0;
+    for (size_t i = 0; i < n; ++i)
+        if (std::fpclassify(frequencies[i]) == FP_NORMAL) ++need;
+    if (xy && *n_points < need) {
+        *n_points = need;
+        set_error("output capacity too small");
+        return SSPSD_ESHORT;
+    }
+    const float logfs = log10f(d.fs);
+    float tx = 0.f, ty = 0.f, ti = 0.f;  // Trapezoidal::default()
+    float pi = 0.f;
+    size_t np = 0;
+    for (size_t i = 0; i < n; ++i) {
+        const float p = psd[i], f = frequencies[i];
+        const float di = (p + ty) * 0.5f * (f - tx);  // Trapezoidal::push, bin/psd.rs:104-110
+        tx = f;
+        ty = p;
+        ti += di;
+        const float ff = d.fs * f;
+        if (ff >= d.integral_start && ff <= d.integral_end) pi += di;  // bin/psd.rs:136-139
+        if (std::fpclassify(f) == FP_NORMAL) {  // f.is_normal(), bin/psd.rs:140
+            if (xy) {
+                xy[2 * np] = (double)(log10f(f) + logfs);
+                xy[2 * np + 1] = (double)(d.integrate ? sqrtf(ti) : 10.0f * (log10f(p) - logfs));
+            }
+            ++np;
+        }
+    }
+    *n_points = np;
+    if (integral) *integral = sqrtf(pi);
+    return SSPSD_OK;
 }
 
 float sspsd_var_eval(const sspsd_var* v, const float* phase_psd, const float* frequencies, size_t n, float tau)

@@ -6,6 +6,7 @@
 #include <cmath>
 #include <cstdlib>
 #include <cstring>
+#include <mutex>
 
 #include "sspsd_decim_kernel.cuh"
 #include "sspsd_stage_kernel.cuh"
@@ -79,21 +80,17 @@ int prepare_stage_t(int hop, int budget_bytes, int* tmax)
 
 // K2 variant for N = 4096 (A/B switch for profiling): SSPSD_K2 = r8 | r16 | ring (default ring:
 // persistent TMA-ring kernel for the Hann window, tiled radix-16 kernel for the rectangular one)
-int k2_variant()
+// (read when a handle is created and stored in it: no process-wide mutable state)
+int k2_variant_from_env()
 {
-    static int v = -1;
-    if (v < 0) {
-        const char* e = getenv("SSPSD_K2");
-        std::string m = e ? e : "ring";
-        v = m == "r8" ? 0 : m == "r16" ? 1 : 2;
-    }
-    return v;
+    const char* e = getenv("SSPSD_K2");
+    std::string m = e ? e : "ring";
+    return m == "r8" ? 0 : m == "r16" ? 1 : 2;
 }
-bool use_r16() { return k2_variant() >= 1; }
 
-int launch_stage(int log2n, const StageParams& p, int grid, cudaStream_t s)
+int launch_stage(int log2n, bool r16, const StageParams& p, int grid, cudaStream_t s)
 {
-    if (log2n == 12 && use_r16()) {
+    if (log2n == 12 && r16) {
         psd_stage_kernel_r16<<<grid, R16::NT, stage_r16_smem_bytes(p.T, p.hop), s>>>(p);
         return cuda_ok(cudaGetLastError(), "psd_stage_kernel_r16 launch") ? SSPSD_OK : SSPSD_ECUDA;
     }
@@ -108,9 +105,9 @@ int launch_stage(int log2n, const StageParams& p, int grid, cudaStream_t s)
     }
 }
 
-int prepare_stage(int log2n, int hop, int* tmax, int* nt)
+int prepare_stage(int log2n, bool r16, int hop, int* tmax, int* nt)
 {
-    if (log2n == 12 && use_r16()) {
+    if (log2n == 12 && r16) {
         int t = 64;
         while (t > 1 && (long long)stage_r16_smem_bytes(t, hop) > 112 * 1024) --t;
         *tmax = t;
@@ -147,15 +144,20 @@ int decim_halo(int preset)
     return preset == SSPSD_HBF_98 ? DecGeom<3, 6, 15>::HALO : DecGeom<5, 10, 23>::HALO;
 }
 
+// Constant-memory tap tables and kernel attributes are per device and set once per device; handles may be
+// created concurrently on different threads (one per GPU), so the "once" is a mutex-guarded flag and the
+// staging arrays are locals.
 int upload_taps_once(int device)
 {
+    static std::mutex mu;
     static bool done[64] = {false};
+    std::lock_guard<std::mutex> lock(mu);
     if (device < 64 && done[device])
         return SSPSD_OK;
     static_assert(sizeof(sspsd_hbf_taps) == sizeof(float) * SSPSD_HBF_NPRESET * 3 * SSPSD_HBF_MAXTAPS, "tap table");
     {
         // rows padded to an even length (8-byte aligned pairs) + a copy shifted by one tap
-        static float t0[SSPSD_HBF_NPRESET][3][SSPSD_HBF_MAXTAPS + 1], t1[SSPSD_HBF_NPRESET][3][SSPSD_HBF_MAXTAPS + 1];
+        float t0[SSPSD_HBF_NPRESET][3][SSPSD_HBF_MAXTAPS + 1], t1[SSPSD_HBF_NPRESET][3][SSPSD_HBF_MAXTAPS + 1];
         for (int p = 0; p < SSPSD_HBF_NPRESET; ++p)
             for (int s = 0; s < 3; ++s)
                 for (int i = 0; i <= SSPSD_HBF_MAXTAPS; ++i) {
@@ -352,7 +354,8 @@ int Cascade::init(const sspsd_config& cfg, uint32_t max_stages)
     }
     int rc = upload_taps_once(cfg.device);
     if (rc) return rc;
-    rc = prepare_stage((int)log2n_, (int)hop_, &tmax_, &nt_);
+    k2_variant_ = k2_variant_from_env();
+    rc = prepare_stage((int)log2n_, k2_variant_ >= 1, (int)hop_, &tmax_, &nt_);
     if (rc) return rc;
 
     const uint32_t m = n / 2;
@@ -462,7 +465,7 @@ int Cascade::launch_psd(size_t i, const StreamSrc& src, uint64_t k0, uint64_t ns
     p.k0 = (long long)k0;
     p.nseg = (int)nseg;
     long long t = ((long long)nseg + 2ll * num_sms_ - 1) / (2ll * num_sms_);
-    const bool ring = log2n_ == 12 && k2_variant() == 2 && hop_ * 2 == n_;
+    const bool ring = log2n_ == 12 && k2_variant_ == 2 && hop_ * 2 == n_;
     if (ring) {
         // persistent kernel: two CTAs per SM, each streams through a contiguous range of segments
         // with the deep stages overlapping on a second stream, stage 0 is cut into ~4 waves of CTAs so
@@ -485,7 +488,7 @@ int Cascade::launch_psd(size_t i, const StreamSrc& src, uint64_t k0, uint64_t ns
         prof_end(psd_stream(i));
         return cuda_ok(cudaGetLastError(), "psd_stage_kernel_ring launch") ? SSPSD_OK : SSPSD_ECUDA;
     }
-    const bool tiled_r16 = log2n_ == 12 && use_r16();
+    const bool tiled_r16 = log2n_ == 12 && k2_variant_ >= 1;
     if (tiled_r16) {
         p.T = (int)std::max<long long>(1, std::min<long long>(t, tmax_));
     } else {
@@ -509,7 +512,7 @@ int Cascade::launch_psd(size_t i, const StreamSrc& src, uint64_t k0, uint64_t ns
     p.tpc = tiled_r16 ? 1 : (int)std::max<long long>(1, (ntiles + 2ll * num_sms_ - 1) / (2ll * num_sms_));
     int grid = (int)((ntiles + p.tpc - 1) / p.tpc);
     prof_begin(i == 0 ? SSPSD_PROF_PSD_STAGE0 : SSPSD_PROF_PSD_DEEP, nseg * (uint64_t)hop_, psd_stream(i));
-    int rc = launch_stage((int)log2n_, p, grid, psd_stream(i));
+    int rc = launch_stage((int)log2n_, k2_variant_ >= 1, p, grid, psd_stream(i));
     prof_end(psd_stream(i));
     return rc;
 }
@@ -1072,6 +1075,9 @@ int Cascade::clone_from(Cascade& o)
     for (size_t i = 0; i < o.stages_.size(); ++i) {
         rc = add_stage();
         if (rc) return rc;
+        // add_stage() zeroes the carry buffers and the accumulator row on stage_stream(i); the copies below run
+        // on stream_, and nothing else orders the two non-blocking streams
+        SSPSD_CUDA(cudaStreamSynchronize(stage_stream(i)));
         StageState& d = stages_[i];
         const StageState& s = o.stages_[i];
         d.L = s.L;

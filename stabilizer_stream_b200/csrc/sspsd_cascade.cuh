@@ -147,6 +147,7 @@ private:
     int drain_ = 0;    // hbf_dec_response_length(3)
     int num_sms_ = 148;
     int tmax_ = 1, nt_ = 256;  // largest tile (segments per CTA) and CTA size of the stage kernel
+    int k2_variant_ = 2;       // SSPSD_K2 at creation: 0 = radix-8 tiled, 1 = radix-16 tiled, 2 = TMA ring (N = 4096)
     bool single_stage_avg_set_ = false;
     uint32_t single_stage_avg_ = 0xffffffffu;
     cudaStream_t stream_ = nullptr;

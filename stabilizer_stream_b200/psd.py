@@ -112,17 +112,46 @@ def _as_buffer(x):
 
 
 def _default_stream(device):
-    """With torch in the process, order the handle's work on torch's current stream of that device, so
-    that device tensors handed to process() follow torch's usual stream-ordered lifetime rules (a
-    temporary tensor may be freed right after the call).  Without torch: a private stream."""
+    """With torch in the process, order the handle's work on torch's current stream of that device (this
+    initialises torch's CUDA context if it is not yet), so that device tensors handed to process() follow
+    torch's usual stream-ordered lifetime rules.  Without torch: a private stream."""
     import sys
     torch = sys.modules.get("torch")
-    if torch is None or not torch.cuda.is_available() or not torch.cuda.is_initialized():
+    if torch is None or not torch.cuda.is_available():
         return None
     h = torch.cuda.current_stream(device).cuda_stream
     # torch's default stream is the legacy NULL stream; a NULL cfg.stream means "private stream" in the
     # C ABI, so name the legacy stream explicitly (cudaStreamLegacy == (cudaStream_t)1)
     return h if h else 1
+
+
+class _StreamOrdered:
+    """Mixin of the handle classes that read CUDA tensors in place: SSPSD_MEM_DEVICE input is consumed
+    asynchronously on the HANDLE's stream (include/sspsd.h), which need not be the stream torch is on when
+    process() is called (a handle made before `with torch.cuda.stream(s)`, or one with a private stream).
+    Before the call the handle's stream waits for torch's current stream (the producer of x); after it the
+    tensor is marked as in use on the handle's stream (record_stream), so the caching allocator cannot
+    recycle a temporary -- e.g. the .contiguous() copy -- while the kernels still read it."""
+
+    _hs = None
+
+    def _stream_ptr(self):  # overridden where the C ABI exposes the handle's stream
+        return None
+
+    def _order_device_input(self, t):
+        import torch
+        if t.device.index != self.device:
+            raise ValueError("tensor lives on cuda:%d, the handle on cuda:%d" % (t.device.index, self.device))
+        if self._hs is None:
+            ptr = self._stream_ptr()
+            if ptr is None:
+                return
+            self._hs = (torch.cuda.default_stream(t.device) if ptr in (0, 1)
+                        else torch.cuda.ExternalStream(ptr, device=t.device))
+        cur = torch.cuda.current_stream(t.device)
+        if (cur.cuda_stream or 1) != (self._hs.cuda_stream or 1):
+            self._hs.wait_stream(cur)
+            t.record_stream(self._hs)
 
 
 def _config(n, window, hbf, device, stream, max_batch, host_stage):
@@ -139,11 +168,12 @@ def _config(n, window, hbf, device, stream, max_batch, host_stage):
     return cfg
 
 
-class PsdCascade:
+class PsdCascade(_StreamOrdered):
     """PsdCascade<N>, src/psd.rs:399-544.  `PsdCascade(n)` is `PsdCascade::<N>::default()`."""
 
     def __init__(self, n=512, device=0, hbf=Hbf.TAPS_140, stream=None, max_batch=0, host_stage=0, _handle=None):
         self.n = n
+        self.device = int(device)
         if _handle is not None:
             self._h = _handle
             return
@@ -155,7 +185,12 @@ class PsdCascade:
     def clone(self):
         h = C.c_void_p()
         L.check(L.lib().sspsd_cascade_clone(self._h, C.byref(h)))
-        return PsdCascade(self.n, _handle=h)
+        return PsdCascade(self.n, device=self.device, _handle=h)
+
+    def _stream_ptr(self):
+        s = C.c_void_p()
+        L.check(L.lib().sspsd_cascade_stream(self._h, C.byref(s)))
+        return s.value or 0
 
     def reset(self):
         L.check(L.lib().sspsd_cascade_reset(self._h))
@@ -173,6 +208,8 @@ class PsdCascade:
 
     def process(self, x):
         ptr, n, mem, keep = _as_buffer(x)
+        if mem == L.MEM_DEVICE:
+            self._order_device_input(keep)
         L.check(L.lib().sspsd_cascade_process_f32(self._h, ptr, n, mem))
         del keep
 
@@ -234,6 +271,10 @@ class PsdCascade:
 
     def process_stage(self, stage, x):
         ptr, n, mem, keep = _as_buffer(x)
+        if mem == L.MEM_DEVICE:
+            # copied into the stage's own buffer on a library stream: make the producer's work visible first
+            import torch
+            torch.cuda.current_stream(keep.device).synchronize()
         L.check(L.lib().sspsd_cascade_process_stage(self._h, stage, ptr, n, mem))
         del keep
 
@@ -266,15 +307,21 @@ class PsdCascade:
             self._h = None
 
 
-class Psd:
+class Psd(_StreamOrdered):
     """Psd<N> + trait PsdStage, src/psd.rs:119-288 (one stage, decimated output exposed)."""
 
     def __init__(self, n=512, window=Window.HANN, device=0, hbf=Hbf.TAPS_140, stream=None):
         self.n = n
+        self.device = int(device)
         cfg = _config(n, window, hbf, device, stream, 0, 0)
         h = C.c_void_p()
         L.check(L.lib().sspsd_stage_create(C.byref(cfg), C.byref(h)))
         self._h = h
+
+    def _stream_ptr(self):
+        s = C.c_void_p()
+        L.check(L.lib().sspsd_stage_stream(self._h, C.byref(s)))
+        return s.value or 0
 
     def set_avg(self, avg: int):
         L.check(L.lib().sspsd_stage_set_avg(self._h, avg))
@@ -286,7 +333,10 @@ class Psd:
         """PsdStage::process(x, y) -> y[..n].  Returns a numpy array, or a view of `out` (a CUDA float32
         tensor that receives the decimated items on the device) when given."""
         ptr, n, mem, keep = _as_buffer(x)
+        if mem == L.MEM_DEVICE:
+            self._order_device_input(keep)
         if out is not None:
+            self._order_device_input(out)  # written on the handle's stream
             yl = C.c_size_t(out.numel())
             L.check(L.lib().sspsd_stage_process_f32(self._h, ptr, n, mem, out.data_ptr(), C.byref(yl), L.MEM_DEVICE))
             return out[:yl.value]
@@ -367,7 +417,7 @@ class Loss:
         return L.lib().sspsd_loss_ratio(C.byref(self.c))
 
 
-class FrameDecoder:
+class FrameDecoder(_StreamOrdered):
     """Batched Frame::from_bytes + Loss::update + Payload::traces (src/de/frame.rs:49-60,
     src/loss.rs:11-26, src/de/data.rs)."""
 
@@ -377,11 +427,18 @@ class FrameDecoder:
             stream = _default_stream(device)
         L.check(L.lib().sspsd_decoder_create(device, stream, C.byref(h)))
         self._h = h
+        self.device = int(device)
 
-    @staticmethod
-    def _frames(frames, frame_len, frame_stride):
+    def _stream_ptr(self):
+        s = C.c_void_p()
+        L.check(L.lib().sspsd_decoder_stream(self._h, C.byref(s)))
+        return s.value or 0
+
+    def _frames(self, frames, frame_len, frame_stride):
         if hasattr(frames, "data_ptr"):
             t = frames.contiguous()
+            if t.is_cuda:
+                self._order_device_input(t)
             return t.data_ptr(), t.numel(), (L.MEM_DEVICE if t.is_cuda else L.MEM_HOST), t
         a = np.frombuffer(frames, dtype=np.uint8) if not isinstance(frames, np.ndarray) else np.ascontiguousarray(frames, np.uint8)
         return a.ctypes.data, a.size, L.MEM_HOST, a
@@ -421,6 +478,8 @@ class FrameDecoder:
         ptr, nbytes, mem, keep = self._frames(frames, frame_len, frame_stride)
         if n_frames is None:
             n_frames = 0 if nbytes < frame_len else 1 + (nbytes - frame_len) // frame_stride
+        for t in out:
+            self._order_device_input(t)  # written on the decoder's stream
         ptrs = (C.c_void_p * L.MAX_TRACES)(*[t.data_ptr() for t in out])
         info = L.DecodeInfoC()
         st = L.lib().sspsd_decode_frames(self._h, ptr, n_frames, frame_len, frame_stride, mem,
@@ -470,6 +529,30 @@ class Var:
         f = np.ascontiguousarray(frequencies, np.float32)
         v = L.VarC(self.x_exp, self.sinx_exp, self.clip, 0, self.dc_cut)
         return L.lib().sspsd_var_eval(C.byref(v), p.ctypes.data, f.ctypes.data, min(p.size, f.size), tau)
+
+
+@dataclass
+class Trace:
+    """struct Trace of src/bin/psd.rs:118-157: a merged spectrum with its breaks and frequencies.
+    plot() is Trace::plot: trapezoidal integration over the irregular frequency grid (struct Trapezoidal,
+    bin/psd.rs:96-116) and the log-log plot points."""
+    name: str
+    breaks: list
+    psd: np.ndarray
+    frequencies: np.ndarray
+
+    def plot(self, fs=1.0, integral_start=1e-6, integral_end=0.5, integrate=False):
+        """-> (sqrt of the integral over [integral_start, integral_end], points [n, 2] float64)"""
+        p = np.ascontiguousarray(self.psd, np.float32)
+        f = np.ascontiguousarray(self.frequencies, np.float32)
+        n = min(p.size, f.size)
+        o = L.PlotOptsC(fs, integral_start, integral_end, int(integrate))
+        xy = np.zeros((max(n, 1), 2), np.float64)
+        integ = C.c_float()
+        npts = C.c_size_t(xy.shape[0])
+        L.check(L.lib().sspsd_trace_plot(C.byref(o), p.ctypes.data, f.ctypes.data, n, C.byref(integ), xy.ctypes.data,
+                                         C.byref(npts)))
+        return integ.value, xy[:npts.value].copy()
 
 
 class SourceKind(enum.IntEnum):

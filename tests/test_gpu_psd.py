@@ -19,12 +19,15 @@ def sp():
     return m
 
 
-DC_RTOL = 1e-2  # bins 0 and 1 under Mean/Span detrend: what is left after subtracting the offset is set by
-#                 the rounding of that offset; the oracle sums sequentially in f32 like the reference
-#                 (src/psd.rs:100,104), the GPU sums as a tree, so the two agree only to ~N*eps*DC/sigma
+DC_RTOL = 1e-2  # bins 0 and 1 under Mean/Span detrend when no f64 truth is at hand (mid-stream option changes):
+#                 what is left after subtracting the offset is set by the rounding of that offset; the oracle
+#                 sums sequentially in f32 like the reference (src/psd.rs:100,104), the GPU sums as a tree, so
+#                 the two agree only to ~N*eps*DC/sigma.  Wherever the float64 model can follow the run the
+#                 statement is instead: the device is at least as close to the TRUTH on those bins as the
+#                 reference's own f32 arithmetic, |gpu - f64| <= |oracle - f64| + 1e-4 * median(row).
 
 
-def assert_bins_close(got, want, what="", loose_head=0):
+def assert_bins_close(got, want, what="", loose_head=0, truth=None):
     got = np.asarray(got, np.float64)
     want = np.asarray(want, np.float64)
     assert got.shape == want.shape, what
@@ -34,9 +37,33 @@ def assert_bins_close(got, want, what="", loose_head=0):
     err = np.abs(got - want) - floor
     rel = err / np.maximum(np.abs(want), 1e-300)
     if loose_head:
-        assert np.max(rel[:loose_head]) <= DC_RTOL, "%s: DC bins rel err %.3g" % (what, np.max(rel[:loose_head]))
+        if truth is not None:
+            truth = np.asarray(truth, np.float64)
+            assert truth.shape == want.shape, what
+            dg = np.abs(got[:loose_head] - truth[:loose_head])
+            do = np.abs(want[:loose_head] - truth[:loose_head])
+            eps = RTOL * np.median(np.abs(truth))
+            assert np.all(dg <= do + eps), "%s: DC bins: |gpu - f64| = %s > |oracle - f64| = %s + %.3g" % (
+                what, dg, do, eps)
+        else:
+            assert np.max(rel[:loose_head]) <= DC_RTOL, "%s: DC bins rel err %.3g" % (what, np.max(rel[:loose_head]))
         rel = rel[loose_head:]
     assert rel.size == 0 or np.max(rel) <= RTOL, "%s: max rel err %.3g" % (what, np.max(rel))
+
+
+def merged_truth(c64, breaks, n):
+    """PsdCascade::psd (src/psd.rs:479-543) evaluated on the float64 model's rows with the given breaks."""
+    out = []
+    for b in breaks:
+        if not b.include:
+            continue
+        stage = 0
+        while 8 ** stage < b.decimation:
+            stage += 1
+        row, cnt, _, _ = c64.stage(stage)
+        gain = (n // 2) * cnt * 1.5 * 0.25
+        out.append(row[b.bins.start:b.bins.stop] / (gain * b.decimation))
+    return np.concatenate(out) if out else np.zeros(0)
 
 
 def breaks_tuple(b):
@@ -69,7 +96,38 @@ def test_detrend_modes(sp, oracle, n, det):
     o.set_detrend(det)
     g.process(x)
     o.process(x)
-    assert_bins_close(g.spectrum(), o.spectrum(), "detrend %d" % det, loose_head=2 if det >= 2 else 0)
+    t = oracle.CascadeF64(n, detrend=det, max_stages=1)
+    t.process(x)
+    assert_bins_close(g.spectrum(), o.spectrum(), "detrend %d" % det, loose_head=2 if det >= 2 else 0,
+                      truth=t.stage(0)[0])
+    # and the whole row against the truth itself
+    assert_bins_close(g.spectrum(), t.stage(0)[0], "detrend %d vs f64" % det, loose_head=2 if det >= 2 else 0,
+                      truth=t.stage(0)[0])
+
+
+@pytest.mark.parametrize("n", [2048, 8192])
+def test_span_detrend_device_is_the_accurate_side(sp, oracle, n):
+    """DESIGN.md section 4 claims that under Detrend::Span the reference's sequential `offset += slope`
+    (src/psd.rs:98-101) is the noisier side of a GPU-vs-restatement difference.  Shown here against the float64
+    model on single segments (the worst case: no averaging): the device stays within 1e-4 of the truth on every
+    bin from 2 on, and is nowhere further from it than the f32 restatement is (plus 1e-4 of the median bin)."""
+    worst_o = 0.0
+    for seed in range(4):
+        x = uniform_noise(n, 900 + seed) + np.float32(3.0) + np.linspace(0, 7, n, dtype=np.float32)
+        g = sp.Psd(n)
+        g.set_detrend(sp.Detrend.SPAN)
+        o = oracle.Stage(n)
+        o.set_detrend(2)
+        t = oracle.CascadeF64(n, detrend=2, max_stages=1)
+        g.process(x); o.process(x); t.process(x)
+        truth = t.stage(0)[0]
+        med = np.median(truth)
+        dg = np.abs(g.spectrum().astype(np.float64) - truth)
+        do = np.abs(o.spectrum().astype(np.float64) - truth)
+        assert np.all(dg[2:] <= RTOL * np.maximum(truth[2:], AFLOOR * med) + AFLOOR * med), np.max(dg[2:] / truth[2:])
+        assert np.all(dg <= do + RTOL * med)
+        worst_o = max(worst_o, float(np.max(do[2:] / np.maximum(truth[2:], AFLOOR * med))))
+    print("f32 restatement vs f64 under Span, N=%d: %.3g" % (n, worst_o))
 
 
 def test_detrend_linear_is_unimplemented(sp):
@@ -138,7 +196,9 @@ def test_cascade_matches_oracle_ragged_host_and_device(sp, oracle, n, det, hbf):
     po, bo = o.psd()
     assert [breaks_tuple(k) for k in b] == [k.as_tuple() for k in bo]
     loose = 2 if det >= 2 else 0
-    assert_bins_close(p, po, "cascade n=%d" % n, loose_head=loose)
+    t = oracle.CascadeF64(n, hbf=hbf, detrend=det)
+    t.process(x)
+    assert_bins_close(p, po, "cascade n=%d" % n, loose_head=loose, truth=merged_truth(t, b, n))
     np.testing.assert_array_equal(sp.Break.frequencies(b), oracle.break_frequencies(bo))
     # every stage on its own, all bins, all merge options
     pk, bk = g.psd(sp.MergeOpts(keep_overlap=True, min_count=0, keep_transition_band=True))
@@ -147,7 +207,8 @@ def test_cascade_matches_oracle_ragged_host_and_device(sp, oracle, n, det, hbf):
     for bi in bk:
         if bi.count:
             sl = slice(bi.start, bi.start + len(bi.bins))
-            assert_bins_close(pk[sl], pok[sl], "stage dec=%d" % bi.decimation, loose_head=loose)
+            assert_bins_close(pk[sl], pok[sl], "stage dec=%d" % bi.decimation, loose_head=loose,
+                              truth=merged_truth(t, [bi], n))
 
 
 def test_cascade_ewma_and_option_changes(sp, oracle):
