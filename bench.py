@@ -6,7 +6,10 @@ PSD cascade; % of HBM roofline).
 
 Workload (config.workload): BASELINE.json configs[1] -- default PsdCascade (N=4096 Hann, 50 % overlap,
 divide-by-8 half-band cascade per stage) over one second of a 200 MS/s synthetic raw f32 stream.
-A step = one pass of the whole cascade over 200e6 samples + the psd() readout.  With N GPUs every
+A step = one pass of the whole cascade over 200e6 samples.  `value` times K back-to-back steps plus ONE
+psd() readout at the end ("process + final psd() readout, steady state"; the reference's GUI
+reads out at frame rate, not per batch); `value_readout_every_step` is the same loop with a psd() readout
+after every step, `sustained_2s` the same loop run for at least two seconds.  With N GPUs every
 rank runs its own channel of the same shape (channels are independent cascades, reference
 src/bin/psd.rs:174-182): weak scaling, no data-path collective, one NCCL gather of the merged
 spectra at readout.
@@ -38,6 +41,17 @@ TRAFFIC_BYTES_PER_SAMPLE = (270.938624e6 + 3.97184e6) / (1 << 26)
 # 2^26 samples): the roof that actually bounds it -- explanatory, next to the contract's HBM roofline
 FP32_LANE_OPS_PER_SAMPLE = (2 * 43.41e6 + 15.44e6) * 32 / (1 << 26)
 WORKLOAD = "PsdCascade N=4096 Hann 50% overlap, div-8 half-band per stage, 200e6-sample f32 stream per channel"
+STAGE_COUNTS_PER_STEP = [97655, 12205, 1524, 189, 22, 1, 0]  # closed form for one 200e6-sample step
+PARITY_NOTE = ("idsp 0.20 hbf (taps, FIR phase, hbf_dec_response_length) is not on disk: decimator parity is against the "
+               "restatement in oracle/, unpinned against the real crate; the CPU arm is that restatement (kind=port), not "
+               "rustfft/idsp")
+
+
+def config_dict(n):
+    """Identical in both arms (the driver compares them): describes the workload only, no measured values."""
+    return {"workload": WORKLOAD, "n_fft": N_FFT, "channels": n, "samples_per_step_per_gpu": SAMPLES_PER_STEP,
+            "stage_counts_per_step": STAGE_COUNTS_PER_STEP,
+            "readout": "one psd() readout at the end of the timed region"}
 
 
 def peaks():
@@ -52,8 +66,9 @@ class ClockSampler:
     """SM clock + throttle reasons sampled DURING the timed region (NVML polled from a thread every
     ~2 ms; the timed region is tens of milliseconds, too short for `nvidia-smi -lms`)."""
 
-    def __init__(self, index):
+    def __init__(self, index, power=False):
         self.index = index
+        self.power = [] if power else None
         self.samples = []
         self.reasons = set()
         self.max_mhz = None
@@ -75,6 +90,8 @@ class ClockSampler:
                 nv.nvmlDeviceGetCurrentClocksThrottleReasons
             while not self._stop.is_set():
                 self.samples.append(float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)))
+                if self.power is not None:
+                    self.power.append(nv.nvmlDeviceGetPowerUsage(h) / 1000.0)
                 r = get_reasons(h)
                 for k, bit in names.items():
                     if r & bit:
@@ -96,44 +113,60 @@ class ClockSampler:
         if not self.samples:
             return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": ["no samples: %s" % self._err]}
         sm = sorted(self.samples)
-        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
-                "samples": len(sm)}
+        out = {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
+               "samples": len(sm)}
+        if self.power:
+            out["sm_mhz_min"] = sm[0]
+            out["power_w_max"] = max(self.power)
+            out["power_w_median"] = sorted(self.power)[len(self.power) // 2]
+        return out
 
 
-def cpu_baseline(seconds_target=12.0, threads=1, n_fft=N_FFT):
-    """Time the CPU restatement (oracle) on this host: `threads` independent channels, one per thread."""
+def _cpu_feed(cas, block, samples):
+    """feed exactly `samples` samples by cycling over a 2^22-sample block (ctypes releases the GIL)"""
+    pos = 0
+    while pos < samples:
+        n = min(block.size, samples - pos)
+        cas.process(block[:n])
+        pos += n
+
+
+def _cpu_block():
     import numpy as np
+    rng = np.random.default_rng(0x7654321)
+    return ((rng.random(1 << 22, dtype=np.float32) - np.float32(0.5)) * np.float32(12 ** 0.5)).astype(np.float32)
+
+
+def cpu_run(samples_per_step, steps, warmup, threads=1, n_fft=N_FFT):
+    """The CPU restatement (oracle) on this host: `threads` independent channels, one cascade per thread, each
+    processing steps x samples_per_step samples + one psd() readout -- the same loop the GPU arm times."""
     from oracle import binding as orc
     orc.lib()
-    rng = np.random.default_rng(0x7654321)
-    block = ((rng.random(1 << 22, dtype=np.float32) - np.float32(0.5)) * np.float32(12 ** 0.5)).astype(np.float32)
+    block = _cpu_block()
     cas = [orc.Cascade(n_fft, orc.HBF_140) for _ in range(threads)]
-    for c in cas:
-        c.process(block[:1 << 20])
-    # calibrate, then run a bounded sample
-    t0 = time.perf_counter()
-    cas[0].process(block)
-    per_block = time.perf_counter() - t0
-    reps = max(1, int(seconds_target / max(per_block, 1e-3)))
-    done = [0] * threads
 
-    def work(i):
-        for _ in range(reps):
-            cas[i].process(block)  # ctypes releases the GIL for the duration of the call
-            done[i] += block.size
+    def work(i, k):
+        for _ in range(k):
+            _cpu_feed(cas[i], block, samples_per_step)
+        cas[i].psd()
 
-    ths = [threading.Thread(target=work, args=(i,)) for i in range(threads)]
-    t0 = time.perf_counter()
-    for t in ths:
-        t.start()
-    for t in ths:
-        t.join()
-    dt = time.perf_counter() - t0
-    total = sum(done)
+    def run(k):
+        ths = [threading.Thread(target=work, args=(i, k)) for i in range(threads)]
+        t0 = time.perf_counter()
+        for t in ths:
+            t.start()
+        for t in ths:
+            t.join()
+        return time.perf_counter() - t0
+
+    if warmup:
+        run(warmup)
+    dt = run(steps)
+    total = threads * steps * samples_per_step
     return {"value": total / dt / 1e6, "unit": "MS/s", "cores": threads, "kind": "port",
-            "sample": "%d channel(s) x %d samples (N=%d cascade, CPU restatement of src/psd.rs, gcc -O3 -march=native; "
-                      "the Rust reference cannot be built offline; it publishes >200 MS/s/core at N=512)"
-                      % (threads, total // threads, n_fft), "seconds": dt}
+            "sample": "%d channel(s) x %d step(s) x %d samples (N=%d cascade, CPU restatement of src/psd.rs, gcc -O3 "
+                      "-march=native; the Rust reference cannot be built offline; it publishes >200 MS/s/core at N=512)"
+                      % (threads, steps, samples_per_step, n_fft), "seconds": dt}
 
 
 def run_reference(args):
@@ -143,21 +176,14 @@ def run_reference(args):
     n = max(1, args.gpus)
     # the reference runs one cascade per trace on one receiver thread; with N channels it can use N threads
     threads = min(n, os.cpu_count() or 1)
-    vals = []
-    for _ in range(args.warmup):
-        cpu_baseline(1.0, threads)
-    t_all = time.perf_counter()
-    for _ in range(args.steps):
-        vals.append(cpu_baseline(max(2.0, 20.0 / args.steps), threads))
-    wall = time.perf_counter() - t_all
-    v = sum(x["value"] for x in vals) / len(vals)
-    cb = dict(vals[-1])
-    cb["value"] = v
+    cb = cpu_run(SAMPLES_PER_STEP, args.steps, min(args.warmup, 1), threads)
+    v = cb["value"] * n / threads  # (threads == n unless the host has fewer cores than channels)
+    cfg = config_dict(n)
     out = {"impl": "reference", "metric": "sustained MS/s through full PSD cascade", "value": v, "unit": "MS/s",
            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
-           "ms_per_step": wall / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-           "dtype": "f32", "data": "synthetic", "config": {"workload": WORKLOAD, "channels": n},
-           "cpu_baseline": cb,
+           "ms_per_step": cb["seconds"] / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
+           "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": cfg,
+           "cpu_baseline": cb, "parity_note": PARITY_NOTE,
            "e2e": {"value": v, "unit": "MS/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(out))
 
@@ -252,6 +278,36 @@ def run_ours(args):
     value = world * SAMPLES_PER_STEP * args.steps / (ms * 1e-3) / 1e6
     value_rs = world * SAMPLES_PER_STEP * args.steps / (ms_rs * 1e-3) / 1e6
 
+    # ---- sustained: the same loop for >= 2 s of device time, clocks + power sampled throughout ----
+    def sustained(seconds=2.0):
+        c = PsdCascade(N_FFT, device=local, stream=stream.cuda_stream or 1)
+        for _ in range(3):
+            c.process(x)
+        c.psd(MergeOpts())
+        barrier()
+        k = max(args.steps, int(seconds / (ms / args.steps * 1e-3)) + 1)
+        sampler = ClockSampler(local, power=True)
+        sampler.start()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for i in range(k):
+            c.process(x)
+            if i % 64 == 63:
+                c.sync()  # bound the launch queue; a sync every 64 steps (56 ms) costs nothing measurable
+        p_, b_ = c.psd(MergeOpts())
+        gather_readout(p_)
+        e1.record(stream)
+        barrier()
+        ck = sampler.stop()
+        t = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        t = float(t.item())
+        return {"value": world * SAMPLES_PER_STEP * k / (t * 1e-3) / 1e6, "unit": "MS/s", "steps": k, "seconds": t * 1e-3,
+                "clocks": ck}
+
+    sus = sustained()
+
     # ---- end-to-end run: host pinned input, H2D inside the timed region, spectra read back ----
     c2 = PsdCascade(N_FFT, device=local, stream=stream.cuda_stream or 1)
     e2e_steps = max(1, min(args.steps, 5))
@@ -279,24 +335,45 @@ def run_ours(args):
             "share_of_step": k_ms / ms,
             "other_kernels_ms": {k: v[0] for k, v in prof.items() if k != "psd_stage0"},
             "whole_step_frac": BYTES_PER_SAMPLE * SAMPLES_PER_STEP * args.steps / (ms * 1e-3) / 1e9 / peak}
-    cb = cpu_baseline(12.0, 1) if world == 1 else None
     d2h = sum(len(k.bins) for k in b if k.include) * 4
     out = {"metric": "sustained MS/s through full PSD cascade", "value": value, "unit": "MS/s", "n_gpus": world,
            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-           "config": {"workload": WORKLOAD, "channels": world, "samples_per_step_per_gpu": SAMPLES_PER_STEP,
-                      "stage_counts_per_step": [k.count for k in reversed(b)][:8],
-                      "cache": "inputs (800 MB per step) larger than the 126 MB L2",
-                      "readout": "one psd() readout at the end of the timed region",
-                      "value_readout_every_step": value_rs},
-           "roofline": roof, "clocks": clocks, "gpu_launches": int(launches),
+           "config": config_dict(world),
+           "cache": "inputs (800 MB per step) larger than the 126 MB L2",
+           "value_readout_every_step": value_rs, "sustained_2s": sus,
+           "roofline": roof, "clocks": clocks, "gpu_launches": int(launches), "parity_note": PARITY_NOTE,
            "e2e": {"value": e2e_value, "unit": "MS/s", "h2d_bytes_per_step": SAMPLES_PER_STEP * 4 * world,
                    "d2h_bytes_per_step": d2h * world, "steps": e2e_steps, "ms_per_step": ms2 / e2e_steps}}
-    if cb is not None:
-        out["cpu_baseline"] = cb
+    if world == 1:
+        # CPU arm beside it: one bounded step of the same workload on one host core, and the reference's own
+        # in-tree size N=512 next to its published ">200 MS/s per core" (README.md:11, src/psd.rs:550)
+        out["cpu_baseline"] = cpu_run(SAMPLES_PER_STEP, 8, 1, 1)
+        n512 = cpu_run(100_000_000, 3, 1, 1, n_fft=512)
+        n512["published"] = ">200 MS/s on one (Skylake) core at N=512 (reference README.md:11, src/psd.rs:550)"
+        out["cpu_baseline_n512"] = n512
+        out["e2e_small_calls"] = small_calls()
     print(json.dumps(out))
     if world > 1:
         dist.destroy_process_group()
+
+
+def small_calls():
+    """The reference's call pattern through the C ABI from plain C: 4096-sample pageable slices
+    (reference src/source.rs:116, src/bin/psd.rs:170-183); tools/small_calls.c"""
+    import subprocess
+    exe = os.path.join(ROOT, "tools", "_build", "small_calls")
+    if not os.path.exists(exe):
+        return {"unavailable": "tools/_build/small_calls not built (run __graft_entry__.build())"}
+    res = {}
+    for name, argv in (("n4096_block4096", ["4096", "4096", "400000000"]), ("n512_block4096", ["512", "4096", "400000000"]),
+                       ("n512_block176", ["512", "176", "100000000"])):
+        try:
+            r = subprocess.run([exe] + argv, capture_output=True, text=True, timeout=120)
+            res[name] = json.loads(r.stdout.strip().splitlines()[-1]) if r.returncode == 0 else {"error": r.stderr[-300:]}
+        except Exception as e:  # noqa: BLE001
+            res[name] = {"error": repr(e)}
+    return res
 
 
 def main():

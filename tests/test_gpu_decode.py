@@ -148,3 +148,40 @@ def test_low_rate_formats_into_cascades(sp, oracle, fmt, batches):
         assert [k.count for k in b] == [k.count for k in bo]
         scale = np.median(po)
         assert np.max((np.abs(p - po) - 1e-5 * scale) / np.maximum(po, 1e-300)) < 1e-4
+
+
+def test_eshort_retry_accounts_the_batch_once(sp, oracle):
+    """Capacity-in / length-out retry (include/sspsd.h): a too small host trace buffer returns ESHORT with the
+    needed length and must leave `Loss` untouched, so that the retried call counts the batch exactly once
+    (the first version advanced received/dropped/seq before the capacity check)."""
+    import ctypes as C
+
+    from stabilizer_stream_b200 import _lib as L
+    n_frames, batches = 50, 22
+    data, flen, stride, hdrs = make_frames(1, batches, n_frames, seed=77, drop_every=7, start_seq=0xFFFFFF00)
+    st, nf, lo, want = oracle_decode_stream(oracle, data, flen, stride, n_frames)
+    dec = sp.FrameDecoder()
+    loss = sp.Loss()
+    loss.update(0xFFFFFF00 - 3 * batches, batches)   # some history, so `dropped` moves on the first frame
+    before = (loss.received, loss.dropped, loss.seq)
+    buf = np.frombuffer(data, np.uint8)
+    need = n_frames * batches * 8
+    small = [np.zeros(need - 1, np.float32) for _ in range(4)]
+    ptrs = (C.c_void_p * 4)(*[t.ctypes.data for t in small])
+    info = L.DecodeInfoC()
+    rc = L.lib().sspsd_decode_frames(dec._h, buf.ctypes.data, n_frames, flen, stride, L.MEM_HOST, C.byref(loss.c), ptrs,
+                                     need - 1, L.MEM_HOST, C.byref(info))
+    assert rc == L.ESHORT and info.samples_per_trace == need and info.frames_ok == 0
+    assert (loss.received, loss.dropped, loss.seq) == before
+    big = [np.zeros(need, np.float32) for _ in range(4)]
+    ptrs = (C.c_void_p * 4)(*[t.ctypes.data for t in big])
+    rc = L.lib().sspsd_decode_frames(dec._h, buf.ctypes.data, n_frames, flen, stride, L.MEM_HOST, C.byref(loss.c), ptrs,
+                                     need, L.MEM_HOST, C.byref(info))
+    assert rc == L.OK and info.frames_ok == n_frames
+    ref = oracle.Loss()
+    ref.update(0xFFFFFF00 - 3 * batches, batches)
+    for seq, b in hdrs:
+        ref.update(seq, b)
+    assert (loss.received, loss.dropped, loss.seq) == (ref.received, ref.dropped, ref.seq)
+    for g, w in zip(big, want):
+        assert np.array_equal(g.view(np.uint32), np.concatenate(w).view(np.uint32))

@@ -61,8 +61,11 @@ def check_rows(name, meta, rows_gpu, z, report):
         e64 = rel_err(g, r64)
         e32 = rel_err(g, r32)
         drift = float(meta["oracle_f32_drift_vs_f64"][i])
+        raw64 = np.abs(g - r64) / np.maximum(r64, 1e-300)
         rec = dict(stage=i, count=int(counts[i]), max_rel_vs_f64=float(np.max(e64[head:])),
-                   max_rel_vs_oracle_f32=float(np.max(e32[head:])), oracle_f32_drift_vs_f64=drift)
+                   max_rel_vs_oracle_f32=float(np.max(e32[head:])), oracle_f32_drift_vs_f64=drift,
+                   # without the absolute floor of 1e-5 of the median bin: raw per-bin relative error
+                   raw_max_rel_vs_f64=float(np.max(raw64[head:])), raw_median_rel_vs_f64=float(np.median(raw64[head:])))
         if head:
             med = float(np.median(r64))
             dg = np.abs(g[:head] - r64[:head])

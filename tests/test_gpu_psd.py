@@ -100,9 +100,10 @@ def test_detrend_modes(sp, oracle, n, det):
     t.process(x)
     assert_bins_close(g.spectrum(), o.spectrum(), "detrend %d" % det, loose_head=2 if det >= 2 else 0,
                       truth=t.stage(0)[0])
-    # and the whole row against the truth itself
-    assert_bins_close(g.spectrum(), t.stage(0)[0], "detrend %d vs f64" % det, loose_head=2 if det >= 2 else 0,
-                      truth=t.stage(0)[0])
+    # and the row against the truth itself (bins 0-1 under Mean/Span are cancellation residue for any f32
+    # evaluation: covered by the statement above)
+    head = 2 if det >= 2 else 0
+    assert_bins_close(g.spectrum()[head:], t.stage(0)[0][head:], "detrend %d vs f64" % det)
 
 
 @pytest.mark.parametrize("n", [2048, 8192])
@@ -348,3 +349,39 @@ def test_rect_window_stage_with_decimation(sp, oracle):
         np.testing.assert_allclose(yg, yo, atol=2e-5)
         assert_bins_close(g.spectrum(), o.spectrum(), "rect %d" % n)
         np.testing.assert_array_equal(g.buf(), o.buf())
+
+
+def test_device_tensors_on_other_torch_streams(sp, oracle):
+    """a handle created BEFORE torch touched CUDA used to get a private stream, and
+    process() read caller tensors on it with no ordering against the torch stream that produced them; a handle
+    is also legitimately used under `with torch.cuda.stream(s)` later.  The mirror now makes the handle's stream
+    wait for torch's current stream and marks the tensor (record_stream), so temporaries may be dropped right
+    after the call.  Exercised with temporaries produced on side streams and an allocator under churn."""
+    import torch
+    n = 512
+    x = uniform_noise(400 * n, 31)
+    g = sp.PsdCascade(n)
+    o = oracle.Cascade(n, 1)
+    o.process(x)
+    xd = torch.from_numpy(x).cuda()
+    side = [torch.cuda.Stream(), torch.cuda.Stream()]
+    block = 37 * n + 5
+    pos = 0
+    i = 0
+    while pos < x.size:
+        s = side[i % 2]
+        s.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(s):
+            # a temporary made on the side stream (non-contiguous view -> .contiguous() copy inside process)
+            tmp = torch.stack([xd[pos:pos + block], xd[pos:pos + block]], dim=1) * 1.0
+            g.process(tmp[:, 0])
+            del tmp
+            # allocator churn on the same stream: would recycle the block if it were not recorded
+            junk = torch.full((block * 2,), float("nan"), device="cuda")
+            del junk
+        pos += block
+        i += 1
+    p, b = g.psd()
+    po, bo = o.psd()
+    assert [breaks_tuple(k) for k in b] == [k.as_tuple() for k in bo]
+    assert_bins_close(p, po, "side streams")
