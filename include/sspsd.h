@@ -84,6 +84,10 @@ typedef struct {
     uint64_t host_stage; /* host-pointer process() calls are staged in pinned memory and launched once
                             this many samples are pending (0 = default 1<<22); psd()/set_*()/flush() launch
                             whatever is staged */
+    uint64_t deep_defer; /* stages >= 1 run once this many samples are pending at stage 1 (>> 3 per deeper stage), so
+                            that their kernels get full-size grids instead of ~20 small dependent launches per batch
+                            (fewer launches; measured neutral for throughput); every call that observes state runs
+                            what is pending first, results do not depend on it (0 or 1 = run them with every batch) */
 } sspsd_config;
 
 /* AvgOpts, src/psd.rs:360-376 */

@@ -15,6 +15,7 @@ struct Config {
     stream: *mut core::ffi::c_void,
     max_batch: u64,
     host_stage: u64,
+    deep_defer: u64,
 }
 #[repr(C)]
 #[derive(Clone, Copy)]

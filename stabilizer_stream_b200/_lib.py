@@ -21,7 +21,8 @@ STATUS_NAMES = {0: "OK", 1: "EINVAL", 2: "EUNIMPLEMENTED", 3: "ECUDA", 4: "ENOME
 
 class Config(C.Structure):
     _fields_ = [("n_fft", C.c_uint32), ("window", C.c_int32), ("hbf", C.c_int32), ("device", C.c_int32),
-                ("stream", C.c_void_p), ("max_batch", C.c_uint64), ("host_stage", C.c_uint64)]
+                ("stream", C.c_void_p), ("max_batch", C.c_uint64), ("host_stage", C.c_uint64),
+                ("deep_defer", C.c_uint64)]
 
 
 class AvgOptsC(C.Structure):

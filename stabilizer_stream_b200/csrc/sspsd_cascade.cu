@@ -139,6 +139,25 @@ int launch_decim_t(const DecimParams& p, int grid, cudaStream_t s)
     return cuda_ok(cudaGetLastError(), "decim8_kernel launch") ? SSPSD_OK : SSPSD_ECUDA;
 }
 
+// persistent TMA-staged decimator (default; SSPSD_K3=tiled selects the first-generation kernel)
+template <int MA, int MB, int MC, int PRESET, int OB, int CTAS>
+int launch_decim_tma_t(const DecimParams& p, long long n_out, int num_sms, cudaStream_t s)
+{
+    const int ntiles = (int)((n_out + OB - 1) / OB);
+    const int grid = std::min(ntiles, num_sms * CTAS);
+    decim8_tma_kernel<MA, MB, MC, PRESET, OB, CTAS><<<grid, DEC_NT, decim_tma_smem_bytes<MA, MB, MC, OB>(), s>>>(p, ntiles);
+    return cuda_ok(cudaGetLastError(), "decim8_tma_kernel launch") ? SSPSD_OK : SSPSD_ECUDA;
+}
+
+template <int MA, int MB, int MC, int PRESET, int OB, int CTAS>
+int launch_decim_async_t(const DecimParams& p, long long n_out, int num_sms, cudaStream_t s)
+{
+    const int ntiles = (int)((n_out + OB - 1) / OB);
+    const int grid = std::min(ntiles, num_sms * CTAS);
+    decim8_async_kernel<MA, MB, MC, PRESET, OB, CTAS><<<grid, DEC_NT, decim_async_smem_bytes<MA, MB, MC, OB>(), s>>>(p, ntiles);
+    return cuda_ok(cudaGetLastError(), "decim8_async_kernel launch") ? SSPSD_OK : SSPSD_ECUDA;
+}
+
 int decim_halo(int preset)
 {
     return preset == SSPSD_HBF_98 ? DecGeom<3, 6, 15>::HALO : DecGeom<5, 10, 23>::HALO;
@@ -171,6 +190,22 @@ int upload_taps_once(int device)
                                     (int)(DecGeom<5, 10, 23>::SMEM_FLOATS * sizeof(float))));
     SSPSD_CUDA(cudaFuncSetAttribute(decim8_kernel<3, 6, 15, SSPSD_HBF_98>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                     (int)(DecGeom<3, 6, 15>::SMEM_FLOATS * sizeof(float))));
+    SSPSD_CUDA(cudaFuncSetAttribute(decim8_async_kernel<5, 10, 23, SSPSD_HBF_140, 960, 2>,
+                                    cudaFuncAttributeMaxDynamicSharedMemorySize, (int)decim_async_smem_bytes<5, 10, 23, 960>()));
+    SSPSD_CUDA(cudaFuncSetAttribute(decim8_async_kernel<5, 10, 23, SSPSD_HBF_140, 640, 3>,
+                                    cudaFuncAttributeMaxDynamicSharedMemorySize, (int)decim_async_smem_bytes<5, 10, 23, 640>()));
+    SSPSD_CUDA(cudaFuncSetAttribute(decim8_async_kernel<3, 6, 15, SSPSD_HBF_98, 960, 2>,
+                                    cudaFuncAttributeMaxDynamicSharedMemorySize, (int)decim_async_smem_bytes<3, 6, 15, 960>()));
+    SSPSD_CUDA(cudaFuncSetAttribute(decim8_async_kernel<3, 6, 15, SSPSD_HBF_98, 640, 3>,
+                                    cudaFuncAttributeMaxDynamicSharedMemorySize, (int)decim_async_smem_bytes<3, 6, 15, 640>()));
+    SSPSD_CUDA(cudaFuncSetAttribute(decim8_tma_kernel<5, 10, 23, SSPSD_HBF_140, 960, 2>,
+                                    cudaFuncAttributeMaxDynamicSharedMemorySize, (int)decim_tma_smem_bytes<5, 10, 23, 960>()));
+    SSPSD_CUDA(cudaFuncSetAttribute(decim8_tma_kernel<5, 10, 23, SSPSD_HBF_140, 640, 3>,
+                                    cudaFuncAttributeMaxDynamicSharedMemorySize, (int)decim_tma_smem_bytes<5, 10, 23, 640>()));
+    SSPSD_CUDA(cudaFuncSetAttribute(decim8_tma_kernel<3, 6, 15, SSPSD_HBF_98, 960, 2>,
+                                    cudaFuncAttributeMaxDynamicSharedMemorySize, (int)decim_tma_smem_bytes<3, 6, 15, 960>()));
+    SSPSD_CUDA(cudaFuncSetAttribute(decim8_tma_kernel<3, 6, 15, SSPSD_HBF_98, 640, 3>,
+                                    cudaFuncAttributeMaxDynamicSharedMemorySize, (int)decim_tma_smem_bytes<3, 6, 15, 640>()));
     if (device < 64)
         done[device] = true;
     return SSPSD_OK;
@@ -354,7 +389,18 @@ int Cascade::init(const sspsd_config& cfg, uint32_t max_stages)
     }
     int rc = upload_taps_once(cfg.device);
     if (rc) return rc;
+    // measured (profiles/r02_variants*.jsonl): letting the deep stages' input pile up makes their kernels
+    // efficient (0.53 -> 0.20 ms of event time per step) but does not shorten the step, because their many
+    // small launches already hide inside the next batch's stage-0 kernels; so it is off unless asked for
+    defer_ = cfg_.deep_defer ? cfg_.deep_defer : 1;
+    if (const char* e = getenv("SSPSD_DEFER")) defer_ = strtoull(e, nullptr, 0);
     k2_variant_ = k2_variant_from_env();
+    {
+        // K3 variant (A/B switch): SSPSD_K3 = tiled | tma960 | tma640 | async960 | async640
+        const char* e = getenv("SSPSD_K3");
+        std::string m = e ? e : "tma960";
+        k3_variant_ = m == "tiled" ? 0 : m == "tma960" ? 1 : m == "tma640" ? 2 : m == "async640" ? 4 : 3;
+    }
     rc = prepare_stage((int)log2n_, k2_variant_ >= 1, (int)hop_, &tmax_, &nt_);
     if (rc) return rc;
 
@@ -434,21 +480,24 @@ int Cascade::add_stage()
     return SSPSD_OK;
 }
 
-int Cascade::ensure_fresh(StageState& st, size_t need)
+int Cascade::ensure_fresh(StageState& st, size_t need, size_t reserve)
 {
     if (need <= st.fresh_cap)
         return SSPSD_OK;
-    // earlier batches may still be reading the old buffers; the head of fresh[fb] (copies of the carry
-    // tail, written by the previous batch's carry_copy_kernel) has to survive the reallocation
+    // earlier batches may still be reading the old buffers; the head of fresh[fb] (copies of the carry tail,
+    // written by the previous batch's carry_copy_kernel) and the samples accumulated there since the stage last
+    // ran (deferred deep stages) have to survive the reallocation
     SSPSD_CUDA(cudaStreamSynchronize(stream_));
     if (deep_stream_) SSPSD_CUDA(cudaStreamSynchronize(deep_stream_));
     if (psd_stream_) SSPSD_CUDA(cudaStreamSynchronize(psd_stream_));
-    size_t cap = std::max(need + 64, st.fresh_cap * 2);
+    const size_t keep = std::min<size_t>(st.fresh_cap, 4 + (size_t)st.pending_in);
+    size_t cap = std::max(std::max(need + 64, st.fresh_cap * 2), need + reserve);
     for (int b = 0; b < 2; ++b) {
         float* nb = nullptr;
         SSPSD_CUDA(cudaMalloc(&nb, cap * sizeof(float)));
         if (st.fresh[b]) {
-            SSPSD_CUDA(cudaMemcpy(nb, st.fresh[b], 4 * sizeof(float), cudaMemcpyDeviceToDevice));
+            SSPSD_CUDA(cudaMemcpy(nb, st.fresh[b], (b == st.fb ? keep : std::min<size_t>(4, st.fresh_cap)) * sizeof(float),
+                                  cudaMemcpyDeviceToDevice));
             SSPSD_CUDA(cudaFree(st.fresh[b]));
         }
         st.fresh[b] = nb;
@@ -534,8 +583,23 @@ int Cascade::launch_decim(size_t i, const StreamSrc& src, uint64_t m0, uint64_t 
     int grid = (int)((p.m1 - lo + DEC_OB - 1) / DEC_OB);
     cudaStream_t ss = stage_stream(i);
     prof_begin(i == 0 ? SSPSD_PROF_DECIM_STAGE0 : SSPSD_PROF_DECIM_DEEP, (uint64_t)(p.m1 - lo) * 8, ss);
-    int rc = cfg_.hbf == SSPSD_HBF_98 ? launch_decim_t<3, 6, 15, SSPSD_HBF_98>(p, grid, ss)
+    int rc;
+    if (k3_variant_ == 0) {
+        rc = cfg_.hbf == SSPSD_HBF_98 ? launch_decim_t<3, 6, 15, SSPSD_HBF_98>(p, grid, ss)
                                       : launch_decim_t<5, 10, 23, SSPSD_HBF_140>(p, grid, ss);
+    } else if (k3_variant_ == 1) {
+        rc = cfg_.hbf == SSPSD_HBF_98 ? launch_decim_tma_t<3, 6, 15, SSPSD_HBF_98, 960, 2>(p, p.m1 - lo, num_sms_, ss)
+                                      : launch_decim_tma_t<5, 10, 23, SSPSD_HBF_140, 960, 2>(p, p.m1 - lo, num_sms_, ss);
+    } else if (k3_variant_ == 2) {
+        rc = cfg_.hbf == SSPSD_HBF_98 ? launch_decim_tma_t<3, 6, 15, SSPSD_HBF_98, 640, 3>(p, p.m1 - lo, num_sms_, ss)
+                                      : launch_decim_tma_t<5, 10, 23, SSPSD_HBF_140, 640, 3>(p, p.m1 - lo, num_sms_, ss);
+    } else if (k3_variant_ == 3) {
+        rc = cfg_.hbf == SSPSD_HBF_98 ? launch_decim_async_t<3, 6, 15, SSPSD_HBF_98, 960, 2>(p, p.m1 - lo, num_sms_, ss)
+                                      : launch_decim_async_t<5, 10, 23, SSPSD_HBF_140, 960, 2>(p, p.m1 - lo, num_sms_, ss);
+    } else {
+        rc = cfg_.hbf == SSPSD_HBF_98 ? launch_decim_async_t<3, 6, 15, SSPSD_HBF_98, 640, 3>(p, p.m1 - lo, num_sms_, ss)
+                                      : launch_decim_async_t<5, 10, 23, SSPSD_HBF_140, 640, 3>(p, p.m1 - lo, num_sms_, ss);
+    }
     prof_end(ss);
     return rc;
 }
@@ -619,7 +683,6 @@ int Cascade::run_stage(size_t i, const float* fresh, long long split, uint64_t n
     const uint64_t D1 = decimated(st);
     uint64_t n_next = 0;
     long long nsplit = 0;
-    const float* nfresh = nullptr;
     if (D1 > D0) {
         const uint64_t m0 = D0 / 8, m1 = D1 / 8;
         const uint64_t em1 = m1 > (uint64_t)drain_ ? m1 - drain_ : 0;
@@ -663,7 +726,10 @@ int Cascade::run_stage(size_t i, const float* fresh, long long split, uint64_t n
                 }
                 StageState& nx = stages_[i + 1];
                 nsplit = floor4((long long)nx.L);
-                rc = ensure_fresh(nx, (size_t)((long long)em1 - nsplit));
+                // with large batches reserve the whole deferral window at once (a reallocation synchronises
+                // all streams and moves what has accumulated); small-batch callers grow by doubling instead
+                const uint64_t thr = defer_threshold(i + 1);
+                rc = ensure_fresh(nx, (size_t)((long long)em1 - nsplit), n_next >= thr / 16 ? (size_t)(thr + n_next) : 0);
                 if (rc) return rc;
                 const int b = nx.fb;
                 // the next stage may still be reading this buffer from two batches ago (other stream)
@@ -676,8 +742,8 @@ int Cascade::run_stage(size_t i, const float* fresh, long long split, uint64_t n
                 }
                 rc = launch_decim(i, src, m0, m1, nx.fresh[b], nsplit);
                 if (rc) return rc;
-                nfresh = nx.fresh[b];
                 stages_[i].emitted = em1;
+                nx.pending_in += n_next;
             }
         }
     }
@@ -718,14 +784,42 @@ int Cascade::run_stage(size_t i, const float* fresh, long long split, uint64_t n
             s2.fb ^= 1;
         }
     }
-    if (n_next > 0) {
-        if (i + 1 == deep_from_ && deep_stream_) {
-            // hand over to the deep stream: it may start once this stage's decimator has written its output
-            SSPSD_CUDA(cudaEventRecord(ev_stage0_, stream_));
-            SSPSD_CUDA(cudaStreamWaitEvent(deep_stream_, ev_stage0_, 0));
-            deep_dirty_ = true;
-        }
-        return run_stage(i + 1, nfresh, nsplit, n_next);
+    // The next stage runs once enough of its input has accumulated (see run_pending): with a 200e6-sample batch
+    // the stages >= 1 are ~20 small dependent launches that cost 0.27 ms when serialised for 1/7 of the work;
+    // letting their input pile up for a few batches gives them stage-0-sized grids.  Invisible to the caller:
+    // every call that observes state (psd, sync, set_*, clone, ...) runs what is pending first.
+    if (n_next > 0 && stages_[i + 1].pending_in >= defer_threshold(i + 1)) return run_pending(i + 1);
+    return SSPSD_OK;
+}
+
+uint64_t Cascade::defer_threshold(size_t j) const
+{
+    if (windowed_ || max_stages_ == 1 || defer_ <= 1 || j == 0) return 0;
+    const unsigned sh = (unsigned)(SSPSD_DEPTH * (j - 1));
+    return sh >= 63 ? 0 : (defer_ >> sh);
+}
+
+// run stage j over the samples the previous stage's decimator has accumulated in fresh[fb]
+int Cascade::run_pending(size_t j)
+{
+    StageState& st = stages_[j];
+    const uint64_t n = st.pending_in;
+    if (n == 0) return SSPSD_OK;
+    st.pending_in = 0;
+    if (j == deep_from_ && deep_stream_) {
+        // hand over to the deep stream: it may start once the decimator launches queued so far have run
+        SSPSD_CUDA(cudaEventRecord(ev_stage0_, stream_));
+        SSPSD_CUDA(cudaStreamWaitEvent(deep_stream_, ev_stage0_, 0));
+        deep_dirty_ = true;
+    }
+    return run_stage(j, st.fresh[st.fb], floor4((long long)st.L), n);
+}
+
+int Cascade::flush_deferred()
+{
+    for (size_t j = 1; j < stages_.size(); ++j) {
+        int rc = run_pending(j);  // may append to stage j + 1, which the loop reaches next
+        if (rc) return rc;
     }
     return SSPSD_OK;
 }
@@ -987,7 +1081,9 @@ int Cascade::flush()
 {
     DeviceGuard g(cfg_.device);
     if (!g.ok) return SSPSD_ECUDA;
-    return flush_staged();
+    int rc = flush_staged();
+    if (rc) return rc;
+    return flush_deferred();
 }
 
 int Cascade::sync()
@@ -995,6 +1091,8 @@ int Cascade::sync()
     DeviceGuard g(cfg_.device);
     if (!g.ok) return SSPSD_ECUDA;
     int rc = flush_staged();
+    if (rc) return rc;
+    rc = flush_deferred();
     if (rc) return rc;
     rc = join_streams();
     if (rc) return rc;
@@ -1212,7 +1310,9 @@ int Cascade::profile_read(sspsd_profile* out)
     if (!out) return SSPSD_EINVAL;
     DeviceGuard g(cfg_.device);
     if (!g.ok) return SSPSD_ECUDA;
-    int rcj = join_streams();
+    int rcj = flush_deferred();
+    if (rcj) return rcj;
+    rcj = join_streams();
     if (rcj) return rcj;
     SSPSD_CUDA(cudaStreamSynchronize(stream_));
     std::memset(out, 0, sizeof(*out));

@@ -47,6 +47,7 @@ struct StageState {
     float* fresh[2] = {nullptr, nullptr};
     int fb = 0;  // buffer the next incoming batch is written to
     size_t fresh_cap = 0;
+    uint64_t pending_in = 0;  // samples the previous stage's decimator has written to fresh[fb] since this stage last ran
     cudaEvent_t ev_read[2] = {nullptr, nullptr};  // recorded when this stage has finished reading fresh[b]
     bool ev_read_pending[2] = {false, false};
     // stages on the deep stream run their PSD kernel on a third stream beside the decimation chain:
@@ -105,7 +106,10 @@ private:
     // stream of stage i's PSD kernel (and its EWMA pre-scale): beside the decimation chain for the deep stages
     cudaStream_t psd_stream(size_t i) const { return (i >= deep_from_ && psd_stream_) ? psd_stream_ : stage_stream(i); }
     int join_streams();  // make stream_ wait for everything queued on deep_stream_
-    int ensure_fresh(StageState& st, size_t need);
+    uint64_t defer_threshold(size_t j) const;  // stage j >= 1 runs once this many samples are pending (0: at once)
+    int run_pending(size_t j);
+    int flush_deferred();
+    int ensure_fresh(StageState& st, size_t need, size_t reserve = 0);
     int ensure_in_buffers(size_t need);
     int process_host(const float* x, size_t n);
     int flush_staged();
@@ -147,6 +151,8 @@ private:
     int drain_ = 0;    // hbf_dec_response_length(3)
     int num_sms_ = 148;
     int tmax_ = 1, nt_ = 256;  // largest tile (segments per CTA) and CTA size of the stage kernel
+    uint64_t defer_ = 1ull << 26;  // sspsd_config::deep_defer
+    int k3_variant_ = 1;       // SSPSD_K3 at creation: 0 = tiled, 1 = persistent TMA (960 outputs/tile), 2 = (640)
     int k2_variant_ = 2;       // SSPSD_K2 at creation: 0 = radix-8 tiled, 1 = radix-16 tiled, 2 = TMA ring (N = 4096)
     bool single_stage_avg_set_ = false;
     uint32_t single_stage_avg_ = 0xffffffffu;

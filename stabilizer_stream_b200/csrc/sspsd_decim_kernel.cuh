@@ -32,13 +32,15 @@ constexpr int DEC_NT = 256;
 
 constexpr int roundup(int v, int m) { return (v + m - 1) / m * m; }
 
-// Tap counts: MA = highest-rate stage (tap set 2), MB = set 1, MC = lowest-rate stage (set 0)
-template <int MA, int MB, int MC>
+// Tap counts: MA = highest-rate stage (tap set 2), MB = set 1, MC = lowest-rate stage (set 0); OB = final
+// outputs per tile
+template <int MA, int MB, int MC, int OB_ = DEC_OB>
 struct DecGeom {
-    static constexpr int NB = roundup(2 * DEC_OB + 4 * MC - 2, DEC_P);  // stage-B outputs computed per CTA
+    static constexpr int OB = OB_;
+    static constexpr int NB = roundup(2 * OB + 4 * MC - 2, DEC_P);  // stage-B outputs computed per CTA
     static constexpr int NA = roundup(2 * NB + 4 * MB - 2, DEC_P);      // stage-A outputs
     static constexpr int NX = roundup(2 * NA + 4 * MA - 2, 8);      // input samples loaded
-    static constexpr int HALO = NX - 8 * DEC_OB;                    // history needed before the block
+    static constexpr int HALO = NX - 8 * OB;                        // history needed before the block
     // polyphase-by-8 plane layout: phase stride S = ceil(len/8) rounded up to 4 mod 32
     static constexpr int phase_stride(int len) { return ((len + DEC_P - 1) / DEC_P + 27) / 32 * 32 + 4; }
     static constexpr int SX = phase_stride(NX / 2), SA = phase_stride(NA / 2), SB = phase_stride(NB / 2);
@@ -196,6 +198,183 @@ __global__ void __launch_bounds__(DEC_NT) decim8_kernel(const DecimParams p)
     hbf_stage<MC, GE::SB, GE::SB, GE::NB / 2 - DEC_OB, true, PRESET, 0>(be, bo, DEC_OB, nullptr, nullptr,
                                                             p.out_fresh + (c_base - p.drain - p.out_split), rel_lo,
                                                             DEC_OB);
+}
+
+// ---------------------------------------------------------------------------------------------
+// K3, second generation: persistent CTAs with the x tile staged by ONE TMA bulk copy.
+//
+// ncu on the tiled kernel above (profiles/r02_ncu_summary.md): 38 % of all stall samples sit on the
+// de-interleaving STS waiting for its LDG (long_scoreboard) -- the synchronous tile load at the start of
+// every CTA, hidden only by the other two CTAs of the SM.  Here a CTA walks over tiles blockIdx.x,
+// blockIdx.x + gridDim.x, ...; the raw tile (NX contiguous floats, two copies when it straddles the
+// carry/fresh boundary of the StreamSrc) is fetched by cp.async.bulk into a staging buffer and reported
+// to an mbarrier; the threads de-interleave it into the polyphase planes (LDS.128 + 4 STS, both short
+// latency), and as soon as the staging buffer has been consumed the NEXT tile's copy is issued, so it
+// lands while stages A, B and C of the current tile run.  Same arithmetic and tile geometry as above
+// (hbf_stage), therefore bit-identical output.
+// ---------------------------------------------------------------------------------------------
+template <int MA, int MB, int MC, int PRESET, int OB, int CTAS>
+__global__ void __launch_bounds__(DEC_NT, CTAS) decim8_tma_kernel(const DecimParams p, const int ntiles)
+{
+    using GE = DecGeom<MA, MB, MC, OB>;
+    extern __shared__ __align__(16) float smem[];
+    float* stg = smem;                      // GE::NX floats, 16-byte aligned
+    float* xe = stg + GE::NX;
+    float* xo = xe + DEC_P * GE::SX;
+    float* ae = xo + DEC_P * GE::SX;
+    float* ao = ae + DEC_P * GE::SA;
+    float* be = ao + DEC_P * GE::SA;
+    float* bo = be + DEC_P * GE::SB;
+    uint64_t* bar = reinterpret_cast<uint64_t*>(bo + DEC_P * GE::SB);  // (all counts above are even)
+
+    const int tid = threadIdx.x;
+    if (tid == 0) {
+        mbar_init(bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    // tile t covers outputs [m1 - (t+1) OB, m1 - t OB): counted down from the top, so that every tile is full
+    // size and only the lowest one is clipped by the store guard
+    // The lowest tile starts up to OB - 1 outputs below m0, i.e. its x range may begin before the carry buffer
+    // does; that part only feeds outputs the store guard discards, so it is simply not copied.
+    auto issue = [&](int t) {
+        const long long g = 8 * (p.m1 - (long long)t * OB) - GE::NX;
+        long long skip = p.src.carry_start - g;
+        skip = skip < 0 ? 0 : (skip > GE::NX ? GE::NX : skip);
+        ring_issue(p.src, g + skip, GE::NX - (int)skip, stg + skip, bar);
+    };
+    int tile = blockIdx.x;
+    if (tid == 0 && tile < ntiles) issue(tile);
+    const long long lo = p.m0 > p.drain ? p.m0 : p.drain;
+    for (unsigned it = 0; tile < ntiles; tile += gridDim.x, ++it) {
+        const long long mhi = p.m1 - (long long)tile * OB;
+        const long long c_base = mhi - OB;
+        mbar_wait(bar, it & 1u);
+        // ---- de-interleave the staged tile into the polyphase planes (as in the tiled kernel) ----
+        {
+            const float4* __restrict__ s4 = reinterpret_cast<const float4*>(stg);
+            constexpr int NV = GE::NX / 4;
+#pragma unroll 4
+            for (int v = tid; v < NV; v += DEC_NT) {
+                const float4 f = s4[v];
+                const int pos = 2 * (v & 3) * GE::SX + (v >> 2);
+                xe[pos] = f.x;
+                xo[pos] = f.y;
+                xe[pos + GE::SX] = f.z;
+                xo[pos + GE::SX] = f.w;
+            }
+        }
+        __syncthreads();  // planes complete; staging buffer consumed
+        if (tid == 0 && tile + (int)gridDim.x < ntiles) issue(tile + (int)gridDim.x);
+        hbf_stage<MA, GE::SX, GE::SA, GE::NX / 2 - GE::NA, false, PRESET, 2>(xe, xo, GE::NA, ae, ao, nullptr, 0, 0);
+        __syncthreads();
+        hbf_stage<MB, GE::SA, GE::SB, GE::NA / 2 - GE::NB, false, PRESET, 1>(ae, ao, GE::NB, be, bo, nullptr, 0, 0);
+        __syncthreads();
+        const int rel_lo = lo > c_base ? (int)(lo - c_base) : 0;
+        hbf_stage<MC, GE::SB, GE::SB, GE::NB / 2 - OB, true, PRESET, 0>(be, bo, OB, nullptr, nullptr,
+                                                                        p.out_fresh + (c_base - p.drain - p.out_split),
+                                                                        rel_lo, OB);
+        // no barrier needed here: the next tile's de-interleave only writes xe/xo (last read before the
+        // barrier after stage A), its stage A writes ae/ao (last read before the barrier after stage B), and
+        // its stage B writes be/bo after two more barriers
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// K3, third generation: persistent CTAs, the NEXT tile's samples are scattered straight into a second set
+// of polyphase x planes by 4-byte cp.async (LDGSTS) while stages A, B, C of the current tile run.
+//
+// The TMA-staged kernel above removed the exposed LDG latency but paid for it in the resource that bounds
+// the decimator, the shared-memory data pipe: one extra LDS.128 per four samples to read the staging buffer
+// back (+19 % wavefronts; 0.250 -> 0.234 ms per 200e6 samples only).  A 4-byte cp.async writes its element
+// where the de-interleaving STS would have, with no register round trip and no second pass: lane l of an
+// instruction takes element 32 k + l of the tile (one 128-byte line of global memory), which lands in plane
+// (e|o), phase (l >> 1) & 7, offset +(l >> 4): with the odd planes shifted by two banks the 32 lanes hit 32
+// distinct banks, one wavefront per instruction -- the same shared-memory traffic as the tiled kernel's
+// stores, issued a whole tile ahead.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void cp_async4(float* dst, const float* src, bool valid)
+{
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(smem_u32(dst)), "l"(src), "r"(valid ? 4 : 0) : "memory");
+}
+
+template <int MA, int MB, int MC, int PRESET, int OB, int CTAS>
+__global__ void __launch_bounds__(DEC_NT, CTAS) decim8_async_kernel(const DecimParams p, const int ntiles)
+{
+    using GE = DecGeom<MA, MB, MC, OB>;
+    constexpr int XP = 2 * DEC_P * GE::SX + 4;  // floats per x plane set: even planes, +2 banks, odd planes, pad
+    static_assert(GE::NX % DEC_NT == 0 || true, "");
+    extern __shared__ __align__(16) float smem[];
+    float* xs = smem;                       // two plane sets
+    float* ae = xs + 2 * XP;
+    float* ao = ae + DEC_P * GE::SA;
+    float* be = ao + DEC_P * GE::SA;
+    float* bo = be + DEC_P * GE::SB;
+
+    const int tid = threadIdx.x;
+    // element i = DEC_NT k + tid of a tile: plane index r = i >> 1 = (DEC_NT / 2) k + (tid >> 1); DEC_NT / 2 is a
+    // multiple of 8, so the phase r & 7 is per thread and the offset r >> 3 advances by DEC_NT / 16 per k
+    const int dst0 = ((tid >> 1) & 7) * GE::SX + (tid >> 4) + ((tid & 1) ? DEC_P * GE::SX + 2 : 0);
+    auto issue = [&](int t, float* planes) {
+        const long long g0 = 8 * (p.m1 - (long long)t * OB) - GE::NX;  // first sample of the tile (multiple of 8)
+        float* d = planes + dst0;
+        if (g0 >= p.src.split) {
+            const float* __restrict__ gx = p.src.fresh + (g0 - p.src.split) + tid;
+#pragma unroll 8
+            for (int k = 0; k < GE::NX / DEC_NT; ++k) cp_async4(d + (DEC_NT / 16) * k, gx + DEC_NT * k, true);
+            if (GE::NX % DEC_NT != 0 && tid < GE::NX % DEC_NT)
+                cp_async4(d + (DEC_NT / 16) * (GE::NX / DEC_NT), gx + DEC_NT * (GE::NX / DEC_NT), true);
+        } else {
+            // first tiles of a batch: carry / fresh per element, zeros before the carry buffer begins
+            for (int k = 0; DEC_NT * k + tid < GE::NX; ++k) {
+                const long long g = g0 + DEC_NT * k + tid;
+                const float* src = g >= p.src.split ? p.src.fresh + (g - p.src.split)
+                                                    : p.src.carry + (g >= p.src.carry_start ? g - p.src.carry_start : 0);
+                cp_async4(d + (DEC_NT / 16) * k, src, g >= p.src.carry_start);
+            }
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    int tile = blockIdx.x;
+    if (tile < ntiles) issue(tile, xs);
+    const long long lo = p.m0 > p.drain ? p.m0 : p.drain;
+    for (unsigned it = 0; tile < ntiles; tile += gridDim.x, ++it) {
+        float* xe = xs + (it & 1u) * XP;
+        float* xo = xe + DEC_P * GE::SX + 2;
+        const int next = tile + (int)gridDim.x;
+        // the other plane set was last read by stage A of the previous tile, two barriers ago
+        if (next < ntiles) {
+            issue(next, xs + ((it + 1u) & 1u) * XP);
+            asm volatile("cp.async.wait_group 1;" ::: "memory");
+        } else {
+            asm volatile("cp.async.wait_group 0;" ::: "memory");
+        }
+        __syncthreads();  // every thread's copies of this tile have landed
+        const long long mhi = p.m1 - (long long)tile * OB;
+        const long long c_base = mhi - OB;
+        hbf_stage<MA, GE::SX, GE::SA, GE::NX / 2 - GE::NA, false, PRESET, 2>(xe, xo, GE::NA, ae, ao, nullptr, 0, 0);
+        __syncthreads();
+        hbf_stage<MB, GE::SA, GE::SB, GE::NA / 2 - GE::NB, false, PRESET, 1>(ae, ao, GE::NB, be, bo, nullptr, 0, 0);
+        __syncthreads();
+        const int rel_lo = lo > c_base ? (int)(lo - c_base) : 0;
+        hbf_stage<MC, GE::SB, GE::SB, GE::NB / 2 - OB, true, PRESET, 0>(be, bo, OB, nullptr, nullptr,
+                                                                        p.out_fresh + (c_base - p.drain - p.out_split),
+                                                                        rel_lo, OB);
+    }
+}
+
+template <int MA, int MB, int MC, int OB>
+constexpr size_t decim_async_smem_bytes()
+{
+    using GE = DecGeom<MA, MB, MC, OB>;
+    return (size_t)(2 * (2 * DEC_P * GE::SX + 4) + 2 * DEC_P * (GE::SA + GE::SB)) * sizeof(float);
+}
+
+template <int MA, int MB, int MC, int OB>
+constexpr size_t decim_tma_smem_bytes()
+{
+    using GE = DecGeom<MA, MB, MC, OB>;
+    return (size_t)(GE::NX + GE::SMEM_FLOATS) * sizeof(float) + 16;
 }
 
 // ---------------------------------------------------------------------------------------------
