@@ -207,6 +207,79 @@ int32_t sspsd_cascade_process_stage(sspsd_cascade *h, uint32_t stage, const floa
 /* overwrite stage bookkeeping after an external reduction: samples received, averaging count (Psd::count) */
 int32_t sspsd_cascade_set_stream_state(sspsd_cascade *h, uint32_t stage, uint64_t samples, uint64_t segments);
 
+/* ---------------------------------------------------------------------------------------------
+ * Multi-GPU partitioning (north_star item 5).  No reference analogue: the reference is ONE process that
+ * loops over its traces on one thread (src/bin/psd.rs:170-183).  A group spreads that loop over GPUs:
+ *   SSPSD_SHARD_CHANNELS  channel (trace) c lives on rank c % n_ranks; nothing is exchanged while processing;
+ *   SSPSD_SHARD_TIME      ONE long stream is cut into n_ranks chunks (see "time-chunked processing" above); the
+ *                         readout is ONE sum-reduction of [accumulator rows | counts | tail slices] to rank 0.
+ * A group holds either all ranks in ONE process -- sspsd_group_create(devices[]): one handle per device,
+ * ncclCommInitAll, or (ranks sharing a GPU, SSPSD_GROUP_REDUCE=p2p) a root kernel that sums the peers' rows
+ * through peer pointers in fixed order -- or one rank of a multi-process job (torchrun, MPI):
+ * sspsd_group_unique_id() on rank 0, the 128 bytes broadcast by the caller, sspsd_group_create_rank() everywhere.
+ * NCCL (libnccl.so.2) is loaded on first use; collective failures return SSPSD_ENCCL.
+ * --------------------------------------------------------------------------------------------- */
+typedef struct sspsd_group sspsd_group;
+enum { SSPSD_SHARD_CHANNELS = 0, SSPSD_SHARD_TIME = 1 };
+enum { SSPSD_REDUCE_NCCL = 0, SSPSD_REDUCE_P2P = 1 };
+#define SSPSD_GROUP_ID_BYTES 128
+#define SSPSD_GROUP_MAX_RANKS 64
+
+int32_t sspsd_group_create(const sspsd_config *cfg, const int32_t *devices, uint32_t n_devices, int32_t shard_mode,
+                           sspsd_group **out);
+int32_t sspsd_group_unique_id(uint8_t id[SSPSD_GROUP_ID_BYTES]);
+/* cfg->device = this rank's device */
+int32_t sspsd_group_create_rank(const sspsd_config *cfg, const uint8_t id[SSPSD_GROUP_ID_BYTES], uint32_t rank,
+                                uint32_t n_ranks, int32_t shard_mode, sspsd_group **out);
+void sspsd_group_destroy(sspsd_group *g);
+/* any pointer may be NULL; first_rank / n_local_ranks: the ranks this process holds; reduce: SSPSD_REDUCE_* in use */
+int32_t sspsd_group_info(const sspsd_group *g, uint32_t *n_ranks, uint32_t *first_rank, uint32_t *n_local_ranks,
+                         int32_t *shard_mode, int32_t *reduce);
+/* PsdCascade::set_avg / set_detrend on every cascade of the group (existing and future ones) */
+int32_t sspsd_group_set_avg(sspsd_group *g, sspsd_avg_opts avg);
+int32_t sspsd_group_set_detrend(sspsd_group *g, int32_t detrend);
+/* wait for all device work of the group's handles in this process */
+int32_t sspsd_group_sync(sspsd_group *g);
+
+/* ---- channels: `dec[channel].process(&trace)` of src/bin/psd.rs:174-182 ----
+ * The cascade of a channel is created on first use on device (channel % n_ranks).  In a multi-process group a
+ * call for a channel another process owns is a no-op returning SSPSD_OK, so every process can run the same loop. */
+int32_t sspsd_group_process_f32(sspsd_group *g, uint32_t channel, const float *x, size_t n, int32_t mem);
+/* where a channel lives: device = -1 if another process owns it */
+int32_t sspsd_group_channel_device(const sspsd_group *g, uint32_t channel, int32_t *device, uint32_t *rank);
+/* psd() of one channel (single-process channel groups), or of THE stream of a time-chunked group after
+ * sspsd_group_time_finish (result on the process that holds rank 0; lengths 0 elsewhere) */
+int32_t sspsd_group_psd(sspsd_group *g, uint32_t channel, const sspsd_merge_opts *opts, float *p, size_t *p_len,
+                        sspsd_break *b, size_t *b_len);
+/* psd() of channels 0..n_channels-1 at once: channel c's spectrum at p + c * p_stride (p_lens[c] floats), its breaks
+ * at b + c * b_stride.  In a multi-process group this is a collective (every process calls it): ONE
+ * ncclAllGather of the accumulator rows + bookkeeping, merged on rank 0 (lengths 0 on the other ranks). */
+int32_t sspsd_group_psd_all(sspsd_group *g, uint32_t n_channels, const sspsd_merge_opts *opts, float *p, size_t p_stride,
+                            size_t *p_lens, sspsd_break *b, size_t b_stride, size_t *b_lens);
+
+/* ---- time chunks of one stream ---- */
+typedef struct {
+    uint64_t own_lo, own_hi;   /* ownership interval in stage-0 samples (own_hi = UINT64_MAX for the last rank) */
+    uint64_t feed_lo, feed_hi; /* samples the rank must be fed: its chunk + FIR warm-up halo + completion halo */
+    uint64_t tail_lo, tail_hi; /* owned index range of the stage-n_local input stream (tail_hi = UINT64_MAX: open) */
+    uint32_t n_local;          /* stages that run on every rank; deeper ones run on rank 0 after the exchange */
+    uint32_t _pad;
+} sspsd_time_chunk;
+/* pure host planner: what rank `rank` of `n_ranks` is fed for a stream of `total` samples (n_local_stages 0 = auto) */
+int32_t sspsd_time_plan(uint32_t n_fft, int32_t window, int32_t hbf, uint64_t total, uint32_t n_ranks, uint32_t rank,
+                        uint32_t n_local_stages, sspsd_time_chunk *out);
+/* start a capture of `total` samples: plans every rank, creates + positions this process's handles */
+int32_t sspsd_group_time_plan(sspsd_group *g, uint64_t total, uint32_t n_local_stages);
+int32_t sspsd_group_time_chunk(const sspsd_group *g, uint32_t rank, sspsd_time_chunk *out);
+/* the next n samples of rank `rank`'s range [feed_lo, feed_hi), in order (no-op for ranks of other processes) */
+int32_t sspsd_group_time_process_f32(sspsd_group *g, uint32_t rank, const float *x, size_t n, int32_t mem);
+/* single-process groups: x = the whole stream in host memory, the library feeds every rank its range */
+int32_t sspsd_group_time_process_all_f32(sspsd_group *g, const float *x, size_t n);
+/* every local rank generates its own range of the synthetic stream (SSPSD_SOURCE_NOISE, exponent >= 0) on its device */
+int32_t sspsd_group_time_process_noise(sspsd_group *g, int64_t exponent, uint64_t seed);
+/* the exchange (collective in a multi-process group): ONE reduction to rank 0, which then runs the deep stages */
+int32_t sspsd_group_time_finish(sspsd_group *g);
+
 /* ---- measurement hooks (no reference analogue) ----
  * With profiling enabled every kernel launch of the handle is bracketed by CUDA events on the
  * handle's stream; sspsd_cascade_profile_read() synchronises, sums the event times per kernel class
@@ -332,6 +405,9 @@ int32_t sspsd_source_reset(sspsd_source *s);
 /* the next n samples into device memory d_out, asynchronously on the source's stream (Source::get) */
 int32_t sspsd_source_generate(sspsd_source *s, float *d_out, size_t n);
 int32_t sspsd_source_position(const sspsd_source *s, uint64_t *pos);
+/* continue the stream at sample `pos` (counter-based uniform stream: white and differentiated noise only;
+ * integrated noise and the modulator carry state and return SSPSD_EUNIMPLEMENTED) */
+int32_t sspsd_source_seek(sspsd_source *s, uint64_t pos);
 /* generate the next n samples straight into the cascade (stream_test.rs:52-58 with a synthetic
  * source): no host memory is touched; generation and consumption share the cascade's stream */
 int32_t sspsd_cascade_process_source(sspsd_cascade *c, sspsd_source *s, size_t n);

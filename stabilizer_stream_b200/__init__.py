@@ -5,7 +5,9 @@ C ABI in include/sspsd.h.  The CUDA library is the only implementation: importin
 works without a GPU, creating any handle does not.
 """
 from .psd import (DEPTH, HBF_PASSBAND, AvgOpts, Break, DecodeError, Detrend, Format, FrameDecoder, Hbf, Loss,
-                  MergeOpts, Psd, PsdCascade, Receiver, Source, SourceKind, Trace, Var, Window)
+                  MergeOpts, Psd, PsdCascade, Receiver, ShardMode, Source, SourceKind, TimeChunk, Trace, Var, Window,
+                  Group, time_plan)
 
 __all__ = ["DEPTH", "HBF_PASSBAND", "AvgOpts", "Break", "DecodeError", "Detrend", "Format", "FrameDecoder", "Hbf",
-           "Loss", "MergeOpts", "Psd", "PsdCascade", "Receiver", "Source", "SourceKind", "Trace", "Var", "Window"]
+           "Loss", "MergeOpts", "Psd", "PsdCascade", "Receiver", "ShardMode", "Source", "SourceKind", "TimeChunk", "Trace",
+           "Var", "Window", "Group", "time_plan"]

@@ -64,6 +64,11 @@ class PlotOptsC(C.Structure):
                 ("integrate", C.c_uint32)]
 
 
+class TimeChunkC(C.Structure):
+    _fields_ = [("own_lo", C.c_uint64), ("own_hi", C.c_uint64), ("feed_lo", C.c_uint64), ("feed_hi", C.c_uint64),
+                ("tail_lo", C.c_uint64), ("tail_hi", C.c_uint64), ("n_local", C.c_uint32), ("_pad", C.c_uint32)]
+
+
 class VarC(C.Structure):
     _fields_ = [("x_exp", C.c_int32), ("sinx_exp", C.c_int32), ("clip", C.c_float), ("_pad", C.c_uint32),
                 ("dc_cut", C.c_uint64)]
@@ -129,6 +134,28 @@ PROTOTYPES = {
     "sspsd_source_generate": (_i32, [_vp, _vp, _sz]),
     "sspsd_source_position": (_i32, [_vp, C.POINTER(C.c_uint64)]),
     "sspsd_cascade_process_source": (_i32, [_vp, _vp, _sz]),
+    "sspsd_source_seek": (_i32, [_vp, C.c_uint64]),
+    "sspsd_group_create": (_i32, [C.POINTER(Config), C.POINTER(_i32), C.c_uint32, _i32, C.POINTER(_vp)]),
+    "sspsd_group_unique_id": (_i32, [_vp]),
+    "sspsd_group_create_rank": (_i32, [C.POINTER(Config), _vp, C.c_uint32, C.c_uint32, _i32, C.POINTER(_vp)]),
+    "sspsd_group_destroy": (None, [_vp]),
+    "sspsd_group_info": (_i32, [_vp, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32), C.POINTER(C.c_uint32),
+                                C.POINTER(_i32), C.POINTER(_i32)]),
+    "sspsd_group_set_avg": (_i32, [_vp, AvgOptsC]),
+    "sspsd_group_set_detrend": (_i32, [_vp, _i32]),
+    "sspsd_group_sync": (_i32, [_vp]),
+    "sspsd_group_process_f32": (_i32, [_vp, C.c_uint32, _vp, _sz, _i32]),
+    "sspsd_group_channel_device": (_i32, [_vp, C.c_uint32, C.POINTER(_i32), C.POINTER(C.c_uint32)]),
+    "sspsd_group_psd": (_i32, [_vp, C.c_uint32, C.POINTER(MergeOptsC), _vp, _psz, C.POINTER(BreakC), _psz]),
+    "sspsd_group_psd_all": (_i32, [_vp, C.c_uint32, C.POINTER(MergeOptsC), _vp, _sz, _psz, C.POINTER(BreakC), _sz, _psz]),
+    "sspsd_time_plan": (_i32, [C.c_uint32, _i32, _i32, C.c_uint64, C.c_uint32, C.c_uint32, C.c_uint32,
+                               C.POINTER(TimeChunkC)]),
+    "sspsd_group_time_plan": (_i32, [_vp, C.c_uint64, C.c_uint32]),
+    "sspsd_group_time_chunk": (_i32, [_vp, C.c_uint32, C.POINTER(TimeChunkC)]),
+    "sspsd_group_time_process_f32": (_i32, [_vp, C.c_uint32, _vp, _sz, _i32]),
+    "sspsd_group_time_process_all_f32": (_i32, [_vp, _vp, _sz]),
+    "sspsd_group_time_process_noise": (_i32, [_vp, C.c_int64, C.c_uint64]),
+    "sspsd_group_time_finish": (_i32, [_vp]),
     "sspsd_receiver_create": (_i32, [C.c_char_p, C.c_uint16, C.c_uint32, C.c_uint32, _i32, C.POINTER(_vp)]),
     "sspsd_receiver_destroy": (None, [_vp]),
     "sspsd_receiver_info": (_i32, [_vp, C.POINTER(C.c_uint16), _psz, C.POINTER(C.c_uint64)]),

@@ -1218,19 +1218,30 @@ float Cascade::gain_of(uint32_t count) const
 
 float Cascade::stage_gain() const { return gain_of(stages_.empty() ? 0 : stages_[0].count); }
 
-int Cascade::psd(const sspsd_merge_opts& o, float* p, size_t* p_len, sspsd_break* b, size_t* b_len)
+// Stage bookkeeping in a flat form that can travel (channel gather of a multi-process group):
+// book[4 i .. 4 i + 3] = (L, craw, count, avg) of stage i, book[4 * SSPSD_MAX_STAGES] = number of stages
+void Cascade::export_book(uint64_t* book) const
 {
-    if (!p_len || !b_len) {
-        set_error("null length pointer");
-        return SSPSD_EINVAL;
+    std::memset(book, 0, (4 * SSPSD_MAX_STAGES + 2) * sizeof(uint64_t));
+    for (size_t i = 0; i < stages_.size(); ++i) {
+        book[4 * i] = stages_[i].L;
+        book[4 * i + 1] = stages_[i].craw;
+        book[4 * i + 2] = stages_[i].count;
+        book[4 * i + 3] = stages_[i].avg;
     }
-    int rc = sync();
-    if (rc) return rc;
-    DeviceGuard g(cfg_.device);
-    if (!g.ok) return SSPSD_ECUDA;
-    const size_t ns = stages_.size();
-    const size_t N = n_;
-    // first pass: sizes (PsdCascade::psd, psd.rs:479-543)
+    book[4 * SSPSD_MAX_STAGES] = stages_.size();
+}
+
+// PsdCascade::psd, psd.rs:479-543, on host copies of the accumulator rows and the stage bookkeeping
+int Cascade::merge_host(const sspsd_config& cfg, const uint64_t* book, const float* rows, size_t stride,
+                        const sspsd_merge_opts& o, float* p, size_t* p_len, sspsd_break* b, size_t* b_len)
+{
+    const size_t ns = (size_t)book[4 * SSPSD_MAX_STAGES];
+    const size_t N = cfg.n_fft;
+    const bool hann = cfg.window == SSPSD_WINDOW_HANN;
+    const float power = hann ? 0.25f : 1.0f, nenbw = hann ? 1.5f : 1.0f;
+    const uint64_t overlap = hann ? N / 2 : 0, hop = N - overlap;
+    // first pass: sizes
     size_t plen = 0;
     {
         size_t end = 0;
@@ -1239,7 +1250,7 @@ int Cascade::psd(const sspsd_merge_opts& o, float* p, size_t* p_len, sspsd_break
             dec >>= SSPSD_DEPTH;
             size_t start = !o.keep_overlap ? (end + 7) >> 3 : 0;
             end = (dec > 1 && !o.keep_transition_band) ? 2 * N / 5 : N / 2 + 1;
-            if (stages_[r].count >= o.min_count)
+            if (book[4 * r + 2] >= o.min_count)
                 plen += end - start;
             else
                 end = start;
@@ -1252,34 +1263,34 @@ int Cascade::psd(const sspsd_merge_opts& o, float* p, size_t* p_len, sspsd_break
         set_error("output capacity too small");
         return SSPSD_ESHORT;
     }
-    if (ns == 0)
-        return SSPSD_OK;
-    SSPSD_CUDA(cudaMemcpyAsync(h_acc_, d_acc_, ns * acc_stride_ * sizeof(float), cudaMemcpyDeviceToHost, stream_));
-    SSPSD_CUDA(cudaStreamSynchronize(stream_));
     size_t pl = 0, bl = 0, end = 0;
     uint64_t dec = 1ull << (SSPSD_DEPTH * ns);
     for (size_t r = ns; r-- > 0;) {
-        const StageState& st = stages_[r];
+        const uint64_t L = book[4 * r], craw = book[4 * r + 1];
+        const uint32_t count = (uint32_t)book[4 * r + 2], avg = (uint32_t)book[4 * r + 3];
         dec >>= SSPSD_DEPTH;
         size_t start = !o.keep_overlap ? (end + 7) >> 3 : 0;
         end = (dec > 1 && !o.keep_transition_band) ? 2 * N / 5 : N / 2 + 1;
-        bool include = st.count >= o.min_count;
+        bool include = count >= o.min_count;
         sspsd_break& bk = b[bl++];
         std::memset(&bk, 0, sizeof(bk));
         bk.start = pl;
         bk.include = include;
-        bk.count = st.count;
-        bk.avg = st.avg;
+        bk.count = count;
+        bk.avg = avg;
         bk.bins_start = start;
         bk.bins_end = end;
         bk.fft_size = N;
         bk.decimation = dec;
-        uint32_t cm1 = st.count > 0 ? st.count - 1 : 0;
-        bk.processed = (uint64_t)N * st.count - (uint64_t)win_.overlap * cm1;
-        bk.pending = st.craw ? st.L - st.craw * (uint64_t)hop_ : st.L;
+        uint32_t cm1 = count > 0 ? count - 1 : 0;
+        bk.processed = (uint64_t)N * count - overlap * cm1;
+        bk.pending = craw ? L - craw * hop : L;
         if (include) {
-            float gg = 1.0f / (gain_of(st.count) * (float)dec);
-            const float* sp = h_acc_ + r * acc_stride_;
+            // PsdStage::gain, psd.rs:279-283; N/2*count formed in 64 bits (the reference wraps in u32 for
+            // count > 2^32/(N/2))
+            const float gain = (float)((uint64_t)(N / 2) * (uint64_t)count) * nenbw * power;
+            float gg = 1.0f / (gain * (float)dec);
+            const float* sp = rows + r * stride;
             for (size_t k = start; k < end; ++k)
                 p[pl++] = sp[k] * gg;
         } else {
@@ -1287,6 +1298,40 @@ int Cascade::psd(const sspsd_merge_opts& o, float* p, size_t* p_len, sspsd_break
         }
     }
     return SSPSD_OK;
+}
+
+int Cascade::psd(const sspsd_merge_opts& o, float* p, size_t* p_len, sspsd_break* b, size_t* b_len)
+{
+    if (!p_len || !b_len) {
+        set_error("null length pointer");
+        return SSPSD_EINVAL;
+    }
+    int rc = sync();
+    if (rc) return rc;
+    DeviceGuard g(cfg_.device);
+    if (!g.ok) return SSPSD_ECUDA;
+    const size_t ns = stages_.size();
+    uint64_t book[4 * SSPSD_MAX_STAGES + 2];
+    export_book(book);
+    // sizes first: a too small buffer is reported without touching the device
+    {
+        size_t pl = 0, bl = 0;
+        int rs = merge_host(cfg_, book, nullptr, acc_stride_, o, nullptr, &pl, nullptr, &bl);
+        const bool fits = (pl <= *p_len) && (ns <= *b_len) && (pl == 0 || p) && (ns == 0 || b);
+        (void)rs;
+        if (!fits || ns == 0) {
+            *p_len = pl;
+            *b_len = ns;
+            if (!fits) {
+                set_error("output capacity too small");
+                return SSPSD_ESHORT;
+            }
+            return SSPSD_OK;
+        }
+    }
+    SSPSD_CUDA(cudaMemcpyAsync(h_acc_, d_acc_, ns * acc_stride_ * sizeof(float), cudaMemcpyDeviceToHost, stream_));
+    SSPSD_CUDA(cudaStreamSynchronize(stream_));
+    return merge_host(cfg_, book, h_acc_, acc_stride_, o, p, p_len, b, b_len);
 }
 
 void Cascade::prof_begin(int cls, uint64_t units, cudaStream_t s)

@@ -71,6 +71,9 @@ public:
     int sync();
     int psd(const sspsd_merge_opts& o, float* p, size_t* p_len, sspsd_break* b, size_t* b_len);
     int partials(sspsd_partials* out);
+    void export_book(uint64_t* book) const;  // 4 * SSPSD_MAX_STAGES + 2 words
+    static int merge_host(const sspsd_config& cfg, const uint64_t* book, const float* rows, size_t stride,
+                          const sspsd_merge_opts& o, float* p, size_t* p_len, sspsd_break* b, size_t* b_len);
     int seek(uint64_t pos);
     int set_window(uint64_t own_lo, uint64_t own_hi, uint32_t n_local);
     int take_tail(uint64_t j_lo, uint64_t j_hi, float* out, size_t* len, uint64_t* first, int mem);

@@ -105,6 +105,16 @@ public:
     }
 
     uint64_t position() const { return pos_; }
+    int seek(uint64_t pos)
+    {
+        // only the counter-based part of the stream can be entered anywhere: white noise and its differences
+        if (kind_ == SSPSD_SOURCE_DSM || (order_ > 0 && !diff_)) {
+            set_error("seek: integrated noise and the modulator carry state");
+            return SSPSD_EUNIMPLEMENTED;
+        }
+        pos_ = pos;
+        return SSPSD_OK;
+    }
     cudaStream_t stream() const { return stream_; }
     int device() const { return device_; }
 
@@ -226,6 +236,12 @@ int32_t sspsd_source_position(const sspsd_source* h, uint64_t* pos)
     if (!h || !pos) return SSPSD_EINVAL;
     *pos = h->s.position();
     return SSPSD_OK;
+}
+
+int32_t sspsd_source_seek(sspsd_source* h, uint64_t pos)
+{
+    if (!h) return SSPSD_EINVAL;
+    return h->s.seek(pos);
 }
 
 int32_t sspsd_cascade_process_source(sspsd_cascade* c, sspsd_source* h, size_t n)

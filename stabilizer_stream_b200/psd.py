@@ -671,3 +671,158 @@ class Receiver:
         h, self._h = getattr(self, "_h", None), None
         if h and L is not None and getattr(L, "_lib", None) is not None:
             L._lib.sspsd_receiver_destroy(h)
+
+
+class ShardMode(enum.IntEnum):
+    CHANNELS = 0
+    TIME = 1
+
+
+@dataclass
+class TimeChunk:
+    """sspsd_time_chunk: what one rank of a time-chunked group owns and is fed"""
+    own_lo: int
+    own_hi: object   # None for the last rank
+    feed_lo: int
+    feed_hi: int
+    tail_lo: int
+    tail_hi: object  # None: open
+    n_local: int
+
+    @staticmethod
+    def _from_c(c):
+        none = 2 ** 64 - 1
+        return TimeChunk(c.own_lo, None if c.own_hi == none else c.own_hi, c.feed_lo, c.feed_hi, c.tail_lo,
+                         None if c.tail_hi == none else c.tail_hi, c.n_local)
+
+
+def time_plan(n_fft, total, n_ranks, rank, n_local=0, window=Window.HANN, hbf=Hbf.TAPS_140):
+    """sspsd_time_plan: pure host planner of the time-chunked mode"""
+    out = L.TimeChunkC()
+    L.check(L.lib().sspsd_time_plan(n_fft, int(window), int(hbf), total, n_ranks, rank, n_local, C.byref(out)))
+    return TimeChunk._from_c(out)
+
+
+class Group:
+    """sspsd_group: the reference's single-threaded loop over traces (src/bin/psd.rs:170-183) spread over GPUs,
+    with the NCCL plumbing inside the library.
+
+    Group(n, devices=[0, 1, ...])            all ranks in this process (ncclCommInitAll / peer loads)
+    Group(n, rank=r, n_ranks=w, unique_id=b) one rank of a multi-process job (torchrun): unique_id from
+                                             Group.unique_id() on rank 0, broadcast by the caller"""
+
+    def __init__(self, n=512, devices=None, mode=ShardMode.CHANNELS, rank=None, n_ranks=None, unique_id=None, device=0,
+                 hbf=Hbf.TAPS_140, max_batch=0, host_stage=0):
+        self.n = n
+        cfg = _config(n, Window.HANN, hbf, device, 0, max_batch, host_stage)
+        cfg.stream = None
+        h = C.c_void_p()
+        if rank is None:
+            devices = list(devices if devices is not None else [0])
+            arr = (C.c_int32 * len(devices))(*devices)
+            L.check(L.lib().sspsd_group_create(C.byref(cfg), arr, len(devices), int(mode), C.byref(h)))
+            self.n_ranks, self.rank = len(devices), 0
+        else:
+            buf = (C.c_uint8 * 128).from_buffer_copy(bytes(unique_id)) if unique_id is not None else None
+            L.check(L.lib().sspsd_group_create_rank(C.byref(cfg), buf, rank, n_ranks, int(mode), C.byref(h)))
+            self.n_ranks, self.rank = n_ranks, rank
+        self._h = h
+        self.mode = ShardMode(mode)
+
+    @staticmethod
+    def unique_id():
+        buf = (C.c_uint8 * 128)()
+        L.check(L.lib().sspsd_group_unique_id(buf))
+        return bytes(buf)
+
+    def info(self):
+        a, b, c = C.c_uint32(), C.c_uint32(), C.c_uint32()
+        m, r = C.c_int32(), C.c_int32()
+        L.check(L.lib().sspsd_group_info(self._h, C.byref(a), C.byref(b), C.byref(c), C.byref(m), C.byref(r)))
+        return dict(n_ranks=a.value, first_rank=b.value, n_local_ranks=c.value, mode=m.value,
+                    reduce="nccl" if r.value == 0 else "p2p")
+
+    def set_avg(self, avg: AvgOpts):
+        L.check(L.lib().sspsd_group_set_avg(self._h, L.AvgOptsC(avg.limit, avg.count)))
+
+    def set_detrend(self, d: Detrend):
+        L.check(L.lib().sspsd_group_set_detrend(self._h, int(d)))
+
+    def sync(self):
+        L.check(L.lib().sspsd_group_sync(self._h))
+
+    # ---- channels ----
+    def process(self, channel, x):
+        ptr, n, mem, keep = _as_buffer(x)
+        if mem == L.MEM_DEVICE:
+            import torch
+            torch.cuda.current_stream(keep.device).synchronize()  # the group's handles own their streams
+        L.check(L.lib().sspsd_group_process_f32(self._h, channel, ptr, n, mem))
+        if mem == L.MEM_DEVICE:
+            self.sync()  # the tensor is borrowed for the call only
+        del keep
+
+    def process_raw(self, channel, ptr, n, mem):
+        L.check(L.lib().sspsd_group_process_f32(self._h, channel, ptr, n, mem))
+
+    def channel_device(self, channel):
+        d, r = C.c_int32(), C.c_uint32()
+        L.check(L.lib().sspsd_group_channel_device(self._h, channel, C.byref(d), C.byref(r)))
+        return d.value, r.value
+
+    def psd(self, channel=0, opts: MergeOpts = None):
+        opts = opts or MergeOpts()
+        o = L.MergeOptsC(int(opts.keep_overlap), opts.min_count, int(opts.keep_transition_band))
+        p = np.zeros(L.MAX_STAGES * (self.n // 2 + 1), np.float32)
+        b = (L.BreakC * L.MAX_STAGES)()
+        pl, bl = C.c_size_t(p.size), C.c_size_t(L.MAX_STAGES)
+        L.check(L.lib().sspsd_group_psd(self._h, channel, C.byref(o), p.ctypes.data, C.byref(pl), b, C.byref(bl)))
+        return p[:pl.value].copy(), [Break._from_c(b[i]) for i in range(bl.value)]
+
+    def psd_all(self, n_channels, opts: MergeOpts = None):
+        """-> [(p, breaks)] per channel on the process holding rank 0 (empty arrays elsewhere); a collective in
+        a multi-process group"""
+        opts = opts or MergeOpts()
+        o = L.MergeOptsC(int(opts.keep_overlap), opts.min_count, int(opts.keep_transition_band))
+        ps = L.MAX_STAGES * (self.n // 2 + 1)
+        p = np.zeros((n_channels, ps), np.float32)
+        b = (L.BreakC * (L.MAX_STAGES * n_channels))()
+        pl = (C.c_size_t * n_channels)()
+        bl = (C.c_size_t * n_channels)()
+        L.check(L.lib().sspsd_group_psd_all(self._h, n_channels, C.byref(o), p.ctypes.data, ps, pl, b, L.MAX_STAGES, bl))
+        return [(p[c, :pl[c]].copy(), [Break._from_c(b[c * L.MAX_STAGES + i]) for i in range(bl[c])])
+                for c in range(n_channels)]
+
+    # ---- time chunks of one stream ----
+    def time_plan(self, total, n_local=0):
+        L.check(L.lib().sspsd_group_time_plan(self._h, total, n_local))
+
+    def time_chunk(self, rank):
+        out = L.TimeChunkC()
+        L.check(L.lib().sspsd_group_time_chunk(self._h, rank, C.byref(out)))
+        return TimeChunk._from_c(out)
+
+    def time_process(self, rank, x):
+        ptr, n, mem, keep = _as_buffer(x)
+        if mem == L.MEM_DEVICE:
+            import torch
+            torch.cuda.current_stream(keep.device).synchronize()
+        L.check(L.lib().sspsd_group_time_process_f32(self._h, rank, ptr, n, mem))
+        if mem == L.MEM_DEVICE:
+            self.sync()
+        del keep
+
+    def time_process_all(self, x):
+        a = np.ascontiguousarray(x, dtype=np.float32)
+        L.check(L.lib().sspsd_group_time_process_all_f32(self._h, a.ctypes.data, a.size))
+
+    def time_process_noise(self, exponent=0, seed=Source.SEED):
+        L.check(L.lib().sspsd_group_time_process_noise(self._h, exponent, seed))
+
+    def time_finish(self):
+        L.check(L.lib().sspsd_group_time_finish(self._h))
+
+    def __del__(self):
+        h, self._h = getattr(self, "_h", None), None
+        if h and L is not None and getattr(L, "_lib", None) is not None:
+            L._lib.sspsd_group_destroy(h)
