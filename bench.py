@@ -185,14 +185,14 @@ def run_reference(args):
            "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": cfg,
            "cpu_baseline": cb, "parity_note": PARITY_NOTE,
            "e2e": {"value": v, "unit": "MS/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(out))
+    emit(out)
 
 
 def run_ours(args):
     import numpy as np
     import torch
     import torch.distributed as dist
-    from stabilizer_stream_b200 import MergeOpts, PsdCascade, multi
+    from stabilizer_stream_b200 import Group, MergeOpts, ShardMode, _lib
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -202,6 +202,15 @@ def run_ours(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     stream = torch.cuda.current_stream(dev)
+
+    # The multi-GPU plumbing lives in the library: every rank joins one sspsd_group (ncclCommInitRank inside
+    # libsspsd.so; torch.distributed only hands the 128-byte id around and provides the barrier of the contract).
+    def new_group(mode=ShardMode.CHANNELS):
+        ids = [Group.unique_id() if (rank == 0 and world > 1) else None]  # a fresh NCCL id per communicator
+        if world > 1:
+            dist.broadcast_object_list(ids, src=0)
+        return Group(N_FFT, rank=rank, n_ranks=world, unique_id=ids[0], device=local, mode=mode,
+                     stream=stream.cuda_stream or 1)
 
     gen = torch.Generator(device=dev).manual_seed(0x7654321 + rank)
     x = (torch.rand(SAMPLES_PER_STEP, device=dev, generator=gen) - 0.5) * (12 ** 0.5)
@@ -214,76 +223,90 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize(dev)
 
-    def gather_readout(p):
-        """readout collective: one NCCL gather of every channel's merged spectrum to rank 0"""
-        if world == 1:
-            return
-        multi.gather_spectra(p, dist, dev, dst=0, max_len=16 * (N_FFT // 2 + 1))
+    class Channel:
+        """this rank's channel (= trace `rank` of the job) of a channel-sharded group"""
 
-    def timed(cascade, src, steps, warmup):
+        def __init__(self):
+            self.g = new_group()
+            self.g.process_raw(rank, x.data_ptr(), 4 * N_FFT, _lib.MEM_DEVICE)  # creates the channel's cascade
+            self.c = self.g.channel_cascade(rank)
+            self.c.reset()
+
+        def process(self, src):
+            if src is x:
+                self.g.process_raw(rank, x.data_ptr(), SAMPLES_PER_STEP, _lib.MEM_DEVICE)
+            else:
+                self.g.process_raw(rank, xh.data_ptr(), SAMPLES_PER_STEP, _lib.MEM_HOST)
+
+        def readout(self):
+            """psd() of every channel of the job on rank 0: ONE ncclAllGather of accumulator rows + bookkeeping"""
+            return self.g.psd_all(world, MergeOpts())
+
+    def timed(ch, src, steps, warmup):
         for _ in range(warmup):
-            cascade.process(src)
-            gather_readout(cascade.psd(MergeOpts())[0])
-        cascade.profile_read()
+            ch.process(src)
+            ch.readout()
+        ch.c.profile_read()
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record(stream)
         for _ in range(steps):
-            cascade.process(src)
-            p, b = cascade.psd(MergeOpts())
-            gather_readout(p)
+            ch.process(src)
+            res = ch.readout()
         e1.record(stream)
         barrier()
         ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
         if world > 1:
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-        return float(ms.item()), p, b
+        return float(ms.item()), res
 
     # ---- device-resident run (value) with per-kernel event timing and clock sampling ----
     # Timed region: K back-to-back process() calls on the resident 200e6-sample buffer + ONE final
     # psd() readout (SURVEY.md 8d: "process + final psd() readout, steady state"; the reference's GUI
     # reads out at frame rate, i.e. every few 1e6 samples of a 200 MS/s stream, not every batch).
     # `value_readout_every_step` repeats the measurement with a psd() readout after every step.
-    def device_run(readout_every_step):
-        c = PsdCascade(N_FFT, device=local, stream=stream.cuda_stream or 1)
-        c.profile_enable(True)
+    def device_run(readout_every_step, profile=False):
+        ch = Channel()
+        ch.c.profile_enable(profile)
         for _ in range(args.warmup):
-            c.process(x)
-            gather_readout(c.psd(MergeOpts())[0])
-        c.profile_read()
+            ch.process(x)
+            ch.readout()
+        ch.c.profile_read()
         barrier()
         sampler = ClockSampler(local)
         sampler.start()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record(stream)
         for _ in range(args.steps):
-            c.process(x)
+            ch.process(x)
             if readout_every_step:
-                p, b = c.psd(MergeOpts())
-                gather_readout(p)
+                res = ch.readout()
         if not readout_every_step:
-            p, b = c.psd(MergeOpts())
-            gather_readout(p)
+            res = ch.readout()
         e1.record(stream)
         barrier()
         clocks = sampler.stop()
         ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
         if world > 1:
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-        prof, launches = c.profile_read()
+        prof, launches = ch.c.profile_read()
+        p, b = res[0] if rank == 0 else (None, None)
         return float(ms.item()), prof, launches, clocks, p, b
 
     ms_rs, _, _, _, _, _ = device_run(True)
-    ms, prof, launches, clocks, p, b = device_run(False)
+    ms, _, launches, clocks, p, b = device_run(False)
+    # the same loop once more with every kernel launch bracketed by CUDA events (per-kernel times for the roofline;
+    # the event records cost a few percent, so the headline comes from the unprofiled run above)
+    ms_prof, prof, _, _, _, _ = device_run(False, profile=True)
     value = world * SAMPLES_PER_STEP * args.steps / (ms * 1e-3) / 1e6
     value_rs = world * SAMPLES_PER_STEP * args.steps / (ms_rs * 1e-3) / 1e6
 
     # ---- sustained: the same loop for >= 2 s of device time (SURVEY.md 8d), clocks + power sampled throughout ----
     def sustained(seconds=2.0):
-        c = PsdCascade(N_FFT, device=local, stream=stream.cuda_stream or 1)
+        c = Channel()
         for _ in range(3):
             c.process(x)
-        c.psd(MergeOpts())
+        c.readout()
         barrier()
         k = max(args.steps, int(seconds / (ms / args.steps * 1e-3)) + 1)
         sampler = ClockSampler(local, power=True)
@@ -293,9 +316,8 @@ def run_ours(args):
         for i in range(k):
             c.process(x)
             if i % 64 == 63:
-                c.sync()  # bound the launch queue; a sync every 64 steps (56 ms) costs nothing measurable
-        p_, b_ = c.psd(MergeOpts())
-        gather_readout(p_)
+                c.g.sync()  # bound the launch queue; a sync every 64 steps (56 ms) costs nothing measurable
+        c.readout()
         e1.record(stream)
         barrier()
         ck = sampler.stop()
@@ -307,11 +329,12 @@ def run_ours(args):
                 "clocks": ck}
 
     sus = sustained()
+    tc = timechunk_record(new_group, barrier, rank, world, dist, dev)
 
     # ---- end-to-end run: host pinned input, H2D inside the timed region, spectra read back ----
-    c2 = PsdCascade(N_FFT, device=local, stream=stream.cuda_stream or 1)
+    c2 = Channel()
     e2e_steps = max(1, min(args.steps, 5))
-    ms2, p2, b2 = timed(c2, xh, e2e_steps, min(args.warmup, 2))
+    ms2, _ = timed(c2, xh, e2e_steps, min(args.warmup, 2))
     e2e_value = world * SAMPLES_PER_STEP * e2e_steps / (ms2 * 1e-3) / 1e6
 
     if rank != 0:
@@ -332,7 +355,7 @@ def run_ours(args):
                           "note": "explanatory: the kernel is FP32 / latency bound, not HBM bound"},
             "launches": int(k_launches), "avg_launch_ms": (k_ms / k_launches) if k_launches else None,
             "algorithmic_bytes_per_launch": BYTES_PER_SAMPLE * k_units / max(k_launches, 1),
-            "share_of_step": k_ms / ms,
+            "share_of_step": k_ms / ms_prof, "profiled_ms_per_step": ms_prof / args.steps,
             "other_kernels_ms": {k: v[0] for k, v in prof.items() if k != "psd_stage0"},
             "whole_step_frac": BYTES_PER_SAMPLE * SAMPLES_PER_STEP * args.steps / (ms * 1e-3) / 1e9 / peak}
     d2h = sum(len(k.bins) for k in b if k.include) * 4
@@ -341,7 +364,8 @@ def run_ours(args):
            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
            "config": config_dict(world),
            "cache": "inputs (800 MB per step) larger than the 126 MB L2",
-           "value_readout_every_step": value_rs, "sustained_2s": sus,
+           "value_readout_every_step": value_rs, "sustained_2s": sus, "timechunk": tc,
+           "readout_collective": "one ncclAllGather of accumulator rows + bookkeeping inside libsspsd.so (sspsd_group_psd_all)",
            "roofline": roof, "clocks": clocks, "gpu_launches": int(launches), "parity_note": PARITY_NOTE,
            "e2e": {"value": e2e_value, "unit": "MS/s", "h2d_bytes_per_step": SAMPLES_PER_STEP * 4 * world,
                    "d2h_bytes_per_step": d2h * world, "steps": e2e_steps, "ms_per_step": ms2 / e2e_steps}}
@@ -353,9 +377,58 @@ def run_ours(args):
         n512["published"] = ">200 MS/s on one (Skylake) core at N=512 (reference README.md:11, src/psd.rs:550)"
         out["cpu_baseline_n512"] = n512
         out["e2e_small_calls"] = small_calls()
-    print(json.dumps(out))
+    emit(out)
     if world > 1:
         dist.destroy_process_group()
+
+
+def timechunk_record(new_group, barrier, rank, world, dist, dev):
+    """BASELINE config 5 beside the headline: ONE 4.8e9-sample capture cut into `world` time chunks (strong scaling),
+    every rank generating its range of the counter-based stream on its device; one NCCL sum-reduction of rows +
+    counts + tail slices at readout, all inside the library (sspsd_group_time_*).  The merged spectrum is checked
+    against the float64 truth rows committed in tests/golden/fullsize_c5_default.npz (tools/gen_golden_fullsize.py)."""
+    import numpy as np
+    import torch
+    from stabilizer_stream_b200 import ShardMode
+    total = 4_800_000_000
+    g = new_group(ShardMode.TIME)
+    times = []
+    for it in range(3):
+        g.time_plan(total)          # creates + positions the handles (allocations): outside the timed region
+        barrier()
+        t0 = time.perf_counter()
+        g.time_process_noise(0, 0x7654321)
+        g.time_finish()             # collective; synchronises
+        p, b = g.psd(0)
+        torch.cuda.synchronize(dev)
+        dt = time.perf_counter() - t0
+        t = torch.tensor([dt], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        times.append(float(t.item()))
+    out = {"workload": "4.8e9-sample capture, N=4096, time-chunked over %d GPU(s) (strong scaling)" % world,
+           "samples": total, "seconds": min(times), "value": total / min(times) / 1e6, "unit": "MS/s",
+           "n_local_stages": g.time_chunk(0).n_local, "reduce": g.info()["reduce"] if world > 1 else "none",
+           "timing": "host clock around process + exchange + psd(), max over ranks, best of 3 (input generated on the device)"}
+    if rank == 0:
+        out["stage_counts"] = [k.count for k in reversed(b)]
+        gold = os.path.join(ROOT, "tests", "golden", "fullsize_c5_default.npz")
+        if os.path.exists(gold):
+            z = np.load(gold)
+            rows64, counts = z["rows64"], z["counts"]
+            truth = []
+            for k in b:
+                stage = 0
+                while 8 ** stage < k.decimation:
+                    stage += 1
+                if k.include:
+                    gain = (N_FFT // 2) * float(counts[stage]) * 1.5 * 0.25
+                    truth.append(rows64[stage][k.bins.start:k.bins.stop] / (gain * k.decimation))
+            truth = np.concatenate(truth)
+            floor = 1e-5 * np.median(truth)
+            out["max_rel_vs_f64"] = float(np.max(np.maximum(np.abs(p - truth) - floor, 0) / truth)) if truth.size == p.size else None
+            out["counts_match_golden"] = [k.count for k in reversed(b)] == [int(c) for c in counts]
+    return out
 
 
 def small_calls():
@@ -376,7 +449,26 @@ def small_calls():
     return res
 
 
+_REAL_STDOUT = None
+
+
+def emit(obj):
+    """the ONE JSON line of the contract, on the process's real stdout"""
+    line = (json.dumps(obj) + "\n").encode()
+    if _REAL_STDOUT is None:
+        sys.stdout.write(line.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_REAL_STDOUT, line)
+
+
 def main():
+    # Libraries print to stdout behind our back (NCCL announces its version at the first communicator when
+    # NCCL_DEBUG=VERSION/WARN is set in the environment): everything but the result line goes to stderr.
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)

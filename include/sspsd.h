@@ -228,7 +228,7 @@ enum { SSPSD_REDUCE_NCCL = 0, SSPSD_REDUCE_P2P = 1 };
 int32_t sspsd_group_create(const sspsd_config *cfg, const int32_t *devices, uint32_t n_devices, int32_t shard_mode,
                            sspsd_group **out);
 int32_t sspsd_group_unique_id(uint8_t id[SSPSD_GROUP_ID_BYTES]);
-/* cfg->device = this rank's device */
+/* cfg->device = this rank's device, cfg->stream = the stream the rank's work is ordered on (NULL: private) */
 int32_t sspsd_group_create_rank(const sspsd_config *cfg, const uint8_t id[SSPSD_GROUP_ID_BYTES], uint32_t rank,
                                 uint32_t n_ranks, int32_t shard_mode, sspsd_group **out);
 void sspsd_group_destroy(sspsd_group *g);
@@ -247,6 +247,9 @@ int32_t sspsd_group_sync(sspsd_group *g);
 int32_t sspsd_group_process_f32(sspsd_group *g, uint32_t channel, const float *x, size_t n, int32_t mem);
 /* where a channel lives: device = -1 if another process owns it */
 int32_t sspsd_group_channel_device(const sspsd_group *g, uint32_t channel, int32_t *device, uint32_t *rank);
+/* the cascade of a channel this process owns (borrowed: valid until the group is destroyed; NULL if the channel has not
+ * received a sample yet or lives elsewhere) -- for the per-handle calls the group does not wrap (profile hooks, clone) */
+int32_t sspsd_group_channel_handle(sspsd_group *g, uint32_t channel, sspsd_cascade **out);
 /* psd() of one channel (single-process channel groups), or of THE stream of a time-chunked group after
  * sspsd_group_time_finish (result on the process that holds rank 0; lengths 0 elsewhere) */
 int32_t sspsd_group_psd(sspsd_group *g, uint32_t channel, const sspsd_merge_opts *opts, float *p, size_t *p_len,

@@ -146,6 +146,7 @@ PROTOTYPES = {
     "sspsd_group_sync": (_i32, [_vp]),
     "sspsd_group_process_f32": (_i32, [_vp, C.c_uint32, _vp, _sz, _i32]),
     "sspsd_group_channel_device": (_i32, [_vp, C.c_uint32, C.POINTER(_i32), C.POINTER(C.c_uint32)]),
+    "sspsd_group_channel_handle": (_i32, [_vp, C.c_uint32, C.POINTER(_vp)]),
     "sspsd_group_psd": (_i32, [_vp, C.c_uint32, C.POINTER(MergeOptsC), _vp, _psz, C.POINTER(BreakC), _psz]),
     "sspsd_group_psd_all": (_i32, [_vp, C.c_uint32, C.POINTER(MergeOptsC), _vp, _sz, _psz, C.POINTER(BreakC), _sz, _psz]),
     "sspsd_time_plan": (_i32, [C.c_uint32, _i32, _i32, C.c_uint64, C.c_uint32, C.c_uint32, C.c_uint32,

@@ -338,6 +338,10 @@ struct sspsd_group {
     uint8_t* d_all = nullptr;
     uint8_t* h_all = nullptr;
     size_t rec_cap = 0, all_cap = 0;
+    cudaStream_t gather_stream = nullptr;
+    std::vector<sspsd_source*> noise_src;  // per local rank, for sspsd_group_time_process_noise
+    int64_t noise_exp = 0;
+    uint64_t noise_seed = 0;
 
     uint32_t n_local() const { return (uint32_t)devices.size(); }
     bool is_root() const { return first_rank == 0; }
@@ -546,6 +550,7 @@ int32_t sspsd_group_create_rank(const sspsd_config* cfg, const uint8_t id[SSPSD_
         return SSPSD_EINVAL;
     }
     g->multi_process = true;
+    g->cfg.stream = cfg->stream;  // one rank, one device: the caller may order the rank's work on its own stream
     g->n_ranks = n_ranks;
     g->first_rank = rank;
     g->devices.push_back(cfg->device);
@@ -573,6 +578,7 @@ int32_t sspsd_group_create_rank(const sspsd_config* cfg, const uint8_t id[SSPSD_
 void sspsd_group_destroy(sspsd_group* g)
 {
     if (!g) return;
+    for (auto* s : g->noise_src) sspsd_source_destroy(s);
     for (auto* c : g->chan) sspsd_cascade_destroy(c);
     for (auto* c : g->tc) sspsd_cascade_destroy(c);
     for (uint32_t l = 0; l < g->d_buf.size(); ++l) {
@@ -587,6 +593,7 @@ void sspsd_group_destroy(sspsd_group* g)
         cudaFree(g->d_rec);
         cudaFree(g->d_all);
         if (g->h_all) cudaFreeHost(g->h_all);
+        if (g->gather_stream) cudaStreamDestroy(g->gather_stream);
     }
     for (uint32_t l = 0; l < g->comms.size(); ++l)
         if (g->comms[l]) nccl().CommDestroy(g->comms[l]);
@@ -682,6 +689,13 @@ int32_t sspsd_group_channel_device(const sspsd_group* g, uint32_t channel, int32
     if (rank) *rank = r;
     const int l = g->local_of(r);
     if (device) *device = l >= 0 ? g->devices[l] : -1;
+    return SSPSD_OK;
+}
+
+int32_t sspsd_group_channel_handle(sspsd_group* g, uint32_t channel, sspsd_cascade** out)
+{
+    if (!g || !out || g->mode != SSPSD_SHARD_CHANNELS) return SSPSD_EINVAL;
+    *out = channel < g->chan.size() ? g->chan[channel] : nullptr;
     return SSPSD_OK;
 }
 
@@ -787,8 +801,8 @@ int32_t sspsd_group_psd_all(sspsd_group* g, uint32_t n_channels, const sspsd_mer
         g->rec_cap = mine;
         g->all_cap = all;
     }
-    // the gather runs on the first local channel's stream (or the legacy stream if this rank owns none)
-    cudaStream_t s = nullptr;
+    if (!g->gather_stream) SSPSD_CUDA(cudaStreamCreateWithFlags(&g->gather_stream, cudaStreamNonBlocking));
+    cudaStream_t s = g->gather_stream;
     SSPSD_CUDA(cudaMemsetAsync(g->d_rec, 0, mine, s));
     std::vector<uint64_t> book((size_t)per_rank * (SSPSD_MAX_STAGES * 4 + 2), 0);
     for (uint32_t k = 0; k < per_rank; ++k) {
@@ -845,11 +859,13 @@ int32_t sspsd_group_time_plan(sspsd_group* g, uint64_t total, uint32_t n_local_s
     }
     const Geo geo = geo_of(g->cfg);
     if (n_local_stages == 0) n_local_stages = auto_n_local(total, g->n_ranks, geo);
-    // destroy a previous capture's state
-    for (auto* c : g->tc) sspsd_cascade_destroy(c);
-    g->tc.clear();
+    // a previous capture's handles are reset and reused (their device buffers stay allocated)
     int rc = ensure_time_cascades(g);
     if (rc) return rc;
+    for (auto* c : g->tc) {
+        rc = c->c.reset();
+        if (rc) return rc;
+    }
     g->total = total;
     g->n_local_stages = n_local_stages;
     g->finished = false;
@@ -920,22 +936,25 @@ int32_t sspsd_group_time_process_noise(sspsd_group* g, int64_t exponent, uint64_
         set_error("no plan (call sspsd_group_time_plan first)");
         return SSPSD_EINVAL;
     }
-    // every local rank generates its own range of the counter-based stream on its own device
+    // every local rank generates its own range of the counter-based stream on its own device; generation and
+    // consumption are ordered on the rank's stream, nothing is waited for here (the sources live with the group)
+    if (g->noise_src.size() != g->n_local() || g->noise_exp != exponent || g->noise_seed != seed) {
+        for (auto* s : g->noise_src) sspsd_source_destroy(s);
+        g->noise_src.assign(g->n_local(), nullptr);
+        for (uint32_t l = 0; l < g->n_local(); ++l) {
+            int rc = sspsd_source_create(SSPSD_SOURCE_NOISE, exponent, seed, g->devices[l], (void*)g->tc[l]->c.stream(),
+                                         &g->noise_src[l]);
+            if (rc) return rc;
+        }
+        g->noise_exp = exponent;
+        g->noise_seed = seed;
+    }
     for (uint32_t l = 0; l < g->n_local(); ++l) {
         const sspsd_time_chunk& pl = g->plan[g->first_rank + l];
-        sspsd_source* src = nullptr;
-        int rc = sspsd_source_create(SSPSD_SOURCE_NOISE, exponent, seed, g->devices[l], (void*)g->tc[l]->c.stream(), &src);
+        int rc = sspsd_source_seek(g->noise_src[l], pl.feed_lo + g->fed[l]);
         if (rc) return rc;
-        rc = sspsd_source_seek(src, pl.feed_lo + g->fed[l]);
         const uint64_t n = pl.feed_hi - pl.feed_lo - g->fed[l];
-        if (!rc) rc = sspsd_cascade_process_source(g->tc[l], src, (size_t)n);
-        if (!rc) {
-            // the source's scratch buffer is read asynchronously by the cascade's kernels
-            rc = g->tc[l]->c.flush();
-            DevGuard dg(g->devices[l]);
-            if (!rc && !sspsd::cuda_ok(cudaStreamSynchronize(g->tc[l]->c.stream()), "cudaStreamSynchronize")) rc = SSPSD_ECUDA;
-        }
-        sspsd_source_destroy(src);
+        rc = sspsd_cascade_process_source(g->tc[l], g->noise_src[l], (size_t)n);
         if (rc) return rc;
         g->fed[l] += n;
     }

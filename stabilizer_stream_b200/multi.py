@@ -1,4 +1,10 @@
-"""Multi-GPU host logic (one process per GPU, torch.distributed; NCCL on GPUs, gloo in the CPU tests).
+"""Multi-GPU host logic in Python (one process per GPU, torch.distributed; NCCL on GPUs, gloo in the CPU tests).
+
+Since round 2 the product path is the library's own sspsd_group_* API (csrc/sspsd_group.cu; `Group` in psd.py):
+planner, seek / window, the single NCCL reduction and the deep stages on rank 0 run inside libsspsd.so, and
+bench.py / tools/run_configs.py call that.  This module stays as the executable specification the C++ planner is
+tested against (tests/test_group_plan_cpu.py) and as the gloo-testable model of the exchange
+(tests/test_multi_rank_cpu.py); `time_chunked_psd` below is the round-1 orchestration of the same steps.
 
 The reference is single threaded and loops over its traces sequentially (src/bin/psd.rs:174-182);
 two partitionings fall out of the cascade's structure:

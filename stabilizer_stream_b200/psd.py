@@ -673,6 +673,13 @@ class Receiver:
             L._lib.sspsd_receiver_destroy(h)
 
 
+class _BorrowedCascade(PsdCascade):
+    """a cascade handle owned by a Group: never destroyed from Python"""
+
+    def __del__(self):
+        self._h = None
+
+
 class ShardMode(enum.IntEnum):
     CHANNELS = 0
     TIME = 1
@@ -712,10 +719,10 @@ class Group:
                                              Group.unique_id() on rank 0, broadcast by the caller"""
 
     def __init__(self, n=512, devices=None, mode=ShardMode.CHANNELS, rank=None, n_ranks=None, unique_id=None, device=0,
-                 hbf=Hbf.TAPS_140, max_batch=0, host_stage=0):
+                 hbf=Hbf.TAPS_140, max_batch=0, host_stage=0, stream=None):
         self.n = n
         cfg = _config(n, Window.HANN, hbf, device, 0, max_batch, host_stage)
-        cfg.stream = None
+        cfg.stream = stream  # one-rank-per-process groups only; None = private streams
         h = C.c_void_p()
         if rank is None:
             devices = list(devices if devices is not None else [0])
@@ -764,6 +771,17 @@ class Group:
 
     def process_raw(self, channel, ptr, n, mem):
         L.check(L.lib().sspsd_group_process_f32(self._h, channel, ptr, n, mem))
+
+    def channel_cascade(self, channel):
+        """the PsdCascade of a channel this process owns (borrowed from the group), or None"""
+        h = C.c_void_p()
+        L.check(L.lib().sspsd_group_channel_handle(self._h, channel, C.byref(h)))
+        if not h.value:
+            return None
+        c = PsdCascade.__new__(PsdCascade)
+        c.n, c.device, c._h, c._borrowed = self.n, self.channel_device(channel)[0], h, self
+        c.__class__ = _BorrowedCascade
+        return c
 
     def channel_device(self, channel):
         d, r = C.c_int32(), C.c_uint32()

@@ -235,6 +235,71 @@ def config5(dev, total, n_local, check, preset=False):
     return out
 
 
+def config5_group(dev, total, n_local, check, preset=False):
+    """config 5 through the library's own multi-GPU plumbing (sspsd_group_time_*): planner, seek / window, the
+    ONE NCCL reduction and the deep stages on rank 0 all run inside libsspsd.so; Python only feeds the samples."""
+    import torch.distributed as dist
+    from stabilizer_stream_b200 import AvgOpts, Detrend, Group, MergeOpts, PsdCascade, ShardMode, _lib, multi
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    n = 4096
+    avg = AvgOpts(limit=999, count=2 ** 32 - 2) if preset else None
+    ids = [Group.unique_id() if (rank == 0 and world > 1) else None]
+    if world > 1:
+        dist.broadcast_object_list(ids, src=0)
+    g = Group(n, rank=rank, n_ranks=world, unique_id=ids[0], device=dev.index, mode=ShardMode.TIME)
+    if preset:
+        g.set_detrend(Detrend.MEAN)
+        g.set_avg(avg)
+    g.time_plan(total, n_local)
+    ch = g.time_chunk(rank)
+    lo, hi = ch.feed_lo, ch.feed_hi
+    parts = []
+    feed_stream(lo, hi, lambda t: parts.append(t.clone()), dev)   # the rank's share, generated into HBM first (untimed)
+    xs = torch.cat(parts)
+    del parts
+    torch.cuda.synchronize()
+
+    def one_pass():
+        g.time_plan(total, n_local)
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        L = _lib
+        L.check(L.lib().sspsd_group_time_process_f32(g._h, rank, xs.data_ptr(), xs.numel(), L.MEM_DEVICE))
+        t1 = time.perf_counter()
+        g.time_finish()
+        p, b = g.psd(0)
+        t2 = time.perf_counter()
+        if world > 1:
+            dist.barrier()
+        return p, b, time.perf_counter() - t0, {"enqueue": t1 - t0, "finish+psd": t2 - t1}
+
+    one_pass()                      # warm-up: NCCL connections, buffers at their final size
+    p, b, dt, tim = one_pass()
+    if rank != 0:
+        return None
+    counts = [k.count for k in reversed(b)]
+    want = [min(s[1], multi.stage_avg(avg, i) + 1) for i, s in enumerate(multi.stream_state(total, n, n // 2, multi.DRAIN[1]))]
+    flat = all(bool(np.all(np.abs(p[k.start:k.start + len(k.bins)] * 0.5 - 1.0) < 10.0 / np.sqrt(k.count)))
+               for k in b if k.include and k.count >= 20)
+    out = {"config": 5, "orchestration": "libsspsd sspsd_group_time_*", "preset": bool(preset), "samples": total, "world": world,
+           "n_local": ch.n_local, "reduce": g.info()["reduce"], "stage_counts": counts, "counts_match_closed_form": counts == want,
+           "flat_10sigma": flat, "wall_s": dt, "MSps": total / dt / 1e6, "phases_s_rank0": tim,
+           "halo_overhead": (hi - lo) * world / total - 1 if world > 1 else 0.0, "bins": int(p.size)}
+    if check and world > 1:
+        seq = PsdCascade(n, device=dev.index)
+        if preset:
+            seq.set_detrend(Detrend.MEAN)
+            seq.set_avg(avg)
+        feed_stream(0, total, seq.process, dev)
+        ps, bs = seq.psd(MergeOpts())
+        out["max_rel_diff_vs_sequential"] = float(np.max(np.abs(p - ps) / np.maximum(ps, 1e-30)))
+        out["breaks_equal"] = [(k.count, k.pending, k.processed) for k in b] == [(k.count, k.pending, k.processed) for k in bs]
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--config", type=int, required=True)
@@ -242,6 +307,8 @@ def main():
     ap.add_argument("--n-local", type=int, default=5)
     ap.add_argument("--check", action="store_true")
     ap.add_argument("--preset", action="store_true")
+    ap.add_argument("--python-orchestration", action="store_true",
+                    help="config 5 through stabilizer_stream_b200/multi.py (round-1 path) instead of sspsd_group_*")
     a = ap.parse_args()
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
@@ -250,7 +317,7 @@ def main():
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=dev)
     r = {1: lambda: config1(dev), 2: lambda: config2(dev), 3: lambda: config3(dev),
-         5: lambda: config5(dev, int(a.total), a.n_local, a.check, a.preset)}[a.config]()
+         5: lambda: (config5 if a.python_orchestration else config5_group)(dev, int(a.total), a.n_local, a.check, a.preset)}[a.config]()
     if r is not None:
         print(json.dumps(r))
     if int(os.environ.get("WORLD_SIZE", "1")) > 1:
