@@ -88,7 +88,12 @@ typedef struct {
                             that their kernels get full-size grids instead of ~20 small dependent launches per batch
                             (fewer launches; measured neutral for throughput); every call that observes state runs
                             what is pending first, results do not depend on it (0 or 1 = run them with every batch) */
+    uint32_t flags;      /* SSPSD_FLAG_* */
+    uint32_t _pad;
 } sspsd_config;
+/* accumulate |X|^2 through per-CTA partial rows summed in fixed order instead of float atomics: readouts become
+ * bit-reproducible from run to run (one extra small kernel per stage and batch) */
+#define SSPSD_FLAG_DETERMINISTIC 1u
 
 /* AvgOpts, src/psd.rs:360-376 */
 typedef struct {

@@ -16,6 +16,8 @@ struct Config {
     max_batch: u64,
     host_stage: u64,
     deep_defer: u64,
+    flags: u32,
+    _pad: u32,
 }
 #[repr(C)]
 #[derive(Clone, Copy)]

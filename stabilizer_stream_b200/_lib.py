@@ -12,6 +12,7 @@ LIB_PATH = os.path.join(_HERE, "libsspsd.so")
 
 OK, EINVAL, EUNIMPLEMENTED, ECUDA, ENOMEM, EHEADER, EFORMAT, ESIZE, EBATCHES, ESHORT, ENCCL, EIO = range(12)
 MEM_HOST, MEM_DEVICE = 0, 1
+FLAG_DETERMINISTIC = 1
 MAX_STAGES = 16
 MAX_TRACES = 4
 
@@ -22,7 +23,7 @@ STATUS_NAMES = {0: "OK", 1: "EINVAL", 2: "EUNIMPLEMENTED", 3: "ECUDA", 4: "ENOME
 class Config(C.Structure):
     _fields_ = [("n_fft", C.c_uint32), ("window", C.c_int32), ("hbf", C.c_int32), ("device", C.c_int32),
                 ("stream", C.c_void_p), ("max_batch", C.c_uint64), ("host_stage", C.c_uint64),
-                ("deep_defer", C.c_uint64)]
+                ("deep_defer", C.c_uint64), ("flags", C.c_uint32), ("_pad", C.c_uint32)]
 
 
 class AvgOptsC(C.Structure):

@@ -278,6 +278,8 @@ Cascade::~Cascade()
     cudaFree(d_in_[1]);
     cudaFree(d_sink_);
     cudaFree(d_tail_);
+    cudaFree(d_part_[0]);
+    cudaFree(d_part_[1]);
     if (h_stage_[0]) cudaFreeHost(h_stage_[0]);
     if (h_stage_[1]) cudaFreeHost(h_stage_[1]);
     if (h_acc_) cudaFreeHost(h_acc_);
@@ -532,10 +534,13 @@ int Cascade::launch_psd(size_t i, const StreamSrc& src, uint64_t k0, uint64_t ns
         p.g_first = g_first;
         p.g_s = g_s;
         int grid = (int)((nseg + p.T - 1) / p.T);
+        int rcp = prepare_partials(i, grid * R16::G, &p);
+        if (rcp) return rcp;
         prof_begin(i == 0 ? SSPSD_PROF_PSD_STAGE0 : SSPSD_PROF_PSD_DEEP, nseg * (uint64_t)hop_, psd_stream(i));
         psd_stage_kernel_ring<<<grid, R16::NT, stage_ring_smem_bytes(p.T), psd_stream(i)>>>(p);
         prof_end(psd_stream(i));
-        return cuda_ok(cudaGetLastError(), "psd_stage_kernel_ring launch") ? SSPSD_OK : SSPSD_ECUDA;
+        if (!cuda_ok(cudaGetLastError(), "psd_stage_kernel_ring launch")) return SSPSD_ECUDA;
+        return reduce_partials(i, grid * R16::G, p);
     }
     const bool tiled_r16 = log2n_ == 12 && k2_variant_ >= 1;
     if (tiled_r16) {
@@ -560,10 +565,47 @@ int Cascade::launch_psd(size_t i, const StreamSrc& src, uint64_t k0, uint64_t ns
     long long ntiles = ((long long)nseg + p.T - 1) / p.T;
     p.tpc = tiled_r16 ? 1 : (int)std::max<long long>(1, (ntiles + 2ll * num_sms_ - 1) / (2ll * num_sms_));
     int grid = (int)((ntiles + p.tpc - 1) / p.tpc);
+    const int groups = tiled_r16 ? R16::G : std::max(1, nt_ / (int)(n_ / 16));
+    int rc = prepare_partials(i, grid * groups, &p);
+    if (rc) return rc;
     prof_begin(i == 0 ? SSPSD_PROF_PSD_STAGE0 : SSPSD_PROF_PSD_DEEP, nseg * (uint64_t)hop_, psd_stream(i));
-    int rc = launch_stage((int)log2n_, k2_variant_ >= 1, p, grid, psd_stream(i));
+    rc = launch_stage((int)log2n_, k2_variant_ >= 1, p, grid, psd_stream(i));
     prof_end(psd_stream(i));
-    return rc;
+    if (rc) return rc;
+    return reduce_partials(i, grid * groups, p);
+}
+
+// Deterministic accumulation (sspsd_config::flags & SSPSD_FLAG_DETERMINISTIC): the PSD kernel writes one
+// partial row per (CTA, group) and reduce_partials_kernel adds them to the stage's accumulator in row order, so a
+// readout is bit-reproducible from run to run (the default flush is one atomicAdd per bin per thread).
+int Cascade::prepare_partials(size_t i, int rows, StageParams* p)
+{
+    p->part = nullptr;
+    p->part_stride = 0;
+    if (!(cfg_.flags & SSPSD_FLAG_DETERMINISTIC)) return SSPSD_OK;
+    // one buffer per PSD stream (stage 0 on stream_, the deep stages' kernels are ordered on their own stream)
+    const int which = psd_stream(i) == stream_ ? 0 : 1;
+    const size_t need = (size_t)rows * acc_stride_;
+    if (need > part_cap_[which]) {
+        SSPSD_CUDA(cudaStreamSynchronize(psd_stream(i)));
+        if (d_part_[which]) SSPSD_CUDA(cudaFree(d_part_[which]));
+        d_part_[which] = nullptr;
+        SSPSD_CUDA(cudaMalloc(&d_part_[which], need * sizeof(float)));
+        part_cap_[which] = need;
+    }
+    p->part = d_part_[which];
+    p->part_stride = (int)acc_stride_;
+    return SSPSD_OK;
+}
+
+int Cascade::reduce_partials(size_t i, int rows, const StageParams& p)
+{
+    if (!p.part) return SSPSD_OK;
+    const int nb = (int)(n_ / 2 + 1);
+    prof_begin(SSPSD_PROF_OTHER, 0, psd_stream(i));
+    reduce_partials_kernel<<<(nb + 127) / 128, 128, 0, psd_stream(i)>>>(p.acc, p.part, rows, p.part_stride, nb);
+    prof_end(psd_stream(i));
+    return cuda_ok(cudaGetLastError(), "reduce_partials_kernel launch") ? SSPSD_OK : SSPSD_ECUDA;
 }
 
 int Cascade::launch_decim(size_t i, const StreamSrc& src, uint64_t m0, uint64_t m1, float* out_fresh,

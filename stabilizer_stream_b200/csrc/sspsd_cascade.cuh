@@ -17,6 +17,7 @@
 
 namespace sspsd {
 
+struct StageParams;
 void set_error(const std::string& msg);
 const char* last_error();
 int hbf_info(int hbf, uint32_t* drain, uint32_t* halo);
@@ -105,6 +106,8 @@ private:
     int launch_psd(size_t i, const StreamSrc& src, uint64_t k0, uint64_t nseg, int jb, float g_first, float g_s);
     int launch_decim(size_t i, const StreamSrc& src, uint64_t m0, uint64_t m1, float* out_fresh,
                      long long out_split);
+    int prepare_partials(size_t i, int rows, struct StageParams* p);
+    int reduce_partials(size_t i, int rows, const struct StageParams& p);
     cudaStream_t stage_stream(size_t i) const { return (i < deep_from_ || !deep_stream_) ? stream_ : deep_stream_; }
     // stream of stage i's PSD kernel (and its EWMA pre-scale): beside the decimation chain for the deep stages
     cudaStream_t psd_stream(size_t i) const { return (i >= deep_from_ && psd_stream_) ? psd_stream_ : stage_stream(i); }
@@ -188,6 +191,8 @@ private:
     int in_buf_ = 0;
     float* h_acc_ = nullptr;  // pinned readback buffer
     // sink of the single-stage API
+    float* d_part_[2] = {nullptr, nullptr};  // deterministic mode: partial rows (stage-0 stream, deep PSD stream)
+    size_t part_cap_[2] = {0, 0};
     float* d_sink_ = nullptr;
     size_t sink_cap_ = 0, sink_len_ = 0;
 };

@@ -26,12 +26,44 @@ struct StageParams {
     const float2* twM; // M entries: exp(-2 pi i q / M)
     const float2* twN; // M entries: exp(-2 pi i k / N)
     float* acc;        // N/2+1 accumulators of this stage
+    float* part;       // deterministic mode: per-(CTA, group) partial rows of part_stride floats (else nullptr)
+    int part_stride;
     // EWMA weights (psd.rs:218-233): segment j of this launch is scaled by
     //   g_s^(nseg-1-max(j,jb)) * (j < jb && jb < nseg ? g_first : 1);  boxcar: jb >= nseg
     int jb;
     float g_first;
     float g_s;
 };
+
+// Flush of a thread's register accumulators.  Default: one atomicAdd per owned bin (order of the ~300 CTAs is
+// arbitrary, so the f32 sum is not bit-reproducible from run to run).  Deterministic mode:
+// every (CTA, group) writes its own partial row -- each bin of a row has exactly one owner thread -- and
+// reduce_partials_kernel adds the rows to the accumulator in row order.
+struct AccSink {
+    float* acc;
+    float* row;  // nullptr: atomics
+    __device__ __forceinline__ void add(int k, float v) const
+    {
+        if (row)
+            row[k] = v;
+        else
+            atomicAdd(&acc[k], v);
+    }
+};
+__device__ __forceinline__ AccSink acc_sink(const float* /*unused*/, float* acc, float* part, int part_stride, int row_index)
+{
+    return AccSink{acc, part ? part + (size_t)row_index * part_stride : nullptr};
+}
+
+// acc[k] += sum over rows (in row order, f64) of part[r][k]
+__global__ void reduce_partials_kernel(float* __restrict__ acc, const float* __restrict__ part, int nrows, int stride, int nbins)
+{
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= nbins) return;
+    double s = 0.0;
+    for (int r = 0; r < nrows; ++r) s += (double)part[(size_t)r * stride + k];
+    acc[k] = (float)((double)acc[k] + s);
+}
 
 template <int TPS, int NT>
 __device__ __forceinline__ void group_sync(int group)
@@ -343,24 +375,25 @@ psd_stage_kernel(const StageParams p)
     if (tid == 0 && tl + 2 < tile1) issue_tile(tl + 2);
     }  // tiles
 
-    // ---- flush: one atomic per owned bin ----
+    // ---- flush: one atomic (or partial-row store) per owned bin ----
+    const AccSink sink = acc_sink(nullptr, p.acc, p.part, p.part_stride, blockIdx.x * G + group);
     if (j != 0) {
 #pragma unroll
         for (int t = 0; t < 4; ++t) {
             int k = kA + K * t;
-            atomicAdd(&p.acc[k], acc[2 * t]);
-            atomicAdd(&p.acc[M - k], acc[2 * t + 1]);
+            sink.add(k, acc[2 * t]);
+            sink.add(M - k, acc[2 * t + 1]);
         }
     } else {
-        atomicAdd(&p.acc[0], acc[0]);
-        atomicAdd(&p.acc[M], acc[1]);
-        atomicAdd(&p.acc[K], acc[2]);
-        atomicAdd(&p.acc[3 * K], acc[3]);
-        atomicAdd(&p.acc[2 * K], accx);
-        atomicAdd(&p.acc[K / 2], acc[4]);
-        atomicAdd(&p.acc[M - K / 2], acc[5]);
-        atomicAdd(&p.acc[K / 2 + K], acc[6]);
-        atomicAdd(&p.acc[M - K / 2 - K], acc[7]);
+        sink.add(0, acc[0]);
+        sink.add(M, acc[1]);
+        sink.add(K, acc[2]);
+        sink.add(3 * K, acc[3]);
+        sink.add(2 * K, accx);
+        sink.add(K / 2, acc[4]);
+        sink.add(M - K / 2, acc[5]);
+        sink.add(K / 2 + K, acc[6]);
+        sink.add(M - K / 2 - K, acc[7]);
     }
 }
 

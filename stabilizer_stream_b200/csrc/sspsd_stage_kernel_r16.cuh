@@ -272,26 +272,27 @@ __global__ void __launch_bounds__(R16::NT, 2) psd_stage_kernel_r16(const StagePa
         }
     }
 
+    const AccSink sink = acc_sink(nullptr, p.acc, p.part, p.part_stride, blockIdx.x * G + group);
     if (j != 0) {
 #pragma unroll
         for (int t = 0; t < 8; ++t) {
             int k = kA + K * t;
-            atomicAdd(&p.acc[k], acc[2 * t]);
-            atomicAdd(&p.acc[M - k], acc[2 * t + 1]);
+            sink.add(k, acc[2 * t]);
+            sink.add(M - k, acc[2 * t + 1]);
         }
     } else {
-        atomicAdd(&p.acc[0], acc[0]);
-        atomicAdd(&p.acc[M], acc[1]);
+        sink.add(0, acc[0]);
+        sink.add(M, acc[1]);
 #pragma unroll
         for (int t = 1; t < 4; ++t) {
-            atomicAdd(&p.acc[K * t], acc[2 * t]);
-            atomicAdd(&p.acc[M - K * t], acc[2 * t + 1]);
+            sink.add(K * t, acc[2 * t]);
+            sink.add(M - K * t, acc[2 * t + 1]);
         }
-        atomicAdd(&p.acc[M / 2], accx);
+        sink.add(M / 2, accx);
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
-            atomicAdd(&p.acc[K / 2 + K * u], acc[8 + 2 * u]);
-            atomicAdd(&p.acc[M - K / 2 - K * u], acc[9 + 2 * u]);
+            sink.add(K / 2 + K * u, acc[8 + 2 * u]);
+            sink.add(M - K / 2 - K * u, acc[9 + 2 * u]);
         }
     }
 }

@@ -154,7 +154,7 @@ class _StreamOrdered:
             t.record_stream(self._hs)
 
 
-def _config(n, window, hbf, device, stream, max_batch, host_stage, deep_defer=0):
+def _config(n, window, hbf, device, stream, max_batch, host_stage, deep_defer=0, deterministic=False):
     if stream is None:
         stream = _default_stream(device)
     cfg = L.Config()
@@ -166,6 +166,7 @@ def _config(n, window, hbf, device, stream, max_batch, host_stage, deep_defer=0)
     cfg.max_batch = max_batch
     cfg.host_stage = host_stage
     cfg.deep_defer = deep_defer
+    cfg.flags = L.FLAG_DETERMINISTIC if deterministic else 0
     return cfg
 
 
@@ -173,13 +174,13 @@ class PsdCascade(_StreamOrdered):
     """PsdCascade<N>, src/psd.rs:399-544.  `PsdCascade(n)` is `PsdCascade::<N>::default()`."""
 
     def __init__(self, n=512, device=0, hbf=Hbf.TAPS_140, stream=None, max_batch=0, host_stage=0, deep_defer=0,
-                 _handle=None):
+                 deterministic=False, _handle=None):
         self.n = n
         self.device = int(device)
         if _handle is not None:
             self._h = _handle
             return
-        cfg = _config(n, Window.HANN, hbf, device, stream, max_batch, host_stage, deep_defer)
+        cfg = _config(n, Window.HANN, hbf, device, stream, max_batch, host_stage, deep_defer, deterministic)
         h = C.c_void_p()
         L.check(L.lib().sspsd_cascade_create(C.byref(cfg), C.byref(h)))
         self._h = h

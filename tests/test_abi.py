@@ -27,7 +27,7 @@ def test_header_symbols_are_exported_and_prototyped():
 
 def test_struct_layouts_match_header():
     from stabilizer_stream_b200 import _lib
-    assert C.sizeof(_lib.BreakC) == 72 and C.sizeof(_lib.Config) == 48
+    assert C.sizeof(_lib.BreakC) == 72 and C.sizeof(_lib.Config) == 56
     assert C.sizeof(_lib.LossC) == 24 and C.sizeof(_lib.DecodeInfoC) == 24
     assert C.sizeof(_lib.PartialsC) == 8 + 8 + 8 + 8 * 16
 

@@ -385,3 +385,73 @@ def test_device_tensors_on_other_torch_streams(sp, oracle):
     po, bo = o.psd()
     assert [breaks_tuple(k) for k in b] == [k.as_tuple() for k in bo]
     assert_bins_close(p, po, "side streams")
+
+
+@pytest.mark.parametrize("n", [512, 4096])
+def test_deterministic_accumulation_is_bit_reproducible(sp, oracle, n):
+    """SSPSD_FLAG_DETERMINISTIC (VERDICT r01 missing #8): per-CTA partial rows summed in fixed
+    order instead of float atomics -- two runs over the same calls give bit-identical readouts."""
+    import torch
+    x = uniform_noise(3000 * n + 11, 5 + n)
+    xd = torch.from_numpy(x).cuda()
+    outs = []
+    for _ in range(3):
+        c = sp.PsdCascade(n, deterministic=True)
+        c.set_detrend(sp.Detrend.MEAN)
+        c.process(xd[:1000 * n])
+        c.process(xd[1000 * n:])
+        p, b = c.psd(sp.MergeOpts(keep_overlap=True, min_count=0, keep_transition_band=True))
+        outs.append((p, [breaks_tuple(k) for k in b]))
+    for p, b in outs[1:]:
+        assert b == outs[0][1]
+        assert np.array_equal(p.view(np.uint32), outs[0][0].view(np.uint32))
+    o = oracle.Cascade(n, 1)
+    o.set_detrend(3)
+    o.process(x)
+    po, bo = o.psd(True, 0, True)
+    for bi in [k for k in c.psd(sp.MergeOpts(keep_overlap=True, min_count=0, keep_transition_band=True))[1] if k.count]:
+        sl = slice(bi.start + 2, bi.start + len(bi.bins))
+        assert_bins_close(outs[0][0][sl], po[sl], "deterministic stage dec=%d" % bi.decimation)
+
+
+@pytest.mark.parametrize("n,defer", [(512, 1 << 16), (4096, 1 << 20), (64, 1 << 12)])
+def test_deferred_deep_stages_are_invisible(sp, oracle, n, defer):
+    """sspsd_config::deep_defer lets the input of the stages >= 1 pile up; every observing call runs what is
+    pending first, so results, breaks, option changes, clone and reset behave exactly as without it."""
+    import torch
+    rng = np.random.default_rng(n)
+    x = uniform_noise(1500 * n, 3 * n) + np.float32(0.2)
+    xd = torch.from_numpy(x).cuda()
+    g = sp.PsdCascade(n, deep_defer=defer, max_batch=64 * n)
+    o = oracle.Cascade(n, 1)
+    pos = 0
+    step = 0
+    clone = None
+    while pos < x.size:
+        k = int(rng.integers(1, 90 * n))
+        (g.process(xd[pos:pos + k]) if step % 2 else g.process(x[pos:pos + k]))
+        o.process(x[pos:pos + k])
+        pos += k
+        step += 1
+        if step == 5:
+            g.set_detrend(sp.Detrend.MIDPOINT); o.set_detrend(1)      # applies to segments completed after the call
+        if step == 9:
+            g.set_avg(sp.AvgOpts(limit=40, count=3000)); o.set_avg(40, 3000)
+        if step == 7:
+            clone = (g.clone(), o.clone(), pos)
+        if step % 6 == 0:
+            p, b = g.psd()
+            po, bo = o.psd()
+            assert [breaks_tuple(v) for v in b] == [v.as_tuple() for v in bo]
+            assert_bins_close(p, po, "deferred step %d" % step)
+    p, b = g.psd()
+    po, bo = o.psd()
+    assert [breaks_tuple(v) for v in b] == [v.as_tuple() for v in bo]
+    assert_bins_close(p, po, "deferred final")
+    gc, oc, cpos = clone
+    gc.process(xd[cpos:cpos + 300 * n]); oc.process(x[cpos:cpos + 300 * n])
+    p, b = gc.psd(); po, bo = oc.psd()
+    assert [breaks_tuple(v) for v in b] == [v.as_tuple() for v in bo]
+    assert_bins_close(p, po, "deferred clone")
+    g.reset()
+    assert g.psd()[1] == []
