@@ -301,8 +301,11 @@ def run_ours(args):
             ch.readout()
         ch.c.profile_read()
         barrier()
+        # clocks are sampled during the headline run; the NVML polling thread of 8 ranks costs the
+        # readout-every-step loop 5-15 % (tools/readout_probe.py), so that run goes without it
         sampler = ClockSampler(local)
-        sampler.start()
+        if not readout_every_step:
+            sampler.start()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record(stream)
         for _ in range(args.steps):
@@ -313,7 +316,7 @@ def run_ours(args):
             res = ch.readout()
         e1.record(stream)
         barrier()
-        clocks = sampler.stop()
+        clocks = sampler.stop() if not readout_every_step else None
         ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
         if world > 1:
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
@@ -406,6 +409,7 @@ def run_ours(args):
         n512["published"] = ">200 MS/s on one (Skylake) core at N=512 (reference README.md:11, src/psd.rs:550)"
         out["cpu_baseline_n512"] = n512
         out["e2e_small_calls"] = small_calls()
+        out["e2e_frames"] = e2e_frames(local)
     emit(out)
     if world > 1:
         dist.destroy_process_group()
@@ -458,6 +462,48 @@ def timechunk_record(new_group, barrier, rank, world, dist, dev):
             out["max_rel_vs_f64"] = float(np.max(np.maximum(np.abs(p - truth) - floor, 0) / truth)) if truth.size == p.size else None
             out["counts_match_golden"] = [k.count for k in reversed(b)] == [int(c) for c in counts]
     return out
+
+
+def e2e_frames(local):
+    """BASELINE config 3 end to end: AdcDac frames (22 batches, 1416 bytes; header + i16 ADC/DAC words, reference
+    src/de/data.rs:12-82) in pinned HOST memory -> H2D -> frame decode + loss accounting -> four cascades
+    (one per trace, src/bin/psd.rs:174-182) -> psd() of each.  2.011 bytes cross PCIe per trace sample instead
+    of 4, so the PCIe-bound end-to-end rate in trace samples is about twice that of the raw f32 stream."""
+    import numpy as np
+    import torch
+    from stabilizer_stream_b200 import FrameDecoder, Loss, MergeOpts, PsdCascade
+    batches, n_frames = 22, 1 << 18
+    flen = 8 + 64 * batches
+    rng = np.random.default_rng(3)
+    fr = np.zeros((n_frames, flen), np.uint8)
+    fr[:, 0], fr[:, 1], fr[:, 2], fr[:, 3] = 0x7B, 0x05, 1, batches
+    seq = (np.arange(n_frames, dtype=np.uint64) * batches + 0xFFFFF000).astype(np.uint32)
+    fr[:, 4:8] = seq.view(np.uint8).reshape(n_frames, 4)
+    fr[:, 8:] = rng.integers(0, 256, (n_frames, flen - 8), dtype=np.uint8)
+    host = torch.from_numpy(fr.reshape(-1)).pin_memory()
+    dec = FrameDecoder(local)
+    cas = [PsdCascade(N_FFT, device=local) for _ in range(4)]
+    loss = Loss()
+    chunk = 1 << 15   # frames per call: the decode call synchronises, the cascades of call c overlap the H2D of call c+1
+
+    def one_pass():
+        for f0 in range(0, n_frames, chunk):
+            dec.process_frames(cas, host[f0 * flen:(f0 + chunk) * flen], flen, loss)
+        return [c.psd(MergeOpts()) for c in cas]
+
+    one_pass()
+    torch.cuda.synchronize()
+    steps = 3
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        res = one_pass()
+    torch.cuda.synchronize()
+    dt = (time.perf_counter() - t0) / steps
+    samples = 4 * n_frames * batches * 8
+    return {"value": samples / dt / 1e6, "unit": "M trace-samples/s", "frames_per_step": n_frames, "frame_bytes": flen,
+            "h2d_bytes_per_step": n_frames * flen, "h2d_GBps": n_frames * flen / dt / 1e9, "seconds_per_step": dt,
+            "bytes_per_trace_sample": n_frames * flen / samples, "loss_received": int(loss.received), "loss_dropped": int(loss.dropped),
+            "stage0_count": res[0][1][-1].count}
 
 
 def small_calls():

@@ -1142,6 +1142,22 @@ int Cascade::sync()
     return SSPSD_OK;
 }
 
+// launch everything pending, make stream_ wait for the handle's side streams and record `ev` there: work queued on
+// another stream behind `ev` sees the handle's complete state without a host synchronisation
+int Cascade::fence(cudaEvent_t ev)
+{
+    DeviceGuard g(cfg_.device);
+    if (!g.ok) return SSPSD_ECUDA;
+    int rc = flush_staged();
+    if (rc) return rc;
+    rc = flush_deferred();
+    if (rc) return rc;
+    rc = join_streams();
+    if (rc) return rc;
+    SSPSD_CUDA(cudaEventRecord(ev, stream_));
+    return SSPSD_OK;
+}
+
 int Cascade::set_avg(sspsd_avg_opts a)
 {
     // options apply to segments completed after the call: launch what is staged first

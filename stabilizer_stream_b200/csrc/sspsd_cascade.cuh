@@ -70,6 +70,7 @@ public:
     int set_detrend(int d);
     int flush();
     int sync();
+    int fence(cudaEvent_t ev);
     int psd(const sspsd_merge_opts& o, float* p, size_t* p_len, sspsd_break* b, size_t* b_len);
     int partials(sspsd_partials* out);
     void export_book(uint64_t* book) const;  // 4 * SSPSD_MAX_STAGES + 2 words

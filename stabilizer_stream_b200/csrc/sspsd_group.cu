@@ -16,7 +16,10 @@
 #include <dlfcn.h>
 #include <nccl.h>
 
+#include <time.h>
+
 #include <algorithm>
+#include <cstdio>
 #include <cmath>
 #include <cstring>
 #include <mutex>
@@ -90,6 +93,13 @@ bool nccl_ok(ncclResult_t r, const char* what)
     do {                                                  \
         if (!nccl_ok((call), #call)) return SSPSD_ENCCL;  \
     } while (0)
+
+double now_s()
+{
+    timespec t;
+    clock_gettime(CLOCK_MONOTONIC, &t);
+    return (double)t.tv_sec + 1e-9 * (double)t.tv_nsec;
+}
 
 struct DevGuard {
     int prev = -1;
@@ -339,6 +349,13 @@ struct sspsd_group {
     uint8_t* h_all = nullptr;
     size_t rec_cap = 0, all_cap = 0;
     cudaStream_t gather_stream = nullptr;
+    // SSPSD_GROUP_TRACE=1: host seconds spent in the phases of sspsd_group_psd_all, printed when the group is destroyed
+    cudaEvent_t ev_chan = nullptr;
+    uint64_t* h_book = nullptr;  // pinned
+    size_t book_cap = 0;
+    bool trace = false;
+    double t_wait = 0, t_pack = 0, t_gather = 0, t_d2h = 0, t_merge = 0;
+    uint64_t n_readouts = 0;
     std::vector<sspsd_source*> noise_src;  // per local rank, for sspsd_group_time_process_noise
     int64_t noise_exp = 0;
     uint64_t noise_seed = 0;
@@ -378,6 +395,7 @@ int create_common(const sspsd_config* cfg, int32_t mode, sspsd_group** out, ssps
     g->cfg = *cfg;
     g->cfg.stream = nullptr;  // every handle of a group owns its stream
     g->mode = mode;
+    g->trace = getenv("SSPSD_GROUP_TRACE") != nullptr;
     *gp = g;
     return SSPSD_OK;
 }
@@ -578,6 +596,10 @@ int32_t sspsd_group_create_rank(const sspsd_config* cfg, const uint8_t id[SSPSD_
 void sspsd_group_destroy(sspsd_group* g)
 {
     if (!g) return;
+    if (g->trace && g->n_readouts)
+        fprintf(stderr, "[sspsd_group rank %u] psd_all x%llu: wait %.1f us, pack %.1f us, gather %.1f us, d2h %.1f us, merge %.1f us per call\n",
+                g->first_rank, (unsigned long long)g->n_readouts, 1e6 * g->t_wait / g->n_readouts, 1e6 * g->t_pack / g->n_readouts,
+                1e6 * g->t_gather / g->n_readouts, 1e6 * g->t_d2h / g->n_readouts, 1e6 * g->t_merge / g->n_readouts);
     for (auto* s : g->noise_src) sspsd_source_destroy(s);
     for (auto* c : g->chan) sspsd_cascade_destroy(c);
     for (auto* c : g->tc) sspsd_cascade_destroy(c);
@@ -594,6 +616,8 @@ void sspsd_group_destroy(sspsd_group* g)
         cudaFree(g->d_all);
         if (g->h_all) cudaFreeHost(g->h_all);
         if (g->gather_stream) cudaStreamDestroy(g->gather_stream);
+        if (g->ev_chan) cudaEventDestroy(g->ev_chan);
+        if (g->h_book) cudaFreeHost(g->h_book);
     }
     for (uint32_t l = 0; l < g->comms.size(); ++l)
         if (g->comms[l]) nccl().CommDestroy(g->comms[l]);
@@ -803,32 +827,58 @@ int32_t sspsd_group_psd_all(sspsd_group* g, uint32_t n_channels, const sspsd_mer
     }
     if (!g->gather_stream) SSPSD_CUDA(cudaStreamCreateWithFlags(&g->gather_stream, cudaStreamNonBlocking));
     cudaStream_t s = g->gather_stream;
+    // Nothing below waits on the host until the very end: the pack, the collective and the read-back are queued
+    // behind an event on each channel's stream, so they start the moment the GPU finishes the channel's work
+    // (a host synchronisation here would put two launch latencies on the critical path of every readout).
+    double t0 = g->trace ? now_s() : 0;
+    if (!g->ev_chan) SSPSD_CUDA(cudaEventCreateWithFlags(&g->ev_chan, cudaEventDisableTiming));
+    const size_t book_words = SSPSD_MAX_STAGES * 4 + 2;
+    if (!g->h_book || g->book_cap < per_rank) {
+        if (g->h_book) cudaFreeHost(g->h_book);
+        g->h_book = nullptr;
+        SSPSD_CUDA(cudaMallocHost(&g->h_book, (size_t)per_rank * book_words * sizeof(uint64_t)));
+        g->book_cap = per_rank;
+    }
+    double t1 = t0;
     SSPSD_CUDA(cudaMemsetAsync(g->d_rec, 0, mine, s));
-    std::vector<uint64_t> book((size_t)per_rank * (SSPSD_MAX_STAGES * 4 + 2), 0);
     for (uint32_t k = 0; k < per_rank; ++k) {
         const uint32_t c = g->first_rank + k * g->n_ranks;
         if (c >= n_channels || !g->chan[c]) continue;
         Cascade& cs = g->chan[c]->c;
-        int rc = cs.sync();
+        int rc = cs.fence(g->ev_chan);  // launches what is staged, joins the handle's side streams, records the event
         if (rc) return rc;
+        SSPSD_CUDA(cudaStreamWaitEvent(s, g->ev_chan, 0));
         sspsd_partials pa;
         rc = cs.partials(&pa);
         if (rc) return rc;
         uint8_t* dst = g->d_rec + (size_t)k * rec;
         SSPSD_CUDA(cudaMemcpyAsync(dst, pa.acc, (size_t)SSPSD_MAX_STAGES * stride * sizeof(float), cudaMemcpyDeviceToDevice, s));
-        uint64_t* bk = book.data() + (size_t)k * (SSPSD_MAX_STAGES * 4 + 2);
+        uint64_t* bk = g->h_book + (size_t)k * book_words;  // pinned: the bookkeeping is closed-form on the host
         cs.export_book(bk);
-        SSPSD_CUDA(cudaMemcpyAsync(dst + (size_t)SSPSD_MAX_STAGES * stride * sizeof(float), bk,
-                                   (SSPSD_MAX_STAGES * 4 + 2) * sizeof(uint64_t), cudaMemcpyHostToDevice, s));
+        SSPSD_CUDA(cudaMemcpyAsync(dst + (size_t)SSPSD_MAX_STAGES * stride * sizeof(float), bk, book_words * sizeof(uint64_t),
+                                   cudaMemcpyHostToDevice, s));
     }
+    double t2 = g->trace ? now_s() : 0;
     SSPSD_NCCL(nccl().AllGather(g->d_rec, g->d_all, mine, ncclUint8, g->comms[0], s));
     if (!g->is_root()) {
         SSPSD_CUDA(cudaStreamSynchronize(s));
+        if (g->trace) {
+            g->t_wait += t1 - t0;
+            g->t_pack += t2 - t1;
+            g->t_gather += now_s() - t2;
+            g->n_readouts++;
+        }
         for (uint32_t c = 0; c < n_channels; ++c) p_lens[c] = b_lens[c] = 0;
         return SSPSD_OK;
     }
+    double t3 = 0;
+    if (g->trace) {
+        SSPSD_CUDA(cudaStreamSynchronize(s));
+        t3 = now_s();
+    }
     SSPSD_CUDA(cudaMemcpyAsync(g->h_all, g->d_all, all, cudaMemcpyDeviceToHost, s));
     SSPSD_CUDA(cudaStreamSynchronize(s));
+    double t4 = g->trace ? now_s() : 0;
     for (uint32_t c = 0; c < n_channels; ++c) {
         const uint32_t r = c % g->n_ranks, k = c / g->n_ranks;
         const uint8_t* src = g->h_all + (size_t)r * mine + (size_t)k * rec;
@@ -840,6 +890,14 @@ int32_t sspsd_group_psd_all(sspsd_group* g, uint32_t n_channels, const sspsd_mer
         p_lens[c] = pl;
         b_lens[c] = bl;
         if (rc) return rc;
+    }
+    if (g->trace) {
+        g->t_wait += t1 - t0;
+        g->t_pack += t2 - t1;
+        g->t_gather += t3 - t2;
+        g->t_d2h += t4 - t3;
+        g->t_merge += now_s() - t4;
+        g->n_readouts++;
     }
     return SSPSD_OK;
 }
