@@ -86,8 +86,9 @@ typedef struct {
                             whatever is staged */
     uint64_t deep_defer; /* stages >= 1 run once this many samples are pending at stage 1 (>> 3 per deeper stage), so
                             that their kernels get full-size grids instead of ~20 small dependent launches per batch
-                            (fewer launches; measured neutral for throughput); every call that observes state runs
-                            what is pending first, results do not depend on it (0 or 1 = run them with every batch) */
+                            (fewer launches; +12 % throughput at N = 512, neutral at N = 4096); every call that observes
+                            state runs what is pending first, results do not depend on it (0 = default 1 << 26,
+                            1 = run them with every batch) */
     uint32_t flags;      /* SSPSD_FLAG_* */
     uint32_t _pad;
 } sspsd_config;

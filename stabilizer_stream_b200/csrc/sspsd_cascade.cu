@@ -12,6 +12,7 @@
 #include "sspsd_stage_kernel.cuh"
 #include "sspsd_stage_kernel_r16.cuh"
 #include "sspsd_stage_kernel_ring.cuh"
+#include "sspsd_stage_kernel_w16.cuh"
 
 namespace sspsd {
 
@@ -118,6 +119,9 @@ int prepare_stage(int log2n, bool r16, int hop, int* tmax, int* nt)
                                         (int)stage_ring_smem_bytes(RingCfg::MAX_W)));
         return SSPSD_OK;
     }
+    if (log2n == 9)
+        SSPSD_CUDA(cudaFuncSetAttribute(psd_stage_kernel_w16, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        (int)stage_w16_smem_bytes(W16::MAX_T)));
     switch (log2n) {
 #define X(L)                                                                   \
     case L:                                                                    \
@@ -391,10 +395,10 @@ int Cascade::init(const sspsd_config& cfg, uint32_t max_stages)
     }
     int rc = upload_taps_once(cfg.device);
     if (rc) return rc;
-    // measured (profiles/r02_variants*.jsonl): letting the deep stages' input pile up makes their kernels
-    // efficient (0.53 -> 0.20 ms of event time per step) but does not shorten the step, because their many
-    // small launches already hide inside the next batch's stage-0 kernels; so it is off unless asked for
-    defer_ = cfg_.deep_defer ? cfg_.deep_defer : 1;
+    // measured (profiles/r02_variants*.jsonl): letting the deep stages' input pile up for a few batches makes their
+    // kernels efficient (N = 512: 0.21 -> 0.13 ms of PSD-kernel time per 200e6-sample step, whole step 0.81 ->
+    // 0.72 ms; N = 4096: neutral, their launches already hide inside the next batch's stage-0 kernels)
+    defer_ = cfg_.deep_defer ? cfg_.deep_defer : (1ull << 26);
     if (const char* e = getenv("SSPSD_DEFER")) defer_ = strtoull(e, nullptr, 0);
     k2_variant_ = k2_variant_from_env();
     {
@@ -516,6 +520,28 @@ int Cascade::launch_psd(size_t i, const StreamSrc& src, uint64_t k0, uint64_t ns
     p.k0 = (long long)k0;
     p.nseg = (int)nseg;
     long long t = ((long long)nseg + 2ll * num_sms_ - 1) / (2ll * num_sms_);
+    if (log2n_ == 9 && k2_variant_ == 2 && hop_ * 2 == n_) {
+        // N = 512, Hann: warp-level kernel (half a warp per segment, shuffles for the real-input split), persistent
+        p.T = (int)std::max<long long>(W16::SPI, std::min<long long>(t, W16::MAX_T));
+        p.hop = (int)hop_;
+        p.detrend = detrend_;
+        p.tile_cap = 0;
+        p.win = d_win_;
+        p.twM = d_twM_;
+        p.twN = d_twN_;
+        p.acc = d_acc_ + i * acc_stride_;
+        p.jb = jb;
+        p.g_first = g_first;
+        p.g_s = g_s;
+        int grid = (int)((nseg + p.T - 1) / p.T);
+        int rcp = prepare_partials(i, grid * W16::SPI, &p);
+        if (rcp) return rcp;
+        prof_begin(i == 0 ? SSPSD_PROF_PSD_STAGE0 : SSPSD_PROF_PSD_DEEP, nseg * (uint64_t)hop_, psd_stream(i));
+        psd_stage_kernel_w16<<<grid, W16::NT, stage_w16_smem_bytes(p.T), psd_stream(i)>>>(p);
+        prof_end(psd_stream(i));
+        if (!cuda_ok(cudaGetLastError(), "psd_stage_kernel_w16 launch")) return SSPSD_ECUDA;
+        return reduce_partials(i, grid * W16::SPI, p);
+    }
     const bool ring = log2n_ == 12 && k2_variant_ == 2 && hop_ * 2 == n_;
     if (ring) {
         // persistent kernel: two CTAs per SM, each streams through a contiguous range of segments
