@@ -794,10 +794,12 @@ int Cascade::run_stage(size_t i, const float* fresh, long long split, uint64_t n
                 }
                 StageState& nx = stages_[i + 1];
                 nsplit = floor4((long long)nx.L);
-                // with large batches reserve the whole deferral window at once (a reallocation synchronises
-                // all streams and moves what has accumulated); small-batch callers grow by doubling instead
-                const uint64_t thr = defer_threshold(i + 1);
-                rc = ensure_fresh(nx, (size_t)((long long)em1 - nsplit), n_next >= thr / 16 ? (size_t)(thr + n_next) : 0);
+                // the deferral window adapts to the caller's batch size (at most 16 batches, at most defer_): small
+                // batches keep the buffers small, and the window is reserved in ONE allocation (a reallocation
+                // synchronises all streams, moves what has accumulated and frees hundreds of MB: growing by
+                // doubling cost 0.5 s over the first 4e8 samples of a small-call stream)
+                defer_window_ = std::min<uint64_t>(defer_threshold(i + 1), 16 * n_next);
+                rc = ensure_fresh(nx, (size_t)((long long)em1 - nsplit), (size_t)(defer_window_ + n_next));
                 if (rc) return rc;
                 const int b = nx.fb;
                 // the next stage may still be reading this buffer from two batches ago (other stream)
@@ -856,7 +858,7 @@ int Cascade::run_stage(size_t i, const float* fresh, long long split, uint64_t n
     // the stages >= 1 are ~20 small dependent launches that cost 0.27 ms when serialised for 1/7 of the work;
     // letting their input pile up for a few batches gives them stage-0-sized grids.  Invisible to the caller:
     // every call that observes state (psd, sync, set_*, clone, ...) runs what is pending first.
-    if (n_next > 0 && stages_[i + 1].pending_in >= defer_threshold(i + 1)) return run_pending(i + 1);
+    if (n_next > 0 && stages_[i + 1].pending_in >= defer_window_) return run_pending(i + 1);
     return SSPSD_OK;
 }
 
