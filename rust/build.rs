@@ -7,7 +7,7 @@ fn main() {
     let root = PathBuf::from(env::var("SSPSD_ROOT").unwrap_or_else(|_| "../stabilizer_stream_b200".into()));
     let out = PathBuf::from(env::var("OUT_DIR").unwrap());
     let lib = out.join("libsspsd.a");
-    let objs: Vec<PathBuf> = ["sspsd_cascade", "sspsd_api", "sspsd_source", "sspsd_receiver"]
+    let objs: Vec<PathBuf> = ["sspsd_cascade", "sspsd_api", "sspsd_source", "sspsd_receiver", "sspsd_group"]
         .iter()
         .map(|name| {
             let obj = out.join(format!("{name}.o"));
@@ -30,5 +30,6 @@ fn main() {
     println!("cargo:rustc-link-search=native=/usr/local/cuda/lib64");
     println!("cargo:rustc-link-lib=cudart");
     println!("cargo:rustc-link-lib=stdc++");
+    println!("cargo:rustc-link-lib=dl"); // NCCL is dlopen()ed by the first multi-GPU group (libnccl.so.2), never linked
     println!("cargo:rerun-if-changed={}", root.join("csrc").display());
 }

@@ -66,6 +66,7 @@ enum CCascade {}
 enum CDecoder {}
 enum CSource {}
 enum CReceiver {}
+enum CGroup {}
 
 extern "C" {
     fn sspsd_last_error() -> *const c_char;
@@ -93,6 +94,17 @@ extern "C" {
     fn sspsd_receiver_destroy(r: *mut CReceiver);
     fn sspsd_receiver_pump(r: *mut CReceiver, d: *mut CDecoder, cascades: *const *mut CCascade, n: u32, max_frames: u32,
                            timeout_ms: i32, loss: *mut CLoss, info: *mut DecodeInfo) -> i32;
+    // multi-GPU partitioning inside the library (include/sspsd.h, "sspsd_group_*")
+    fn sspsd_group_create(cfg: *const Config, devices: *const i32, n_devices: u32, shard_mode: i32, out: *mut *mut CGroup) -> i32;
+    fn sspsd_group_destroy(g: *mut CGroup);
+    fn sspsd_group_set_avg(g: *mut CGroup, avg: CAvgOpts) -> i32;
+    fn sspsd_group_set_detrend(g: *mut CGroup, detrend: i32) -> i32;
+    fn sspsd_group_process_f32(g: *mut CGroup, channel: u32, x: *const f32, n: usize, mem: i32) -> i32;
+    fn sspsd_group_psd(g: *mut CGroup, channel: u32, opts: *const CMergeOpts, p: *mut f32, p_len: *mut usize,
+                       b: *mut CBreak, b_len: *mut usize) -> i32;
+    fn sspsd_group_time_plan(g: *mut CGroup, total: u64, n_local_stages: u32) -> i32;
+    fn sspsd_group_time_process_all_f32(g: *mut CGroup, x: *const f32, n: usize) -> i32;
+    fn sspsd_group_time_finish(g: *mut CGroup) -> i32;
 }
 
 fn check(status: i32) {
@@ -275,5 +287,82 @@ impl UdpReceiver {
 impl Drop for UdpReceiver {
     fn drop(&mut self) {
         unsafe { sspsd_receiver_destroy(self.r) }
+    }
+}
+
+
+fn to_break(c: &CBreak) -> Break {
+    Break {
+        start: c.start as usize,
+        include: c.include != 0,
+        count: c.count,
+        avg: c.avg,
+        bins: Range { start: c.bins_start as usize, end: c.bins_end as usize },
+        fft_size: c.fft_size as usize,
+        decimation: c.decimation as usize,
+        pending: c.pending as usize,
+        processed: c.processed as usize,
+    }
+}
+
+/// The receiver loop's `Vec<(&str, PsdCascade<N>)>` (src/bin/psd.rs:170-183) spread over the GPUs of the box:
+/// trace `c` lives on `devices[c % devices.len()]`; NCCL / peer loads stay inside the library.
+pub struct Group<const N: usize> {
+    g: *mut CGroup,
+}
+unsafe impl<const N: usize> Send for Group<N> {}
+
+impl<const N: usize> Group<N> {
+    fn new(devices: &[i32], mode: i32) -> Self {
+        let mut cfg = std::mem::MaybeUninit::<Config>::uninit();
+        let mut g = ptr::null_mut();
+        unsafe {
+            check(sspsd_config_default(N as u32, cfg.as_mut_ptr()));
+            check(sspsd_group_create(cfg.as_ptr(), devices.as_ptr(), devices.len() as u32, mode, &mut g));
+        }
+        Self { g }
+    }
+    /// one cascade per trace (SSPSD_SHARD_CHANNELS)
+    pub fn channels(devices: &[i32]) -> Self {
+        Self::new(devices, 0)
+    }
+    /// one long capture cut into time chunks (SSPSD_SHARD_TIME)
+    pub fn time_chunks(devices: &[i32]) -> Self {
+        Self::new(devices, 1)
+    }
+    pub fn set_avg(&mut self, avg: AvgOpts) {
+        unsafe { check(sspsd_group_set_avg(self.g, CAvgOpts { limit: avg.limit, count: avg.count })) }
+    }
+    pub fn set_detrend(&mut self, d: Detrend) {
+        unsafe { check(sspsd_group_set_detrend(self.g, d as i32)) }
+    }
+    /// `dec[channel].process(&trace)`
+    pub fn process(&mut self, channel: u32, x: &[f32]) {
+        unsafe { check(sspsd_group_process_f32(self.g, channel, x.as_ptr(), x.len(), 0)) }
+    }
+    /// `dec[channel].psd(&merge_opts)`; for a time-chunked group (channel 0) after `time_finish`
+    pub fn psd(&self, channel: u32, opts: &MergeOpts) -> (Vec<f32>, Vec<Break>) {
+        let o = CMergeOpts { keep_overlap: opts.keep_overlap as u32, min_count: opts.min_count, keep_transition_band: opts.keep_transition_band as u32 };
+        let mut p = vec![0f32; 16 * (N / 2 + 1)];
+        let mut b = [CBreak::default(); 16];
+        let (mut pl, mut bl) = (p.len(), b.len());
+        unsafe { check(sspsd_group_psd(self.g, channel, &o, p.as_mut_ptr(), &mut pl, b.as_mut_ptr(), &mut bl)) };
+        p.truncate(pl);
+        (p, b[..bl].iter().map(to_break).collect())
+    }
+    pub fn time_plan(&mut self, total: u64, n_local_stages: u32) {
+        unsafe { check(sspsd_group_time_plan(self.g, total, n_local_stages)) }
+    }
+    pub fn time_process_all(&mut self, x: &[f32]) {
+        unsafe { check(sspsd_group_time_process_all_f32(self.g, x.as_ptr(), x.len())) }
+    }
+    pub fn time_finish(&mut self) {
+        unsafe { check(sspsd_group_time_finish(self.g)) }
+    }
+}
+
+impl<const N: usize> Drop for Group<N> {
+    fn drop(&mut self) {
+        unsafe { sspsd_group_destroy(self.g) }
     }
 }

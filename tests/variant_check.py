@@ -1,4 +1,4 @@
-"""Helper of test_gpu_variants.py: one N=4096 cascade against the CPU oracle, run in a fresh process so that
+"""Helper of test_gpu_variants.py: one cascade (N = 4096 unless given) against the CPU oracle, run in a fresh process so that
 the library reads the SSPSD_* environment switches at handle creation."""
 import sys
 
@@ -9,7 +9,7 @@ from oracle import binding as orc
 import stabilizer_stream_b200 as sp
 
 det = int(sys.argv[1]) if len(sys.argv) > 1 else 0
-n = 4096
+n = int(sys.argv[2]) if len(sys.argv) > 2 else 4096
 x = uniform_noise(300 * n + 123, 31) + np.float32(0.1)
 g = sp.PsdCascade(n)
 g.set_detrend(sp.Detrend(det))
