@@ -176,7 +176,9 @@ def run_reference(args):
     n = max(1, args.gpus)
     # the reference runs one cascade per trace on one receiver thread; with N channels it can use N threads
     threads = min(n, os.cpu_count() or 1)
-    cb = cpu_run(SAMPLES_PER_STEP, args.steps, min(args.warmup, 1), threads)
+    # (SSPSD_BENCH_CPU_SAMPLES shortens the step for the CPU-only smoke test of this arm; the driver never sets it)
+    per_step = int(os.environ.get("SSPSD_BENCH_CPU_SAMPLES", SAMPLES_PER_STEP))
+    cb = cpu_run(per_step, args.steps, min(args.warmup, 1), threads)
     v = cb["value"] * n / threads  # (threads == n unless the host has fewer cores than channels)
     cfg = config_dict(n)
     out = {"impl": "reference", "metric": "sustained MS/s through full PSD cascade", "value": v, "unit": "MS/s",

@@ -223,7 +223,9 @@ int32_t sspsd_cascade_set_stream_state(sspsd_cascade *h, uint32_t stage, uint64_
  * ncclCommInitAll, or (ranks sharing a GPU, SSPSD_GROUP_REDUCE=p2p) a root kernel that sums the peers' rows
  * through peer pointers in fixed order -- or one rank of a multi-process job (torchrun, MPI):
  * sspsd_group_unique_id() on rank 0, the 128 bytes broadcast by the caller, sspsd_group_create_rank() everywhere.
- * NCCL (libnccl.so.2) is loaded on first use; collective failures return SSPSD_ENCCL.
+ * NCCL (libnccl.so.2) is loaded on first use; collective failures return SSPSD_ENCCL.  Like a cascade handle, a group
+ * is not thread-safe but may be moved between threads; in a multi-process group the calls marked "collective"
+ * (sspsd_group_psd_all, sspsd_group_time_finish) must be made by every process, in the same order.
  * --------------------------------------------------------------------------------------------- */
 typedef struct sspsd_group sspsd_group;
 enum { SSPSD_SHARD_CHANNELS = 0, SSPSD_SHARD_TIME = 1 };

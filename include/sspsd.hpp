@@ -16,6 +16,7 @@
 #include <stdexcept>
 #include <string>
 #include <utility>
+#include <array>
 #include <vector>
 
 #include "sspsd.h"
@@ -342,6 +343,87 @@ struct Var {
         sspsd_var v{x_exp, sinx_exp, clip, 0, dc_cut};
         return sspsd_var_eval(&v, phase_psd.data(), frequencies.data(), std::min(phase_psd.size(), frequencies.size()), tau);
     }
+};
+
+/// struct Trace + Trace::plot + struct Trapezoidal, src/bin/psd.rs:96-157
+struct Trace {
+    std::string name;
+    std::vector<Break> breaks;
+    std::vector<float> psd;
+    std::vector<float> frequencies;
+    /// -> (sqrt of the trapezoidal integral over [integral_start, integral_end] in units of fs * f, plot points)
+    std::pair<float, std::vector<std::array<double, 2>>> plot(float fs = 1.0f, float integral_start = 1e-6f,
+                                                              float integral_end = 0.5f, bool integrate = false) const
+    {
+        sspsd_plot_opts o{fs, integral_start, integral_end, integrate ? 1u : 0u};
+        const size_t n = std::min(psd.size(), frequencies.size());
+        std::vector<std::array<double, 2>> xy(n ? n : 1);
+        size_t np = xy.size();
+        float integral = 0.f;
+        check(sspsd_trace_plot(&o, psd.data(), frequencies.data(), n, &integral, &xy[0][0], &np));
+        xy.resize(np);
+        return {integral, std::move(xy)};
+    }
+};
+
+/// The receiver loop's `Vec<(&str, PsdCascade<N>)>` (src/bin/psd.rs:170-183) spread over the GPUs of the box:
+/// channel (trace) c lives on devices[c % devices.size()], or ONE long capture is cut into time chunks; NCCL / peer
+/// loads stay inside the library (sspsd_group_*).
+template <size_t N>
+class Group {
+public:
+    enum class Shard : int32_t { Channels = SSPSD_SHARD_CHANNELS, Time = SSPSD_SHARD_TIME };
+    explicit Group(const std::vector<int32_t>& devices, Shard mode = Shard::Channels, int32_t hbf = SSPSD_HBF_140)
+    {
+        sspsd_config cfg;
+        check(sspsd_config_default((uint32_t)N, &cfg));
+        cfg.hbf = hbf;
+        check(sspsd_group_create(&cfg, devices.data(), (uint32_t)devices.size(), (int32_t)mode, &g_));
+    }
+    Group(const Group&) = delete;
+    Group& operator=(const Group&) = delete;
+    ~Group() { sspsd_group_destroy(g_); }
+    void set_avg(AvgOpts a) { check(sspsd_group_set_avg(g_, sspsd_avg_opts{a.limit, a.count})); }
+    void set_detrend(Detrend d) { check(sspsd_group_set_detrend(g_, (int32_t)d)); }
+    /// `dec[channel].process(&trace)`
+    void process(uint32_t channel, const float* x, size_t n, Mem mem = Mem::Host)
+    {
+        check(sspsd_group_process_f32(g_, channel, x, n, (int32_t)mem));
+    }
+    void process(uint32_t channel, const std::vector<float>& x) { process(channel, x.data(), x.size()); }
+    std::pair<std::vector<float>, std::vector<Break>> psd(uint32_t channel = 0, const MergeOpts& o = MergeOpts()) const
+    {
+        sspsd_merge_opts mo{o.keep_overlap, o.min_count, o.keep_transition_band};
+        std::vector<float> p(SSPSD_MAX_STAGES * (N / 2 + 1));
+        sspsd_break cb[SSPSD_MAX_STAGES];
+        size_t pl = p.size(), bl = SSPSD_MAX_STAGES;
+        check(sspsd_group_psd(g_, channel, &mo, p.data(), &pl, cb, &bl));
+        p.resize(pl);
+        std::vector<Break> b;
+        for (size_t i = 0; i < bl; ++i)
+            b.push_back(Break{(size_t)cb[i].start, cb[i].include != 0, cb[i].count, cb[i].avg,
+                              {(size_t)cb[i].bins_start, (size_t)cb[i].bins_end}, (size_t)cb[i].fft_size,
+                              (size_t)cb[i].decimation, (size_t)cb[i].pending, (size_t)cb[i].processed});
+        return {std::move(p), std::move(b)};
+    }
+    // time chunks of one stream
+    void time_plan(uint64_t total, uint32_t n_local_stages = 0) { check(sspsd_group_time_plan(g_, total, n_local_stages)); }
+    sspsd_time_chunk time_chunk(uint32_t rank) const
+    {
+        sspsd_time_chunk c;
+        check(sspsd_group_time_chunk(g_, rank, &c));
+        return c;
+    }
+    void time_process(uint32_t rank, const float* x, size_t n, Mem mem = Mem::Host)
+    {
+        check(sspsd_group_time_process_f32(g_, rank, x, n, (int32_t)mem));
+    }
+    void time_process_all(const std::vector<float>& x) { check(sspsd_group_time_process_all_f32(g_, x.data(), x.size())); }
+    void time_finish() { check(sspsd_group_time_finish(g_)); }
+    void sync() { check(sspsd_group_sync(g_)); }
+
+private:
+    sspsd_group* g_ = nullptr;
 };
 
 }  // namespace sspsd

@@ -91,6 +91,46 @@ int main()
                     REQUIRE(std::fabs(pn[k] * 0.5f - 1.0f) < 10.0f / std::sqrt((float)bi.count));
         }
 
+        // the receiver loop over traces (bin/psd.rs:170-183) on a group: three traces on two ranks that share GPU 0
+        {
+            Group<N> grp({0, 0});
+            grp.set_detrend(Detrend::Midpoint);
+            std::vector<std::vector<float>> tr(3, x);
+            for (size_t c = 0; c < tr.size(); ++c)
+                for (auto& v : tr[c]) v *= (float)(c + 1);
+            for (size_t c = 0; c < tr.size(); ++c) grp.process((uint32_t)c, tr[c]);
+            for (size_t c = 0; c < tr.size(); ++c) {
+                PsdCascade<N> one;
+                one.set_detrend(Detrend::Midpoint);
+                one.process(tr[c]);
+                auto [pg, bg] = grp.psd((uint32_t)c);
+                auto [po, bo] = one.psd();
+                REQUIRE(pg.size() == po.size() && bg.size() == bo.size());
+                for (size_t k = 0; k < pg.size(); ++k) REQUIRE(std::fabs(pg[k] - po[k]) <= 1e-5f * po[k]);
+            }
+            // ONE stream cut into three time chunks: same spectrum as the sequential cascade
+            Group<N> tg({0, 0, 0}, Group<N>::Shard::Time);
+            std::vector<float> longx;
+            for (int r = 0; r < 40; ++r) longx.insert(longx.end(), x.begin(), x.end());
+            tg.time_plan(longx.size());
+            tg.time_process_all(longx);
+            tg.time_finish();
+            PsdCascade<N> seq;
+            seq.process(longx);
+            auto [pt, bt] = tg.psd();
+            auto [ps, bs] = seq.psd();
+            REQUIRE(pt.size() == ps.size() && bt.size() == bs.size());
+            for (size_t i = 0; i < bt.size(); ++i) REQUIRE(bt[i].count == bs[i].count && bt[i].pending == bs[i].pending);
+            for (size_t k = 0; k < pt.size(); ++k) REQUIRE(std::fabs(pt[k] - ps[k]) <= 5e-5f * ps[k]);
+        }
+
+        // Trace::plot + Trapezoidal (bin/psd.rs:96-157): trapezoids 0.2 + 0.3 + 0.8 between four points
+        {
+            Trace t{"t", {}, {2.0f, 2.0f, 4.0f, 4.0f}, {0.0f, 0.1f, 0.2f, 0.4f}};
+            auto [integral, pts] = t.plot();
+            REQUIRE(std::fabs(integral - std::sqrt(1.3f)) < 1e-6f && pts.size() == 3);
+        }
+
         // var.rs:52-60
         float v = Var().eval({1000.0f, 100.0f, 1.2f, 3.4f, 5.6f}, {0.0f, 1.0f, 3.0f, 6.0f, 9.0f}, 2.7f);
         REQUIRE(std::fabs(0.13478442f - v) < 1e-6f);

@@ -30,6 +30,7 @@ def test_struct_layouts_match_header():
     assert C.sizeof(_lib.BreakC) == 72 and C.sizeof(_lib.Config) == 56
     assert C.sizeof(_lib.LossC) == 24 and C.sizeof(_lib.DecodeInfoC) == 24
     assert C.sizeof(_lib.PartialsC) == 8 + 8 + 8 + 8 * 16
+    assert C.sizeof(_lib.TimeChunkC) == 56 and C.sizeof(_lib.PlotOptsC) == 16
 
 
 def test_host_helpers_without_gpu():

@@ -22,3 +22,24 @@ def test_bench_reference_arm_contract_keys():
                 '"scaling"', '"vs_baseline"', '"dtype"', '"data"', '"config"', '"roofline"', '"cpu_baseline"', '"clocks"',
                 '"gpu_launches"', '"e2e"', '"h2d_bytes_per_step"', '"d2h_bytes_per_step"', '"impl"'):
         assert key in src, key
+
+
+def test_reference_arm_runs_and_matches_the_gpu_arms_config():
+    """the CPU arm on a tiny step count: same `config` as the GPU arm builds (same_config was false),
+    one JSON line on stdout, sane scaling keys"""
+    import json
+    import subprocess
+    import sys
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0"],
+                       capture_output=True, text=True, timeout=600, env=dict(os.environ, SSPSD_BENCH_CPU_SAMPLES="4000000"))
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [l for l in r.stdout.splitlines() if l.strip()]
+    assert len(lines) == 1
+    out = json.loads(lines[0])
+    sys.path.insert(0, ROOT)
+    import bench
+    assert out["impl"] == "reference" and out["config"] == bench.config_dict(1)
+    assert out["cpu_baseline"]["kind"] == "port" and out["cpu_baseline"]["cores"] == 1 and out["value"] > 1
+    assert out["e2e"]["h2d_bytes_per_step"] == 0 and "parity_note" in out
+    for key in ("sustained_2s", "timechunk", "e2e_small_calls", "e2e_frames", "cpu_baseline_n512", "value_readout_every_step"):
+        assert '"%s"' % key in open(os.path.join(ROOT, "bench.py")).read()
