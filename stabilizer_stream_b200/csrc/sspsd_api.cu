@@ -376,6 +376,13 @@ int decode_on_device(sspsd_decoder* d, const uint8_t* frames, size_t n_frames, s
         SSPSD_CUDA(cudaMemcpyAsync(d->d_frames, frames, n_bytes, cudaMemcpyHostToDevice, d->stream));
         dfr = d->d_frames;
     }
+    // the trace buffers the decode kernels are about to overwrite may still be read by the cascades of the previous
+    // sspsd_cascade_process_frames call (other streams)
+    for (int t = 0; t < SSPSD_MAX_TRACES; ++t)
+        if (d->consumed_pending[t]) {
+            SSPSD_CUDA(cudaStreamWaitEvent(d->stream, d->ev_consumed[t], 0));
+            d->consumed_pending[t] = false;
+        }
     if (n_frames > d->status_cap) {
         SSPSD_CUDA(cudaStreamSynchronize(d->stream));
         if (d->d_status) SSPSD_CUDA(cudaFree(d->d_status));
@@ -565,12 +572,9 @@ int32_t sspsd_cascade_process_frames(sspsd_decoder* d, sspsd_cascade* const* cas
     if (!g.ok) return SSPSD_ECUDA;
     const size_t payload = frame_len - SSPSD_HEADER_SIZE;
     const size_t worst = n_frames * std::max<size_t>(payload / 64 * 8, payload / 24);
-    // the previous batch's traces may still be read by the cascades' streams
-    for (int t = 0; t < SSPSD_MAX_TRACES; ++t)
-        if (d->consumed_pending[t]) {
-            SSPSD_CUDA(cudaStreamWaitEvent(d->stream, d->ev_consumed[t], 0));
-            d->consumed_pending[t] = false;
-        }
+    // (the previous batch's traces may still be read by the cascades' streams: decode_on_device makes the decode
+    // kernels -- not the frames' H2D copy, which only touches the frame buffer -- wait for them, so the copy of
+    // batch c + 1 overlaps the cascades of batch c)
     if (worst > d->traces_cap) {
         SSPSD_CUDA(cudaDeviceSynchronize());
         for (int t = 0; t < SSPSD_MAX_TRACES; ++t) {
