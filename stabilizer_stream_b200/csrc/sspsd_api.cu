@@ -359,7 +359,7 @@ namespace {
 // Runs scan + loss + payload decode on d->stream.  dst[t] are device pointers (aligned if `aligned`).
 // On return (stream synchronised) d->h_res holds the batch result.
 int decode_on_device(sspsd_decoder* d, const uint8_t* frames, size_t n_frames, size_t frame_len, size_t frame_stride,
-                     int frames_mem, const sspsd_loss* loss, float* const* dst, bool dst_aligned)
+                     int frames_mem, const sspsd_loss* loss, float* const* dst, bool dst_aligned, size_t dst_cap)
 {
     using namespace sspsd;
     const size_t n_bytes = n_frames ? (n_frames - 1) * frame_stride + frame_len : 0;
@@ -411,6 +411,7 @@ int decode_on_device(sspsd_decoder* d, const uint8_t* frames, size_t n_frames, s
     if (dst) {
         TraceOut out{};
         for (int t = 0; t < SSPSD_MAX_TRACES; ++t) out.t[t] = dst[t];
+        out.cap = dst_cap;
         const bool flat_ok = dst_aligned && (reinterpret_cast<uintptr_t>(dfr) % 8 == 0) && (frame_stride % 8 == 0) &&
                              frame_len >= SSPSD_HEADER_SIZE && ((frame_len - SSPSD_HEADER_SIZE) % 64 == 0);
         // The format byte of frame 0 decides the kernel; peek at it on the host when the frames are host
@@ -515,7 +516,8 @@ int32_t sspsd_decode_frames(sspsd_decoder* d, const uint8_t* frames, size_t n_fr
             for (int t = 0; t < SSPSD_MAX_TRACES; ++t) dst[t] = d->d_traces[t];
         }
     }
-    int rc = decode_on_device(d, frames, n_frames, frame_len, frame_stride, frames_mem, loss, want ? dst : nullptr, aligned);
+    int rc = decode_on_device(d, frames, n_frames, frame_len, frame_stride, frames_mem, loss, want ? dst : nullptr, aligned,
+                              traces_mem == SSPSD_MEM_DEVICE ? trace_cap : d->traces_cap);
     if (rc) return rc;
     const sspsd::DecodeResult r = *d->h_res;
     const unsigned int div = r.format == SSPSD_FORMAT_ADCDAC ? 8 : 1;
@@ -584,7 +586,7 @@ int32_t sspsd_cascade_process_frames(sspsd_decoder* d, sspsd_cascade* const* cas
         }
         d->traces_cap = worst;
     }
-    int rc = decode_on_device(d, frames, n_frames, frame_len, frame_stride, frames_mem, loss, d->d_traces, true);
+    int rc = decode_on_device(d, frames, n_frames, frame_len, frame_stride, frames_mem, loss, d->d_traces, true, d->traces_cap);
     if (rc) return rc;
     const sspsd::DecodeResult r = *d->h_res;
     const unsigned int div = r.format == SSPSD_FORMAT_ADCDAC ? 8 : 1;

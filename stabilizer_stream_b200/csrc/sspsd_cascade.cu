@@ -635,7 +635,7 @@ int Cascade::reduce_partials(size_t i, int rows, const StageParams& p)
 }
 
 int Cascade::launch_decim(size_t i, const StreamSrc& src, uint64_t m0, uint64_t m1, float* out_fresh,
-                          long long out_split)
+                          long long out_split, long long out_cap)
 {
     DecimParams p{};
     p.src = src;
@@ -644,6 +644,7 @@ int Cascade::launch_decim(size_t i, const StreamSrc& src, uint64_t m0, uint64_t 
     p.drain = drain_;
     p.out_fresh = out_fresh;
     p.out_split = out_split;
+    p.out_cap = out_cap;
     p.preset = cfg_.hbf;
     long long lo = std::max<long long>(p.m0, p.drain);
     if (p.m1 <= lo)
@@ -684,7 +685,7 @@ int Cascade::run_stage(size_t i, const float* fresh, long long split, uint64_t n
     const uint64_t L1 = st.L + n_new;
     const uint64_t craw0 = st.craw;
     const uint64_t craw1 = L1 < n_ ? 0 : 1 + (L1 - n_) / hop_;
-    const StreamSrc src{st.carry[st.cur], fresh, st.carry_start, split};
+    const StreamSrc src{st.carry[st.cur], fresh, st.carry_start, split, (long long)L1};
     int rc;
     bool psd_launched = false;
     if (ps != ss && craw1 > craw0) {
@@ -771,7 +772,7 @@ int Cascade::run_stage(size_t i, const float* fresh, long long split, uint64_t n
                     tail_cap_ = cap;
                 }
                 if (tail_len_ == 0) tail_first_ = st.emitted;
-                rc = launch_decim(i, src, m0, m1, d_tail_ + tail_len_, (long long)st.emitted);
+                rc = launch_decim(i, src, m0, m1, d_tail_ + tail_len_, (long long)st.emitted, (long long)(tail_cap_ - tail_len_));
                 if (rc) return rc;
                 tail_len_ += n_next;
                 st.emitted = em1;
@@ -782,7 +783,7 @@ int Cascade::run_stage(size_t i, const float* fresh, long long split, uint64_t n
                     set_error("internal: sink overflow");
                     return SSPSD_EINVAL;
                 }
-                rc = launch_decim(i, src, m0, m1, d_sink_ + sink_len_, (long long)st.emitted);
+                rc = launch_decim(i, src, m0, m1, d_sink_ + sink_len_, (long long)st.emitted, (long long)(sink_cap_ - sink_len_));
                 if (rc) return rc;
                 sink_len_ += n_next;
                 st.emitted = em1;
@@ -810,7 +811,7 @@ int Cascade::run_stage(size_t i, const float* fresh, long long split, uint64_t n
                     if (psd_stream(i + 1) != stage_stream(i + 1)) SSPSD_CUDA(cudaStreamWaitEvent(ss, nx.ev_psd[b], 0));
                     nx.ev_read_pending[b] = false;
                 }
-                rc = launch_decim(i, src, m0, m1, nx.fresh[b], nsplit);
+                rc = launch_decim(i, src, m0, m1, nx.fresh[b], nsplit, (long long)nx.fresh_cap);
                 if (rc) return rc;
                 stages_[i].emitted = em1;
                 nx.pending_in += n_next;
@@ -840,8 +841,12 @@ int Cascade::run_stage(size_t i, const float* fresh, long long split, uint64_t n
         // kernel read (a wait on an event that was never recorded returns at once)
         if (ps != ss) SSPSD_CUDA(cudaStreamWaitEvent(ss, s2.ev_psd[s2.fb ^ 1], 0));
         prof_begin(SSPSD_PROF_OTHER, 0, ss);
+        if (n < 0 || n > hb_ + (int)n_ + 16) {
+            set_error("internal: carry overflow");
+            return SSPSD_EINVAL;
+        }
         carry_copy_kernel<<<std::max(1, std::min(64, (n + 255) / 256)), 256, 0, ss>>>(src, cs, n, s2.carry[s2.cur ^ 1],
-                                                                                     head_dst, head_n);
+                                                                                     head_dst, head_n, hb_ + (int)n_ + 16);
         prof_end(ss);
         SSPSD_CUDA(cudaGetLastError());
         s2.cur ^= 1;

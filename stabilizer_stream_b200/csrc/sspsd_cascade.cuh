@@ -106,7 +106,7 @@ private:
     int run_stage(size_t i, const float* fresh, long long split, uint64_t n_new);
     int launch_psd(size_t i, const StreamSrc& src, uint64_t k0, uint64_t nseg, int jb, float g_first, float g_s);
     int launch_decim(size_t i, const StreamSrc& src, uint64_t m0, uint64_t m1, float* out_fresh,
-                     long long out_split);
+                     long long out_split, long long out_cap);
     int prepare_partials(size_t i, int rows, struct StageParams* p);
     int reduce_partials(size_t i, int rows, const struct StageParams& p);
     cudaStream_t stage_stream(size_t i) const { return (i < deep_from_ || !deep_stream_) ? stream_ : deep_stream_; }

@@ -62,14 +62,18 @@ struct DecimParams {
     // out_fresh[g - out_split] (out_split = floor4 of the next stage's sample count, so g >= out_split)
     float* out_fresh;
     long long out_split;
+    long long out_cap;  // floats available at out_fresh (bounds-checking build)
     int preset;
 };
 
 template <int M, int SI, int SO, int REL0, bool FINAL, int PRESET, int SET>
 __device__ __forceinline__ void hbf_stage(const float* __restrict__ ine, const float* __restrict__ ino,
                                           int n_out, float* __restrict__ oute,
-                                          float* __restrict__ outo, float* __restrict__ gout, int rel_lo, int rel_hi)
+                                          float* __restrict__ outo, float* __restrict__ gout, int rel_lo, int rel_hi,
+                                          long long gidx0 = 0, long long gcap = 0)
 {
+    (void)gidx0;
+    (void)gcap;
     constexpr int P = DEC_P, LP = DEC_LP;
     for (int w = threadIdx.x; w < n_out / P; w += DEC_NT) {
         // plane index of window element i is P w + (REL0 - 2M + 1 + i): its phase and offset are compile
@@ -116,7 +120,10 @@ __device__ __forceinline__ void hbf_stage(const float* __restrict__ ine, const f
 #pragma unroll
             for (int q = 0; q < P; ++q) {
                 const int r = P * w + q;
-                if (r >= rel_lo && r < rel_hi) gout[r] = y[q];
+                if (r >= rel_lo && r < rel_hi) {
+                    SSPSD_ASSERT(gidx0 + r >= 0 && gidx0 + r < gcap);
+                    gout[r] = y[q];
+                }
             }
         } else {
             // out_base is even: q even -> even plane, q odd -> odd plane, plane index (P/2) w + q/2, whose
@@ -197,7 +204,7 @@ __global__ void __launch_bounds__(DEC_NT) decim8_kernel(const DecimParams p)
     const int rel_lo = lo > c_base ? (int)(lo - c_base) : 0;
     hbf_stage<MC, GE::SB, GE::SB, GE::NB / 2 - DEC_OB, true, PRESET, 0>(be, bo, DEC_OB, nullptr, nullptr,
                                                             p.out_fresh + (c_base - p.drain - p.out_split), rel_lo,
-                                                            DEC_OB);
+                                                            DEC_OB, c_base - p.drain - p.out_split, p.out_cap);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -273,7 +280,7 @@ __global__ void __launch_bounds__(DEC_NT, CTAS) decim8_tma_kernel(const DecimPar
         const int rel_lo = lo > c_base ? (int)(lo - c_base) : 0;
         hbf_stage<MC, GE::SB, GE::SB, GE::NB / 2 - OB, true, PRESET, 0>(be, bo, OB, nullptr, nullptr,
                                                                         p.out_fresh + (c_base - p.drain - p.out_split),
-                                                                        rel_lo, OB);
+                                                                        rel_lo, OB, c_base - p.drain - p.out_split, p.out_cap);
         // no barrier needed here: the next tile's de-interleave only writes xe/xo (last read before the
         // barrier after stage A), its stage A writes ae/ao (last read before the barrier after stage B), and
         // its stage B writes be/bo after two more barriers
@@ -359,7 +366,7 @@ __global__ void __launch_bounds__(DEC_NT, CTAS) decim8_async_kernel(const DecimP
         const int rel_lo = lo > c_base ? (int)(lo - c_base) : 0;
         hbf_stage<MC, GE::SB, GE::SB, GE::NB / 2 - OB, true, PRESET, 0>(be, bo, OB, nullptr, nullptr,
                                                                         p.out_fresh + (c_base - p.drain - p.out_split),
-                                                                        rel_lo, OB);
+                                                                        rel_lo, OB, c_base - p.drain - p.out_split, p.out_cap);
     }
 }
 
@@ -385,8 +392,10 @@ constexpr size_t decim_tma_smem_bytes()
 // fresh samples go to, so that buffer is valid from floor4(L) on and aligned 128-bit loads never have
 // to straddle the carry/fresh boundary.
 __global__ void carry_copy_kernel(StreamSrc src, long long g0, int n, float* __restrict__ dst,
-                                  float* __restrict__ head_dst, int head_n)
+                                  float* __restrict__ head_dst, int head_n, int dst_cap)
 {
+    SSPSD_ASSERT(n >= 0 && n <= dst_cap && head_n >= 0 && head_n < 4 && g0 >= src.carry_start - 0 * n);
+    (void)dst_cap;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
         float v = ld_stream1(src, g0 + i);
         dst[i] = v;

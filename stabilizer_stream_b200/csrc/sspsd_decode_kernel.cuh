@@ -124,6 +124,7 @@ __global__ void loss_kernel(const DecodeParams p)
 
 struct TraceOut {
     float* t[SSPSD_MAX_TRACES];
+    unsigned long long cap;  // floats available per trace (bounds-checking build)
 };
 
 __device__ __forceinline__ float4 adc_word(uint2 w, bool dac)
@@ -178,6 +179,7 @@ __global__ void __launch_bounds__(ADC_NT) adcdac_flat_kernel(const uint8_t* __re
             if (j < n_words8 && f < nb && r >= SSPSD_HEADER_SIZE && r < frame_len) {
                 const unsigned int w = (unsigned int)(r - SSPSD_HEADER_SIZE) >> 3;  // 8-byte word of the payload
                 const unsigned int b = w >> 3, c = (w >> 1) & 3u, h = w & 1u;
+                SSPSD_ASSERT(f * spf + b * 8u + h * 4u + 4u <= out.cap);
                 *reinterpret_cast<float4*>(out.t[c] + f * spf + b * 8u + h * 4u) = adc_word(v[u], c >= 2);
             }
             r += step;
@@ -201,6 +203,7 @@ __global__ void decode_generic_kernel(const uint8_t* __restrict__ frames, unsign
     unsigned int b = (unsigned int)(i - f * bat);
     const uint8_t* d = frames + f * stride + SSPSD_HEADER_SIZE + (unsigned long long)b * batch_bytes(fmt);
     const unsigned long long o = f * bat + b;
+    SSPSD_ASSERT((fmt == SSPSD_FORMAT_ADCDAC ? o * 8 + 8 : o + 1) <= out.cap);
     if (fmt == SSPSD_FORMAT_ADCDAC) {
         const float k = __int_as_float(0x39a3d70b);
         for (int c = 0; c < 4; ++c)

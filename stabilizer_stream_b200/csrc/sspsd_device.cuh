@@ -7,6 +7,17 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+// Bounds-checking build (make libsspsd_bounds.so, -DSSPSD_BOUNDS): every global-memory index a kernel forms from
+// run-time bookkeeping is asserted on the device against the extents the host passes along.  compute-sanitizer is
+// closed on the pool these kernels were developed on (profiles/r02_compute_sanitizer_refused.log), so this build
+// -- run over the parity, fuzz and group tests (tests/test_gpu_bounds.py) -- is the memory-safety evidence.
+#ifdef SSPSD_BOUNDS
+#include <assert.h>
+#define SSPSD_ASSERT(c) assert(c)
+#else
+#define SSPSD_ASSERT(c) ((void)0)
+#endif
+
 namespace sspsd {
 
 // ---------------------------------------------------------------------------------------------
@@ -20,10 +31,12 @@ struct StreamSrc {
     const float* fresh;
     long long carry_start;
     long long split;
+    long long end;  // one past the last valid sample (stream length after this batch)
 };
 
 __device__ __forceinline__ float4 ld_stream4(const StreamSrc& s, long long g)
 {
+    SSPSD_ASSERT(g + 4 <= s.end && (g & 3) == 0);
     if (g >= s.split)
         return __ldg(reinterpret_cast<const float4*>(s.fresh + (g - s.split)));
     if (g >= s.carry_start)
@@ -33,6 +46,7 @@ __device__ __forceinline__ float4 ld_stream4(const StreamSrc& s, long long g)
 
 __device__ __forceinline__ float ld_stream1(const StreamSrc& s, long long g)
 {
+    SSPSD_ASSERT(g < s.end);
     if (g >= s.split)
         return __ldg(s.fresh + (g - s.split));
     if (g >= s.carry_start)
@@ -79,6 +93,7 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t by
 // issue the copies of stream samples [g, g + n) into dst (n multiple of 4, g multiple of 4)
 __device__ __forceinline__ void ring_issue(const StreamSrc& s, long long g, int n, float* dst, uint64_t* bar)
 {
+    SSPSD_ASSERT(n >= 0 && (n & 3) == 0 && (g & 3) == 0 && (n == 0 || (g >= s.carry_start && g + n <= s.end)));
     mbar_expect_tx(bar, (uint32_t)n * 4u);
     long long nc = s.split - g;  // samples that live in the carry
     if (nc > n) nc = n;

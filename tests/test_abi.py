@@ -51,3 +51,20 @@ def test_no_cpu_fallback():
     with pytest.raises(_lib.SspsdError) as e:
         PsdCascade(512)
     assert e.value.status == _lib.ECUDA
+
+
+def test_bounds_build_carries_the_device_asserts_and_the_product_build_does_not():
+    """libsspsd_bounds.so (-DSSPSD_BOUNDS) is the memory-safety build the GPU tests run (tests/test_gpu_bounds.py); make
+    sure its device-side asserts are really compiled in, and that the product library is free of them."""
+    import os
+    here = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "stabilizer_stream_b200")
+    b = os.path.join(here, "libsspsd_bounds.so")
+    if not os.path.exists(b):
+        pytest.skip("libsspsd_bounds.so not built")
+    needles = [b"g + 4 <= s.end", b"gidx0 + r < gcap", b"<= out.cap"]
+    blob = open(b, "rb").read()
+    for n in needles:
+        assert n in blob, n
+    prod = open(os.path.join(here, "libsspsd.so"), "rb").read()
+    for n in needles:
+        assert n not in prod, n
