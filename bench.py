@@ -33,9 +33,9 @@ sys.path.insert(0, ROOT)
 N_FFT = 4096
 SAMPLES_PER_STEP = 200_000_000
 BYTES_PER_SAMPLE = 4.0  # algorithmic: every raw f32 sample must cross HBM once
-# measured DRAM traffic of the stage-0 PSD kernel: dram__bytes_read.sum + dram__bytes_write.sum = 270.94 MB +
-# 3.97 MB for a 2^26-sample launch (ncu --set full, profiles/r01_ncu_stage0_ring_metrics.csv)
-TRAFFIC_BYTES_PER_SAMPLE = (270.938624e6 + 3.97184e6) / (1 << 26)
+# measured DRAM traffic of the stage-0 PSD kernel: dram__bytes_read.sum + dram__bytes_write.sum = 270.96 MB +
+# 3.82 MB for a 2^26-sample launch (ncu --set full, profiles/r02_ncu_final_k2ring_k3tma_metrics.csv)
+TRAFFIC_BYTES_PER_SAMPLE = (270.964224e6 + 3.822336e6) / (1 << 26)
 # FP32 lane operations the stage-0 PSD kernel executes per input sample (ncu instruction mix of the final kernel,
 # profiles/r01_ncu_ring_packed_instruction_mix.csv: 2 x 43.41 M packed + 15.44 M scalar FP warp instructions for
 # 2^26 samples): the roof that actually bounds it -- explanatory, next to the contract's HBM roofline
@@ -381,7 +381,7 @@ def run_ours(args):
     roof = {"bound": "hbm", "kernel": "psd_stage_kernel_ring (stage 0, N=4096)", "achieved": achieved, "peak": peak,
             "peak_kind": peak_kind, "unit": "GB/s", "frac": achieved / peak,
             "traffic": TRAFFIC_BYTES_PER_SAMPLE * k_units / max(k_launches, 1),
-            "traffic_source": "ncu --set full, profiles/r01_ncu_stage0_ring_metrics.csv, scaled per sample",
+            "traffic_source": "ncu --set full, profiles/r02_ncu_final_k2ring_k3tma_metrics.csv, scaled per sample",
             "fp32_pipe": {"lane_ops_per_sample": FP32_LANE_OPS_PER_SAMPLE,
                           "achieved_Tops": FP32_LANE_OPS_PER_SAMPLE * k_units / (k_ms * 1e-3) / 1e12 if k_ms > 0 else 0.0,
                           "peak_Tops": 148 * 128 * (clocks.get("sm_max_mhz") or 1965.0) * 1e6 / 1e12,
