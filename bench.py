@@ -466,7 +466,7 @@ def timechunk_record(new_group, barrier, rank, world, dist, dev):
     return out
 
 
-def e2e_frames(local):
+def e2e_frames(local, chunk=1 << 16):
     """BASELINE config 3 end to end: AdcDac frames (22 batches, 1416 bytes; header + i16 ADC/DAC words, reference
     src/de/data.rs:12-82) in pinned HOST memory -> H2D -> frame decode + loss accounting -> four cascades
     (one per trace, src/bin/psd.rs:174-182) -> psd() of each.  2.011 bytes cross PCIe per trace sample instead
@@ -486,7 +486,8 @@ def e2e_frames(local):
     dec = FrameDecoder(local)
     cas = [PsdCascade(N_FFT, device=local) for _ in range(4)]
     loss = Loss()
-    chunk = 1 << 15   # frames per call: the decode call synchronises, the cascades of call c overlap the H2D of call c+1
+    # chunk = frames per call: the call returns once its frames are decoded (Loss is returned by value), the cascades of
+    # call c run while the frames of call c + 1 cross PCIe
 
     def one_pass():
         for f0 in range(0, n_frames, chunk):
@@ -503,7 +504,8 @@ def e2e_frames(local):
         times.append(time.perf_counter() - t0)
     dt = sorted(times)[len(times) // 2]   # median of 5 passes (host-clocked: the decode call synchronises per chunk)
     samples = 4 * n_frames * batches * 8
-    return {"value": samples / dt / 1e6, "unit": "M trace-samples/s", "frames_per_step": n_frames, "frame_bytes": flen,
+    return {"value": samples / dt / 1e6, "unit": "M trace-samples/s", "frames_per_step": n_frames, "frames_per_call": chunk,
+            "frame_bytes": flen,
             "h2d_bytes_per_step": n_frames * flen, "h2d_GBps": n_frames * flen / dt / 1e9, "seconds_per_step": dt,
             "seconds_per_step_all": times, "bytes_per_trace_sample": n_frames * flen / samples, "loss_received": int(loss.received), "loss_dropped": int(loss.dropped),
             "stage0_count": res[0][1][-1].count}

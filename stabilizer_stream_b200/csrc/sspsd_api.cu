@@ -356,24 +356,33 @@ void sspsd_decoder_destroy(sspsd_decoder* d)
 
 namespace {
 
+// queue the H2D copy of `n_bytes` of frames into the decoder's device buffer (d->stream)
+int frames_h2d(sspsd_decoder* d, const uint8_t* frames, size_t n_bytes)
+{
+    size_t need = (n_bytes + 15) & ~(size_t)15;
+    if (need > d->frames_cap) {
+        SSPSD_CUDA(cudaStreamSynchronize(d->stream));
+        if (d->d_frames) SSPSD_CUDA(cudaFree(d->d_frames));
+        d->d_frames = nullptr;
+        SSPSD_CUDA(cudaMalloc(&d->d_frames, need + 64));
+        d->frames_cap = need;
+    }
+    SSPSD_CUDA(cudaMemcpyAsync(d->d_frames, frames, n_bytes, cudaMemcpyHostToDevice, d->stream));
+    return SSPSD_OK;
+}
+
 // Runs scan + loss + payload decode on d->stream.  dst[t] are device pointers (aligned if `aligned`).
 // On return (stream synchronised) d->h_res holds the batch result.
 int decode_on_device(sspsd_decoder* d, const uint8_t* frames, size_t n_frames, size_t frame_len, size_t frame_stride,
-                     int frames_mem, const sspsd_loss* loss, float* const* dst, bool dst_aligned, size_t dst_cap)
+                     int frames_mem, const sspsd_loss* loss, float* const* dst, bool dst_aligned, size_t dst_cap,
+                     bool wait = true, int fmt_hint = -1)
 {
     using namespace sspsd;
     const size_t n_bytes = n_frames ? (n_frames - 1) * frame_stride + frame_len : 0;
     const uint8_t* dfr = frames;
     if (frames_mem == SSPSD_MEM_HOST) {
-        size_t need = (n_bytes + 15) & ~(size_t)15;
-        if (need > d->frames_cap) {
-            SSPSD_CUDA(cudaStreamSynchronize(d->stream));
-            if (d->d_frames) SSPSD_CUDA(cudaFree(d->d_frames));
-            d->d_frames = nullptr;
-            SSPSD_CUDA(cudaMalloc(&d->d_frames, need + 64));
-            d->frames_cap = need;
-        }
-        SSPSD_CUDA(cudaMemcpyAsync(d->d_frames, frames, n_bytes, cudaMemcpyHostToDevice, d->stream));
+        int rc = frames_h2d(d, frames, n_bytes);
+        if (rc) return rc;
         dfr = d->d_frames;
     }
     // the trace buffers the decode kernels are about to overwrite may still be read by the cascades of the previous
@@ -417,7 +426,9 @@ int decode_on_device(sspsd_decoder* d, const uint8_t* frames, size_t n_frames, s
         // The format byte of frame 0 decides the kernel; peek at it on the host when the frames are host
         // memory, otherwise read it back (4 bytes) -- the call synchronises for the result anyway.
         uint8_t hdr[4] = {0, 0, 0, 0};
-        if (frames_mem == SSPSD_MEM_HOST) {
+        if (fmt_hint >= 0) {
+            hdr[2] = (uint8_t)fmt_hint;  // the caller has already looked at the headers
+        } else if (frames_mem == SSPSD_MEM_HOST) {
             if (n_bytes >= 4) std::memcpy(hdr, frames, 4);
         } else if (n_bytes >= 4) {
             SSPSD_CUDA(cudaMemcpyAsync(hdr, dfr, 4, cudaMemcpyDeviceToHost, d->stream));
@@ -442,6 +453,17 @@ int decode_on_device(sspsd_decoder* d, const uint8_t* frames, size_t n_frames, s
         }
     }
     SSPSD_CUDA(cudaMemcpyAsync(d->h_res, d->d_res, sizeof(DecodeResult), cudaMemcpyDeviceToHost, d->stream));
+    if (!wait) {
+        // the caller queues its consumers behind ev_decoded and synchronises later (decode_wait)
+        SSPSD_CUDA(cudaEventRecord(d->ev_decoded, d->stream));
+        return SSPSD_OK;
+    }
+    SSPSD_CUDA(cudaStreamSynchronize(d->stream));
+    return SSPSD_OK;
+}
+
+int decode_wait(sspsd_decoder* d)
+{
     SSPSD_CUDA(cudaStreamSynchronize(d->stream));
     return SSPSD_OK;
 }
@@ -585,6 +607,60 @@ int32_t sspsd_cascade_process_frames(sspsd_decoder* d, sspsd_cascade* const* cas
             SSPSD_CUDA(cudaMalloc(&d->d_traces[t], (worst + 64) * sizeof(float)));
         }
         d->traces_cap = worst;
+    }
+    if (frames_mem == SSPSD_MEM_HOST) {
+        // Host frames: the 8-byte headers are validated here first (the same frame_status() the scan kernel runs), so
+        // the number of good frames, the format and the batch count are known before anything is queued.  The frames'
+        // H2D copy, the scan / loss / decode kernels and -- behind an event -- the cascades are then queued without a
+        // host round trip in between; the only wait is for the loss counters at the end, by which time the next call's
+        // copy can start right away (the synchronous version left PCIe idle while the host launched four cascades).
+        const size_t n_bytes = (n_frames - 1) * frame_stride + frame_len;
+        int rc = frames_h2d(d, frames, n_bytes);  // the DMA of the whole batch starts now ...
+        if (rc) return rc;
+        // ... and the host walks the headers meanwhile (one cache line per frame, prefetched ahead)
+        const unsigned int fmt0 = frames[2];
+        const unsigned int want_fmt = (fmt0 >= 1 && fmt0 <= 4) ? fmt0 : 0;
+        size_t n_ok = 0;
+        unsigned int bad_status = SSPSD_OK;
+        for (; n_ok < n_frames; ++n_ok) {
+            if (n_ok + 24 < n_frames) __builtin_prefetch(frames + (n_ok + 24) * frame_stride);
+            bad_status = sspsd::frame_status(frames + n_ok * frame_stride, frame_len, want_fmt);
+            if (bad_status != SSPSD_OK) break;
+        }
+        if (n_ok == 0) {
+            SSPSD_CUDA(cudaStreamSynchronize(d->stream));  // the caller's buffer is borrowed for the call only
+            if (info) std::memset(info, 0, sizeof(*info));
+            set_error("malformed frame");
+            return (int32_t)bad_status;
+        }
+        const unsigned int batches = frames[3];
+        const unsigned int div = fmt0 == SSPSD_FORMAT_ADCDAC ? 8 : 1;
+        const size_t ns = n_ok * batches * div;
+        const uint32_t ntr = fmt0 == SSPSD_FORMAT_MPLL ? 3 : 4;
+        rc = decode_on_device(d, d->d_frames, n_ok, frame_len, frame_stride, SSPSD_MEM_DEVICE, loss, d->d_traces, true,
+                              d->traces_cap, /*wait=*/false, (int)fmt0);
+        if (rc) return rc;
+        for (uint32_t t = 0; t < n_cascades && t < ntr; ++t) {
+            if (!cascades[t]) continue;
+            SSPSD_CUDA(cudaStreamWaitEvent(cascades[t]->c.stream(), d->ev_decoded, 0));
+            rc = cascades[t]->c.process(d->d_traces[t], ns, SSPSD_MEM_DEVICE);
+            if (rc) return rc;
+            SSPSD_CUDA(cudaEventRecord(d->ev_consumed[t], cascades[t]->c.stream()));
+            d->consumed_pending[t] = true;
+        }
+        rc = decode_wait(d);
+        if (rc) return rc;
+        const sspsd::DecodeResult r = *d->h_res;
+        if (r.first_bad != n_ok || r.format != fmt0 || r.batches != batches) {
+            set_error("internal: device scan disagrees with the host pre-scan");
+            return SSPSD_EINVAL;
+        }
+        apply_result(r, n_ok, loss, info, div);
+        if (n_ok < n_frames) {
+            set_error("malformed frame");
+            return (int32_t)bad_status;
+        }
+        return SSPSD_OK;
     }
     int rc = decode_on_device(d, frames, n_frames, frame_len, frame_stride, frames_mem, loss, d->d_traces, true, d->traces_cap);
     if (rc) return rc;

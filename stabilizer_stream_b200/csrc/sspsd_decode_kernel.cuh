@@ -37,7 +37,7 @@ struct DecodeParams {
     unsigned int has_prev;
 };
 
-__device__ __forceinline__ unsigned int batch_bytes(unsigned int format)
+__host__ __device__ __forceinline__ unsigned int batch_bytes(unsigned int format)
 {
     // AdcDac [[[[u8;2];8];4]] = 64, Fls [[[u8;4];7];2] = 56, ThermostatEem [[u8;4];20] = 80, Mpll [[u8;4];6] = 24
     return format == 1 ? 64u : format == 2 ? 56u : format == 3 ? 80u : 24u;
@@ -49,7 +49,7 @@ __device__ __forceinline__ unsigned int rd_u32(const uint8_t* p)
 }
 
 // status of one frame; fmt0 = format the batch must have (0: take this frame's)
-__device__ __forceinline__ unsigned int frame_status(const uint8_t* f, unsigned long long len, unsigned int fmt0)
+__host__ __device__ __forceinline__ unsigned int frame_status(const uint8_t* f, unsigned long long len, unsigned int fmt0)
 {
     if (len < SSPSD_HEADER_SIZE) return SSPSD_ESHORT;            // frame.rs:50
     if (f[0] != 0x7b || f[1] != 0x05) return SSPSD_EHEADER;      // frame.rs:26-28
