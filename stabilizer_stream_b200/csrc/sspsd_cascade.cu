@@ -86,7 +86,7 @@ int k2_variant_from_env()
 {
     const char* e = getenv("SSPSD_K2");
     std::string m = e ? e : "ring";
-    return m == "r8" ? 0 : m == "r16" ? 1 : 2;
+    return m == "r8" ? 0 : m == "r16" ? 1 : m == "ring1" ? 3 : 2;
 }
 
 int launch_stage(int log2n, bool r16, const StageParams& p, int grid, cudaStream_t s)
@@ -117,6 +117,8 @@ int prepare_stage(int log2n, bool r16, int hop, int* tmax, int* nt)
                                         (int)stage_r16_smem_bytes(t, hop)));
         SSPSD_CUDA(cudaFuncSetAttribute(psd_stage_kernel_ring, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                         (int)stage_ring_smem_bytes(RingCfg::MAX_W)));
+        SSPSD_CUDA(cudaFuncSetAttribute(psd_stage_kernel_ring1, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        (int)stage_ring_smem_bytes(1024, 1, RingCfg::RING1, false)));
         return SSPSD_OK;
     }
     if (log2n == 9)
@@ -520,7 +522,7 @@ int Cascade::launch_psd(size_t i, const StreamSrc& src, uint64_t k0, uint64_t ns
     p.k0 = (long long)k0;
     p.nseg = (int)nseg;
     long long t = ((long long)nseg + 2ll * num_sms_ - 1) / (2ll * num_sms_);
-    if (log2n_ == 9 && k2_variant_ == 2 && hop_ * 2 == n_) {
+    if (log2n_ == 9 && k2_variant_ >= 2 && hop_ * 2 == n_) {
         // N = 512, Hann: warp-level kernel (half a warp per segment, shuffles for the real-input split), persistent
         p.T = (int)std::max<long long>(W16::SPI, std::min<long long>(t, W16::MAX_T));
         p.hop = (int)hop_;
@@ -542,7 +544,30 @@ int Cascade::launch_psd(size_t i, const StreamSrc& src, uint64_t k0, uint64_t ns
         if (!cuda_ok(cudaGetLastError(), "psd_stage_kernel_w16 launch")) return SSPSD_ECUDA;
         return reduce_partials(i, grid * W16::SPI, p);
     }
-    const bool ring = log2n_ == 12 && k2_variant_ == 2 && hop_ * 2 == n_;
+    const bool ring = log2n_ == 12 && k2_variant_ >= 2 && hop_ * 2 == n_;
+    if (ring && k2_variant_ == 3) {
+        // four independent single-group CTAs per SM (A/B variant, SSPSD_K2=ring1)
+        long long t1 = ((long long)nseg + 4ll * num_sms_ - 1) / (4ll * num_sms_);
+        p.T = (int)std::max<long long>(1, std::min<long long>(t1, 1024));
+        p.hop = (int)hop_;
+        p.detrend = detrend_;
+        p.tile_cap = 0;
+        p.win = d_win_;
+        p.twM = d_twM_;
+        p.twN = d_twN_;
+        p.acc = d_acc_ + i * acc_stride_;
+        p.jb = jb;
+        p.g_first = g_first;
+        p.g_s = g_s;
+        int grid = (int)((nseg + p.T - 1) / p.T);
+        int rcp = prepare_partials(i, grid, &p);
+        if (rcp) return rcp;
+        prof_begin(i == 0 ? SSPSD_PROF_PSD_STAGE0 : SSPSD_PROF_PSD_DEEP, nseg * (uint64_t)hop_, psd_stream(i));
+        psd_stage_kernel_ring1<<<grid, R16::TPS, stage_ring_smem_bytes(p.T, 1, RingCfg::RING1, false), psd_stream(i)>>>(p);
+        prof_end(psd_stream(i));
+        if (!cuda_ok(cudaGetLastError(), "psd_stage_kernel_ring1 launch")) return SSPSD_ECUDA;
+        return reduce_partials(i, grid, p);
+    }
     if (ring) {
         // persistent kernel: two CTAs per SM, each streams through a contiguous range of segments
         // with the deep stages overlapping on a second stream, stage 0 is cut into ~4 waves of CTAs so

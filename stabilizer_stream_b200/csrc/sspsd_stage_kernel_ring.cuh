@@ -21,18 +21,21 @@ namespace sspsd {
 
 struct RingCfg {
     static constexpr int RING = 6;        // hop slots (8 KiB each at N = 4096)
+    static constexpr int RING1 = 4;       // single-group variant: hops s, s + 1 in use, two in flight
     static constexpr int MAX_W = 2048;    // per-CTA weight table (segments per CTA upper bound)
 };
 
-__global__ void __launch_bounds__(R16::NT, 2) psd_stage_kernel_ring(const StageParams p)
+// G = 128-thread groups (segments in flight) per CTA, RING = hop slots, WIN_SMEM = window table in shared memory (else
+// re-read through L1 with LDG.64: the table is 16 KiB per CTA, too much for four single-group CTAs per SM)
+template <int G, int RING, bool WIN_SMEM>
+__device__ __forceinline__ void psd_stage_ring_body(const StageParams& p)
 {
-    constexpr int N = R16::N, M = R16::M, TPS = R16::TPS, NT = R16::NT, G = R16::G, K = R16::K, WS = R16::WS;
+    constexpr int N = R16::N, M = R16::M, TPS = R16::TPS, NT = TPS * G, K = R16::K, WS = R16::WS;
     constexpr int HOP = N / 2;  // Hann; the rectangular window uses the tiled kernel
-    constexpr int RING = RingCfg::RING;
     extern __shared__ __align__(16) float smem[];
     float* ring = smem;                      // RING * HOP
-    float2* wtab = reinterpret_cast<float2*>(ring + RING * HOP);  // the window as N/2 pairs (16 KiB)
-    float* wsb = ring + RING * HOP + N;      // G * 2 * WS
+    float2* wtab = reinterpret_cast<float2*>(ring + RING * HOP);  // the window as N/2 pairs (16 KiB), if WIN_SMEM
+    float* wsb = ring + RING * HOP + (WIN_SMEM ? N : 0);      // G * 2 * WS
     float* wgt = wsb + G * 2 * WS;           // p.T entries (segments per CTA)
     float* red = wgt + ((p.T + 3) & ~3);     // G * 4
     uint64_t* bars = reinterpret_cast<uint64_t*>(red + 8);  // RING mbarriers (8-byte aligned: all counts above are even)
@@ -69,7 +72,9 @@ __global__ void __launch_bounds__(R16::NT, 2) psd_stage_kernel_ring(const StageP
     // ---- segment-invariant per-thread constants (as in the tiled radix-16 kernel) ----
     // the window lives in shared memory (one LDS.64 per point and segment): the packed arithmetic needs
     // aligned register pairs, and 32 registers of window values no longer fit beside it
-    for (int i = tid; i < N / 2; i += NT) wtab[i] = __ldg(reinterpret_cast<const float2*>(p.win) + i);
+    if constexpr (WIN_SMEM)
+        for (int i = tid; i < N / 2; i += NT) wtab[i] = __ldg(reinterpret_cast<const float2*>(p.win) + i);
+    const float2* __restrict__ gwin = reinterpret_cast<const float2*>(p.win);
     const float2 a1 = __ldg(&p.twM[j]), a2 = __ldg(&p.twM[2 * j]), a4 = __ldg(&p.twM[4 * j]), a8 = __ldg(&p.twM[8 * j]);
     const int o = j & 7;
     const float2 b1 = __ldg(&p.twM[16 * o]), b2 = __ldg(&p.twM[32 * o]), b4 = __ldg(&p.twM[64 * o]),
@@ -144,7 +149,7 @@ __global__ void __launch_bounds__(R16::NT, 2) psd_stage_kernel_ring(const StageP
             for (int t = 0; t < 16; ++t) v[t] = __fadd2_rn(v[t], make_float2(-off, -off));
         }
 #pragma unroll
-        for (int t = 0; t < 16; ++t) v[t] = __fmul2_rn(v[t], wtab[j + t * TPS]);
+        for (int t = 0; t < 16; ++t) v[t] = __fmul2_rn(v[t], WIN_SMEM ? wtab[j + t * TPS] : __ldg(gwin + j + t * TPS));
 
         dft16(v);
         twiddle16(v, a1, a2, a4, a8);
@@ -250,10 +255,23 @@ __global__ void __launch_bounds__(R16::NT, 2) psd_stage_kernel_ring(const StageP
     }
 }
 
-inline size_t stage_ring_smem_bytes(int segs_per_cta)
+// default: two groups per CTA, two CTAs per SM, window in shared memory
+__global__ void __launch_bounds__(R16::NT, 2) psd_stage_kernel_ring(const StageParams p)
 {
-    size_t fl = (size_t)RingCfg::RING * (R16::N / 2) + R16::N + (size_t)R16::G * 2 * R16::WS + ((segs_per_cta + 3) & ~3) + 8;
-    return fl * sizeof(float) + RingCfg::RING * sizeof(uint64_t) + 16;
+    psd_stage_ring_body<R16::G, RingCfg::RING, true>(p);
+}
+
+// variant (SSPSD_K2=ring1): four independent single-group CTAs per SM -- no CTA-wide barrier couples two groups, the
+// groups of an SM drift apart freely; 3-slot ring, window through L1
+__global__ void __launch_bounds__(R16::TPS, 4) psd_stage_kernel_ring1(const StageParams p)
+{
+    psd_stage_ring_body<1, RingCfg::RING1, false>(p);
+}
+
+inline size_t stage_ring_smem_bytes(int segs_per_cta, int groups = R16::G, int ring = RingCfg::RING, bool win_smem = true)
+{
+    size_t fl = (size_t)ring * (R16::N / 2) + (win_smem ? R16::N : 0) + (size_t)groups * 2 * R16::WS + ((segs_per_cta + 3) & ~3) + 8;
+    return fl * sizeof(float) + ring * sizeof(uint64_t) + 16;
 }
 
 }  // namespace sspsd
