@@ -1,5 +1,8 @@
 // sspsd_api.cu -- extern "C" boundary (include/sspsd.h) over the internal C++ classes.
+#include <chrono>
 #include <cmath>
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <vector>
@@ -19,8 +22,12 @@ struct sspsd_decoder {
     size_t frames_cap = 0;
     unsigned int* d_status = nullptr;
     size_t status_cap = 0;
-    sspsd::DecodeResult* d_res = nullptr;
-    sspsd::DecodeResult* h_res = nullptr;  // pinned
+    static constexpr int MAX_SUB = 8;      // sub-chunks of one sspsd_cascade_process_frames call (host frames)
+    sspsd::DecodeResult* d_res = nullptr;  // MAX_SUB result slots
+    sspsd::DecodeResult* h_res = nullptr;  // pinned, MAX_SUB
+    cudaStream_t h2d_stream = nullptr;     // the sub-chunks' copies, so that decode k runs while sub-chunk k + 1 crosses PCIe
+    cudaEvent_t ev_copied[MAX_SUB] = {};
+
     float* d_traces[SSPSD_MAX_TRACES] = {nullptr, nullptr, nullptr, nullptr};
     size_t traces_cap = 0;
     cudaEvent_t ev_decoded = nullptr;
@@ -314,8 +321,11 @@ int32_t sspsd_decoder_create(int32_t device, void* stream, sspsd_decoder** out)
         ok = ok && sspsd::cuda_ok(cudaStreamCreateWithFlags(&d->stream, cudaStreamNonBlocking), "cudaStreamCreate");
         d->own_stream = ok;
     }
-    ok = ok && sspsd::cuda_ok(cudaMalloc(&d->d_res, sizeof(sspsd::DecodeResult)), "cudaMalloc");
-    ok = ok && sspsd::cuda_ok(cudaMallocHost(&d->h_res, sizeof(sspsd::DecodeResult)), "cudaMallocHost");
+    ok = ok && sspsd::cuda_ok(cudaMalloc(&d->d_res, sspsd_decoder::MAX_SUB * sizeof(sspsd::DecodeResult)), "cudaMalloc");
+    ok = ok && sspsd::cuda_ok(cudaMallocHost(&d->h_res, sspsd_decoder::MAX_SUB * sizeof(sspsd::DecodeResult)), "cudaMallocHost");
+    ok = ok && sspsd::cuda_ok(cudaStreamCreateWithFlags(&d->h2d_stream, cudaStreamNonBlocking), "cudaStreamCreate");
+    for (int k = 0; k < sspsd_decoder::MAX_SUB && ok; ++k)
+        ok = sspsd::cuda_ok(cudaEventCreateWithFlags(&d->ev_copied[k], cudaEventDisableTiming), "cudaEventCreate");
     ok = ok && sspsd::cuda_ok(cudaEventCreateWithFlags(&d->ev_decoded, cudaEventDisableTiming), "cudaEventCreate");
     for (int t = 0; t < SSPSD_MAX_TRACES && ok; ++t)
         ok = sspsd::cuda_ok(cudaEventCreateWithFlags(&d->ev_consumed[t], cudaEventDisableTiming), "cudaEventCreate");
@@ -339,6 +349,12 @@ void sspsd_decoder_destroy(sspsd_decoder* d)
     if (!d) return;
     DevGuard g(d->device);
     if (d->stream) cudaStreamSynchronize(d->stream);
+    if (d->h2d_stream) {
+        cudaStreamSynchronize(d->h2d_stream);
+        cudaStreamDestroy(d->h2d_stream);
+    }
+    for (auto& e : d->ev_copied)
+        if (e) cudaEventDestroy(e);
     cudaFree(d->d_frames);
     cudaFree(d->d_status);
     cudaFree(d->d_res);
@@ -356,42 +372,32 @@ void sspsd_decoder_destroy(sspsd_decoder* d)
 
 namespace {
 
-// queue the H2D copy of `n_bytes` of frames into the decoder's device buffer (d->stream)
-int frames_h2d(sspsd_decoder* d, const uint8_t* frames, size_t n_bytes)
+// make room for `n_bytes` of frames in the decoder's device buffer
+int frames_reserve(sspsd_decoder* d, size_t n_bytes)
 {
     size_t need = (n_bytes + 15) & ~(size_t)15;
     if (need > d->frames_cap) {
         SSPSD_CUDA(cudaStreamSynchronize(d->stream));
+        SSPSD_CUDA(cudaStreamSynchronize(d->h2d_stream));
         if (d->d_frames) SSPSD_CUDA(cudaFree(d->d_frames));
         d->d_frames = nullptr;
         SSPSD_CUDA(cudaMalloc(&d->d_frames, need + 64));
         d->frames_cap = need;
     }
+    return SSPSD_OK;
+}
+
+// queue the H2D copy of `n_bytes` of frames into the decoder's device buffer (d->stream)
+int frames_h2d(sspsd_decoder* d, const uint8_t* frames, size_t n_bytes)
+{
+    int rc = frames_reserve(d, n_bytes);
+    if (rc) return rc;
     SSPSD_CUDA(cudaMemcpyAsync(d->d_frames, frames, n_bytes, cudaMemcpyHostToDevice, d->stream));
     return SSPSD_OK;
 }
 
-// Runs scan + loss + payload decode on d->stream.  dst[t] are device pointers (aligned if `aligned`).
-// On return (stream synchronised) d->h_res holds the batch result.
-int decode_on_device(sspsd_decoder* d, const uint8_t* frames, size_t n_frames, size_t frame_len, size_t frame_stride,
-                     int frames_mem, const sspsd_loss* loss, float* const* dst, bool dst_aligned, size_t dst_cap,
-                     bool wait = true, int fmt_hint = -1)
+int status_reserve(sspsd_decoder* d, size_t n_frames)
 {
-    using namespace sspsd;
-    const size_t n_bytes = n_frames ? (n_frames - 1) * frame_stride + frame_len : 0;
-    const uint8_t* dfr = frames;
-    if (frames_mem == SSPSD_MEM_HOST) {
-        int rc = frames_h2d(d, frames, n_bytes);
-        if (rc) return rc;
-        dfr = d->d_frames;
-    }
-    // the trace buffers the decode kernels are about to overwrite may still be read by the cascades of the previous
-    // sspsd_cascade_process_frames call (other streams)
-    for (int t = 0; t < SSPSD_MAX_TRACES; ++t)
-        if (d->consumed_pending[t]) {
-            SSPSD_CUDA(cudaStreamWaitEvent(d->stream, d->ev_consumed[t], 0));
-            d->consumed_pending[t] = false;
-        }
     if (n_frames > d->status_cap) {
         SSPSD_CUDA(cudaStreamSynchronize(d->stream));
         if (d->d_status) SSPSD_CUDA(cudaFree(d->d_status));
@@ -399,17 +405,40 @@ int decode_on_device(sspsd_decoder* d, const uint8_t* frames, size_t n_frames, s
         SSPSD_CUDA(cudaMalloc(&d->d_status, (n_frames + 64) * sizeof(unsigned int)));
         d->status_cap = n_frames + 64;
     }
+    return SSPSD_OK;
+}
+
+// the trace buffers the decode kernels are about to overwrite may still be read by the cascades of the previous
+// sspsd_cascade_process_frames call (other streams)
+int wait_traces_consumed(sspsd_decoder* d)
+{
+    for (int t = 0; t < SSPSD_MAX_TRACES; ++t)
+        if (d->consumed_pending[t]) {
+            SSPSD_CUDA(cudaStreamWaitEvent(d->stream, d->ev_consumed[t], 0));
+            d->consumed_pending[t] = false;
+        }
+    return SSPSD_OK;
+}
+
+// Queues scan + loss + payload decode of `n_frames` DEVICE-resident frames on d->stream and the read-back of the result
+// into h_res[slot].  `fmt` = format byte of frame 0 (selects the payload kernel), status words at d_status + status_off,
+// dst[t] device pointers (16-byte aligned if `dst_aligned`) with room for dst_cap items each.
+int queue_decode(sspsd_decoder* d, const uint8_t* dfr, size_t n_frames, size_t status_off, size_t frame_len, size_t frame_stride,
+                 const sspsd_loss* loss, float* const* dst, bool dst_aligned, size_t dst_cap, unsigned int fmt, int slot)
+{
+    using namespace sspsd;
+    const size_t n_bytes = n_frames ? (n_frames - 1) * frame_stride + frame_len : 0;
     DecodeResult init{};
     init.first_bad = n_frames;
-    *d->h_res = init;
-    SSPSD_CUDA(cudaMemcpyAsync(d->d_res, d->h_res, sizeof(init), cudaMemcpyHostToDevice, d->stream));
+    d->h_res[slot] = init;
+    SSPSD_CUDA(cudaMemcpyAsync(d->d_res + slot, d->h_res + slot, sizeof(init), cudaMemcpyHostToDevice, d->stream));
     DecodeParams p{};
     p.frames = dfr;
     p.n_frames = n_frames;
     p.frame_len = frame_len;
     p.frame_stride = frame_stride;
-    p.status = d->d_status;
-    p.res = d->d_res;
+    p.status = d->d_status + status_off;
+    p.res = d->d_res + slot;
     p.prev_seq = loss ? loss->seq : 0;
     p.has_prev = loss ? (loss->has_seq != 0) : 0;
     const int nt = 256;
@@ -417,47 +446,61 @@ int decode_on_device(sspsd_decoder* d, const uint8_t* frames, size_t n_frames, s
     frame_scan_kernel<<<gf, nt, 0, d->stream>>>(p);
     loss_kernel<<<(unsigned int)((n_frames + 1 + nt - 1) / nt), nt, 0, d->stream>>>(p);
     SSPSD_CUDA(cudaGetLastError());
-    if (dst) {
+    if (dst && fmt >= 1 && fmt <= 4 && frame_len >= SSPSD_HEADER_SIZE) {
         TraceOut out{};
         for (int t = 0; t < SSPSD_MAX_TRACES; ++t) out.t[t] = dst[t];
         out.cap = dst_cap;
         const bool flat_ok = dst_aligned && (reinterpret_cast<uintptr_t>(dfr) % 8 == 0) && (frame_stride % 8 == 0) &&
-                             frame_len >= SSPSD_HEADER_SIZE && ((frame_len - SSPSD_HEADER_SIZE) % 64 == 0);
-        // The format byte of frame 0 decides the kernel; peek at it on the host when the frames are host
-        // memory, otherwise read it back (4 bytes) -- the call synchronises for the result anyway.
-        uint8_t hdr[4] = {0, 0, 0, 0};
-        if (fmt_hint >= 0) {
-            hdr[2] = (uint8_t)fmt_hint;  // the caller has already looked at the headers
-        } else if (frames_mem == SSPSD_MEM_HOST) {
+                             ((frame_len - SSPSD_HEADER_SIZE) % 64 == 0);
+        if (fmt == SSPSD_FORMAT_ADCDAC && flat_ok) {
+            const unsigned long long n_words8 = n_bytes / 8;
+            const unsigned long long per_cta = (unsigned long long)ADC_NT * ADC_ITERS;
+            adcdac_flat_kernel<<<(unsigned int)((n_words8 + per_cta - 1) / per_cta), ADC_NT, 0, d->stream>>>(
+                dfr, n_words8, frame_stride, frame_len, d->d_res + slot, out);
+        } else {
+            const unsigned int bb = batch_bytes(fmt);
+            unsigned long long per = (frame_len - SSPSD_HEADER_SIZE) / bb;
+            unsigned long long total = n_frames * per;
+            if (total)
+                decode_generic_kernel<<<(unsigned int)((total + nt - 1) / nt), nt, 0, d->stream>>>(
+                    dfr, frame_stride, d->d_res + slot, out);
+        }
+        SSPSD_CUDA(cudaGetLastError());
+    }
+    SSPSD_CUDA(cudaMemcpyAsync(d->h_res + slot, d->d_res + slot, sizeof(DecodeResult), cudaMemcpyDeviceToHost, d->stream));
+    return SSPSD_OK;
+}
+
+// Runs scan + loss + payload decode on d->stream.  dst[t] are device pointers (aligned if `aligned`).
+// On return (stream synchronised) d->h_res[0] holds the batch result.
+int decode_on_device(sspsd_decoder* d, const uint8_t* frames, size_t n_frames, size_t frame_len, size_t frame_stride,
+                     int frames_mem, const sspsd_loss* loss, float* const* dst, bool dst_aligned, size_t dst_cap)
+{
+    const size_t n_bytes = n_frames ? (n_frames - 1) * frame_stride + frame_len : 0;
+    const uint8_t* dfr = frames;
+    int rc;
+    if (frames_mem == SSPSD_MEM_HOST) {
+        rc = frames_h2d(d, frames, n_bytes);
+        if (rc) return rc;
+        dfr = d->d_frames;
+    }
+    rc = wait_traces_consumed(d);
+    if (rc) return rc;
+    rc = status_reserve(d, n_frames);
+    if (rc) return rc;
+    // The format byte of frame 0 decides the kernel; peek at it on the host when the frames are host
+    // memory, otherwise read it back (4 bytes) -- the call synchronises for the result anyway.
+    uint8_t hdr[4] = {0, 0, 0, 0};
+    if (dst) {
+        if (frames_mem == SSPSD_MEM_HOST) {
             if (n_bytes >= 4) std::memcpy(hdr, frames, 4);
         } else if (n_bytes >= 4) {
             SSPSD_CUDA(cudaMemcpyAsync(hdr, dfr, 4, cudaMemcpyDeviceToHost, d->stream));
             SSPSD_CUDA(cudaStreamSynchronize(d->stream));
         }
-        const unsigned int fmt = hdr[2];
-        if (fmt >= 1 && fmt <= 4 && frame_len >= SSPSD_HEADER_SIZE) {
-            if (fmt == SSPSD_FORMAT_ADCDAC && flat_ok) {
-                const unsigned long long n_words8 = n_bytes / 8;
-                const unsigned long long per_cta = (unsigned long long)ADC_NT * ADC_ITERS;
-                adcdac_flat_kernel<<<(unsigned int)((n_words8 + per_cta - 1) / per_cta), ADC_NT, 0, d->stream>>>(
-                    dfr, n_words8, frame_stride, frame_len, d->d_res, out);
-            } else {
-                const unsigned int bb = fmt == 1 ? 64u : fmt == 2 ? 56u : fmt == 3 ? 80u : 24u;
-                unsigned long long per = (frame_len - SSPSD_HEADER_SIZE) / bb;
-                unsigned long long total = n_frames * per;
-                if (total)
-                    decode_generic_kernel<<<(unsigned int)((total + nt - 1) / nt), nt, 0, d->stream>>>(
-                        dfr, frame_stride, d->d_res, out);
-            }
-            SSPSD_CUDA(cudaGetLastError());
-        }
     }
-    SSPSD_CUDA(cudaMemcpyAsync(d->h_res, d->d_res, sizeof(DecodeResult), cudaMemcpyDeviceToHost, d->stream));
-    if (!wait) {
-        // the caller queues its consumers behind ev_decoded and synchronises later (decode_wait)
-        SSPSD_CUDA(cudaEventRecord(d->ev_decoded, d->stream));
-        return SSPSD_OK;
-    }
+    rc = queue_decode(d, dfr, n_frames, 0, frame_len, frame_stride, loss, dst, dst_aligned, dst_cap, hdr[2], 0);
+    if (rc) return rc;
     SSPSD_CUDA(cudaStreamSynchronize(d->stream));
     return SSPSD_OK;
 }
@@ -609,53 +652,123 @@ int32_t sspsd_cascade_process_frames(sspsd_decoder* d, sspsd_cascade* const* cas
         d->traces_cap = worst;
     }
     if (frames_mem == SSPSD_MEM_HOST) {
-        // Host frames: the 8-byte headers are validated here first (the same frame_status() the scan kernel runs), so
-        // the number of good frames, the format and the batch count are known before anything is queued.  The frames'
-        // H2D copy, the scan / loss / decode kernels and -- behind an event -- the cascades are then queued without a
-        // host round trip in between; the only wait is for the loss counters at the end, by which time the next call's
-        // copy can start right away (the synchronous version left PCIe idle while the host launched four cascades).
+        // Host frames.  The batch is cut into up to MAX_SUB sub-chunks whose H2D copies are all queued up front on the
+        // decoder's copy stream.  While sub-chunk k crosses PCIe the host validates its 8-byte headers (the same
+        // frame_status() the scan kernel runs, one cache line per frame, prefetched ahead) and applies Loss::update to
+        // them, so the number of good frames, the format, the batch count and the sequence state the NEXT sub-chunk starts
+        // from are known without a device round trip; scan / loss / payload decode of sub-chunk k are queued behind its
+        // copy and the cascades behind its decode, so they run while sub-chunk k + 1 is still being copied.  The one
+        // wait is at the end (the caller's buffer is borrowed for the call only, and the loss counters the device
+        // computed are the ones returned: the host's serve as a cross-check).
+        static const bool trace = getenv("SSPSD_FRAMES_TRACE") != nullptr;
+        using clk = std::chrono::steady_clock;
+        const auto t0 = clk::now();
         const size_t n_bytes = (n_frames - 1) * frame_stride + frame_len;
-        int rc = frames_h2d(d, frames, n_bytes);  // the DMA of the whole batch starts now ...
+        int rc = frames_reserve(d, n_bytes);
         if (rc) return rc;
-        // ... and the host walks the headers meanwhile (one cache line per frame, prefetched ahead)
+        rc = status_reserve(d, n_frames);
+        if (rc) return rc;
+        // sub-chunks of >= 16384 frames: the host needs ~0.2 ms per sub-chunk (headers + launching the cascades)
+        const size_t n_sub = std::max<size_t>(1, std::min<size_t>(sspsd_decoder::MAX_SUB, n_frames >> 14));
+        const size_t per = (n_frames + n_sub - 1) / n_sub;
+        for (size_t k = 0; k < n_sub; ++k) {
+            const size_t f0 = k * per, f1 = std::min(n_frames, f0 + per);
+            const size_t nb = (f1 - 1 - f0) * frame_stride + frame_len;
+            SSPSD_CUDA(cudaMemcpyAsync(d->d_frames + f0 * frame_stride, frames + f0 * frame_stride, nb, cudaMemcpyHostToDevice,
+                                       d->h2d_stream));
+            SSPSD_CUDA(cudaEventRecord(d->ev_copied[k], d->h2d_stream));
+        }
+        const auto t1 = clk::now();
+        rc = wait_traces_consumed(d);
+        if (rc) return rc;
         const unsigned int fmt0 = frames[2];
         const unsigned int want_fmt = (fmt0 >= 1 && fmt0 <= 4) ? fmt0 : 0;
-        size_t n_ok = 0;
+        const unsigned int batches = frames[3];
+        const unsigned int div = fmt0 == SSPSD_FORMAT_ADCDAC ? 8 : 1;
+        const uint32_t ntr = fmt0 == SSPSD_FORMAT_MPLL ? 3 : 4;
+        sspsd_loss hl{};  // the host's own Loss::update over the headers
+        if (loss) hl = *loss;
+        size_t n_ok = 0, queued = 0;
         unsigned int bad_status = SSPSD_OK;
-        for (; n_ok < n_frames; ++n_ok) {
-            if (n_ok + 24 < n_frames) __builtin_prefetch(frames + (n_ok + 24) * frame_stride);
-            bad_status = sspsd::frame_status(frames + n_ok * frame_stride, frame_len, want_fmt);
-            if (bad_status != SSPSD_OK) break;
+        size_t sub_n[sspsd_decoder::MAX_SUB] = {};
+        double us_scan = 0, us_launch = 0;
+        for (size_t k = 0; k < n_sub && bad_status == SSPSD_OK; ++k) {
+            const auto ta = clk::now();
+            const size_t f0 = k * per, f1 = std::min(n_frames, f0 + per);
+            const sspsd_loss at_start = hl;
+            size_t f = f0;
+            for (; f < f1; ++f) {
+                const uint8_t* fr = frames + f * frame_stride;
+                if (f + 24 < n_frames) __builtin_prefetch(fr + 24 * frame_stride);
+                bad_status = sspsd::frame_status(fr, frame_len, want_fmt);
+                if (bad_status != SSPSD_OK) break;
+                uint32_t seq;
+                std::memcpy(&seq, fr + 4, 4);  // little endian, frame.rs:31
+                sspsd_loss_update(&hl, seq, fr[3]);
+            }
+            n_ok = f;
+            const size_t nk = f - f0;
+            sub_n[k] = nk;
+            const auto tb = clk::now();
+            if (nk) {
+                const size_t off = f0 * batches * div;  // items per trace before this sub-chunk
+                float* dst[SSPSD_MAX_TRACES];
+                for (int t = 0; t < SSPSD_MAX_TRACES; ++t) dst[t] = d->d_traces[t] + off;
+                SSPSD_CUDA(cudaStreamWaitEvent(d->stream, d->ev_copied[k], 0));
+                rc = queue_decode(d, d->d_frames + f0 * frame_stride, nk, f0, frame_len, frame_stride, loss ? &at_start : nullptr,
+                                  dst, off % 4 == 0, d->traces_cap - off, fmt0, (int)k);
+                if (rc) return rc;
+                SSPSD_CUDA(cudaEventRecord(d->ev_decoded, d->stream));
+                const size_t ns = nk * batches * div;
+                for (uint32_t t = 0; t < n_cascades && t < ntr; ++t) {
+                    if (!cascades[t]) continue;
+                    SSPSD_CUDA(cudaStreamWaitEvent(cascades[t]->c.stream(), d->ev_decoded, 0));
+                    rc = cascades[t]->c.process(dst[t], ns, SSPSD_MEM_DEVICE);
+                    if (rc) return rc;
+                    SSPSD_CUDA(cudaEventRecord(d->ev_consumed[t], cascades[t]->c.stream()));
+                    d->consumed_pending[t] = true;
+                }
+                queued = k + 1;
+            }
+            if (trace) {
+                us_scan += std::chrono::duration<double, std::micro>(tb - ta).count();
+                us_launch += std::chrono::duration<double, std::micro>(clk::now() - tb).count();
+            }
         }
+        const auto t3 = clk::now();
+        SSPSD_CUDA(cudaStreamSynchronize(d->h2d_stream));  // the caller's buffer is borrowed for the call only
+        rc = decode_wait(d);
+        if (rc) return rc;
+        if (trace)
+            fprintf(stderr, "[sspsd frames] n=%zu in %zu sub-chunks: enqueue h2d %.0f us, header scan %.0f us, launches %.0f us, wait %.0f us\n",
+                    n_frames, n_sub, std::chrono::duration<double, std::micro>(t1 - t0).count(), us_scan, us_launch,
+                    std::chrono::duration<double, std::micro>(clk::now() - t3).count());
         if (n_ok == 0) {
-            SSPSD_CUDA(cudaStreamSynchronize(d->stream));  // the caller's buffer is borrowed for the call only
             if (info) std::memset(info, 0, sizeof(*info));
             set_error("malformed frame");
             return (int32_t)bad_status;
         }
-        const unsigned int batches = frames[3];
-        const unsigned int div = fmt0 == SSPSD_FORMAT_ADCDAC ? 8 : 1;
-        const size_t ns = n_ok * batches * div;
-        const uint32_t ntr = fmt0 == SSPSD_FORMAT_MPLL ? 3 : 4;
-        rc = decode_on_device(d, d->d_frames, n_ok, frame_len, frame_stride, SSPSD_MEM_DEVICE, loss, d->d_traces, true,
-                              d->traces_cap, /*wait=*/false, (int)fmt0);
-        if (rc) return rc;
-        for (uint32_t t = 0; t < n_cascades && t < ntr; ++t) {
-            if (!cascades[t]) continue;
-            SSPSD_CUDA(cudaStreamWaitEvent(cascades[t]->c.stream(), d->ev_decoded, 0));
-            rc = cascades[t]->c.process(d->d_traces[t], ns, SSPSD_MEM_DEVICE);
-            if (rc) return rc;
-            SSPSD_CUDA(cudaEventRecord(d->ev_consumed[t], cascades[t]->c.stream()));
-            d->consumed_pending[t] = true;
+        // the device's results, sub-chunk by sub-chunk, against the host's walk over the headers
+        sspsd::DecodeResult sum{};
+        for (size_t k = 0; k < queued; ++k) {
+            const sspsd::DecodeResult& r = d->h_res[k];
+            if (r.first_bad != sub_n[k] || r.format != fmt0 || r.batches != batches) {
+                set_error("internal: device scan disagrees with the host pre-scan");
+                return SSPSD_EINVAL;
+            }
+            sum.received += r.received;
+            sum.dropped += r.dropped;
+            sum.last_seq_end = r.last_seq_end;
         }
-        rc = decode_wait(d);
-        if (rc) return rc;
-        const sspsd::DecodeResult r = *d->h_res;
-        if (r.first_bad != n_ok || r.format != fmt0 || r.batches != batches) {
-            set_error("internal: device scan disagrees with the host pre-scan");
+        sum.first_bad = n_ok;
+        sum.format = fmt0;
+        sum.batches = batches;
+        if (loss && (loss->received + sum.received != hl.received || loss->dropped + sum.dropped != hl.dropped ||
+                     sum.last_seq_end != hl.seq)) {
+            set_error("internal: device loss counters disagree with the host's");
             return SSPSD_EINVAL;
         }
-        apply_result(r, n_ok, loss, info, div);
+        apply_result(sum, n_ok, loss, info, div);
         if (n_ok < n_frames) {
             set_error("malformed frame");
             return (int32_t)bad_status;

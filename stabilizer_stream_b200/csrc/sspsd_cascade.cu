@@ -86,7 +86,7 @@ int k2_variant_from_env()
 {
     const char* e = getenv("SSPSD_K2");
     std::string m = e ? e : "ring";
-    return m == "r8" ? 0 : m == "r16" ? 1 : m == "ring1" ? 3 : 2;
+    return m == "r8" ? 0 : m == "r16" ? 1 : m == "ring1" ? 3 : m == "ring1x5" ? 4 : 2;
 }
 
 int launch_stage(int log2n, bool r16, const StageParams& p, int grid, cudaStream_t s)
@@ -119,6 +119,8 @@ int prepare_stage(int log2n, bool r16, int hop, int* tmax, int* nt)
                                         (int)stage_ring_smem_bytes(RingCfg::MAX_W)));
         SSPSD_CUDA(cudaFuncSetAttribute(psd_stage_kernel_ring1, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                         (int)stage_ring_smem_bytes(1024, 1, RingCfg::RING1, false)));
+        SSPSD_CUDA(cudaFuncSetAttribute(psd_stage_kernel_ring1x5, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        (int)stage_ring_smem_bytes(384, 1, 3, false)));
         return SSPSD_OK;
     }
     if (log2n == 9)
@@ -545,10 +547,12 @@ int Cascade::launch_psd(size_t i, const StreamSrc& src, uint64_t k0, uint64_t ns
         return reduce_partials(i, grid * W16::SPI, p);
     }
     const bool ring = log2n_ == 12 && k2_variant_ >= 2 && hop_ * 2 == n_;
-    if (ring && k2_variant_ == 3) {
-        // four independent single-group CTAs per SM (A/B variant, SSPSD_K2=ring1)
-        long long t1 = ((long long)nseg + 4ll * num_sms_ - 1) / (4ll * num_sms_);
-        p.T = (int)std::max<long long>(1, std::min<long long>(t1, 1024));
+    if (ring && k2_variant_ >= 3) {
+        // four (five: ring1x5, 96 registers) independent single-group CTAs per SM (A/B variants, SSPSD_K2=ring1|ring1x5)
+        const bool x5 = k2_variant_ == 4;
+        const long long per_sm = x5 ? 5 : 4;
+        long long t1 = ((long long)nseg + per_sm * num_sms_ - 1) / (per_sm * num_sms_);
+        p.T = (int)std::max<long long>(1, std::min<long long>(t1, x5 ? 384 : 1024));
         p.hop = (int)hop_;
         p.detrend = detrend_;
         p.tile_cap = 0;
@@ -563,7 +567,10 @@ int Cascade::launch_psd(size_t i, const StreamSrc& src, uint64_t k0, uint64_t ns
         int rcp = prepare_partials(i, grid, &p);
         if (rcp) return rcp;
         prof_begin(i == 0 ? SSPSD_PROF_PSD_STAGE0 : SSPSD_PROF_PSD_DEEP, nseg * (uint64_t)hop_, psd_stream(i));
-        psd_stage_kernel_ring1<<<grid, R16::TPS, stage_ring_smem_bytes(p.T, 1, RingCfg::RING1, false), psd_stream(i)>>>(p);
+        if (x5)
+            psd_stage_kernel_ring1x5<<<grid, R16::TPS, stage_ring_smem_bytes(p.T, 1, 3, false), psd_stream(i)>>>(p);
+        else
+            psd_stage_kernel_ring1<<<grid, R16::TPS, stage_ring_smem_bytes(p.T, 1, RingCfg::RING1, false), psd_stream(i)>>>(p);
         prof_end(psd_stream(i));
         if (!cuda_ok(cudaGetLastError(), "psd_stage_kernel_ring1 launch")) return SSPSD_ECUDA;
         return reduce_partials(i, grid, p);

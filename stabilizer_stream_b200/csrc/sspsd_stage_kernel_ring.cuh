@@ -268,6 +268,12 @@ __global__ void __launch_bounds__(R16::TPS, 4) psd_stage_kernel_ring1(const Stag
     psd_stage_ring_body<1, RingCfg::RING1, false>(p);
 }
 
+// variant (SSPSD_K2=ring1x5): five single-group CTAs per SM (20 warps instead of 16) at <= 96 registers, 3-slot ring
+__global__ void __launch_bounds__(R16::TPS, 5) psd_stage_kernel_ring1x5(const StageParams p)
+{
+    psd_stage_ring_body<1, 3, false>(p);
+}
+
 inline size_t stage_ring_smem_bytes(int segs_per_cta, int groups = R16::G, int ring = RingCfg::RING, bool win_smem = true)
 {
     size_t fl = (size_t)ring * (R16::N / 2) + (win_smem ? R16::N : 0) + (size_t)groups * 2 * R16::WS + ((segs_per_cta + 3) & ~3) + 8;

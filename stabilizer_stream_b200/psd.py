@@ -129,29 +129,42 @@ class _StreamOrdered:
     """Mixin of the handle classes that read CUDA tensors in place: SSPSD_MEM_DEVICE input is consumed
     asynchronously on the HANDLE's stream (include/sspsd.h), which need not be the stream torch is on when
     process() is called (a handle made before `with torch.cuda.stream(s)`, or one with a private stream).
-    Before the call the handle's stream waits for torch's current stream (the producer of x); after it the
-    tensor is marked as in use on the handle's stream (record_stream), so the caching allocator cannot
-    recycle a temporary -- e.g. the .contiguous() copy -- while the kernels still read it."""
+    Before the call the handle's stream waits for torch's current stream (the producer of x); after it torch's
+    current stream waits for the handle's stream (_release_device_input), so the caching allocator -- which reuses
+    a freed block in the order of the stream it was allocated on -- cannot recycle a temporary (e.g. the
+    .contiguous() copy) while the kernels still read it.  (Not Tensor.record_stream: the allocator would later
+    record an event on the handle's stream, which may have been destroyed with the handle by then.)"""
 
     _hs = None
 
     def _stream_ptr(self):  # overridden where the C ABI exposes the handle's stream
         return None
 
-    def _order_device_input(self, t):
+    def _handle_stream(self, t):
         import torch
         if t.device.index != self.device:
             raise ValueError("tensor lives on cuda:%d, the handle on cuda:%d" % (t.device.index, self.device))
         if self._hs is None:
             ptr = self._stream_ptr()
             if ptr is None:
-                return
+                return None, None
             self._hs = (torch.cuda.default_stream(t.device) if ptr in (0, 1)
                         else torch.cuda.ExternalStream(ptr, device=t.device))
         cur = torch.cuda.current_stream(t.device)
-        if (cur.cuda_stream or 1) != (self._hs.cuda_stream or 1):
-            self._hs.wait_stream(cur)
-            t.record_stream(self._hs)
+        if (cur.cuda_stream or 1) == (self._hs.cuda_stream or 1):
+            return None, None
+        return self._hs, cur
+
+    def _order_device_input(self, t):
+        hs, cur = self._handle_stream(t)
+        if hs is not None:
+            hs.wait_stream(cur)
+
+    def _release_device_input(self, t):
+        """after an ASYNCHRONOUS call that read (or wrote) t on the handle's stream"""
+        hs, cur = self._handle_stream(t)
+        if hs is not None:
+            cur.wait_stream(hs)
 
 
 def _config(n, window, hbf, device, stream, max_batch, host_stage, deep_defer=0, deterministic=False):
@@ -214,6 +227,8 @@ class PsdCascade(_StreamOrdered):
         if mem == L.MEM_DEVICE:
             self._order_device_input(keep)
         L.check(L.lib().sspsd_cascade_process_f32(self._h, ptr, n, mem))
+        if mem == L.MEM_DEVICE:
+            self._release_device_input(keep)
         del keep
 
     def process_raw(self, ptr, n, mem):
@@ -342,6 +357,7 @@ class Psd(_StreamOrdered):
             self._order_device_input(out)  # written on the handle's stream
             yl = C.c_size_t(out.numel())
             L.check(L.lib().sspsd_stage_process_f32(self._h, ptr, n, mem, out.data_ptr(), C.byref(yl), L.MEM_DEVICE))
+            self._release_device_input(out)  # also orders the read of x, if that is a CUDA tensor
             return out[:yl.value]
         y = np.zeros(n // 8 + self.n // 8 + 16, np.float32)
         yl = C.c_size_t(y.size)
@@ -425,10 +441,11 @@ class FrameDecoder(_StreamOrdered):
     src/loss.rs:11-26, src/de/data.rs)."""
 
     def __init__(self, device=0, stream=None):
+        # stream=None: a private stream of the decoder's own (NULL in the C ABI), not torch's current one -- the frames'
+        # H2D copy of call c + 1 must not queue behind the cascades of call c, which usually sit on torch's stream;
+        # CUDA tensors handed in are ordered against torch's stream by _order_device_input
         h = C.c_void_p()
-        if stream is None:
-            stream = _default_stream(device)
-        L.check(L.lib().sspsd_decoder_create(device, stream, C.byref(h)))
+        L.check(L.lib().sspsd_decoder_create(device, stream or None, C.byref(h)))
         self._h = h
         self.device = int(device)
 

@@ -185,3 +185,45 @@ def test_eshort_retry_accounts_the_batch_once(sp, oracle):
     assert (loss.received, loss.dropped, loss.seq) == (ref.received, ref.dropped, ref.seq)
     for g, w in zip(big, want):
         assert np.array_equal(g.view(np.uint32), np.concatenate(w).view(np.uint32))
+
+
+@pytest.mark.parametrize("fmt,batches,bad_at", [(1, 3, None), (1, 3, 30_000), (2, 1, None), (2, 1, 16_667), (4, 2, 49_999)])
+def test_large_host_batches_are_pipelined_in_sub_chunks(sp, oracle, fmt, batches, bad_at):
+    """>= 32768 host frames per sspsd_cascade_process_frames call are cut into sub-chunks (copy k + 1 overlaps decode and
+    cascades of k); the loss state chains from sub-chunk to sub-chunk on the host, the device's counters are the ones
+    returned.  Against the frame-by-frame oracle, with drops, a sequence wrap, trace offsets that are not 16-byte aligned
+    (fmt 2, one item per frame) and a malformed frame in the middle / at the start of a sub-chunk / in the last frame."""
+    n, n_frames = 512, 50_000
+    data, flen, stride, hdrs = make_frames(fmt, batches, n_frames, seed=77 + fmt, drop_every=997,
+                                           start_seq=0xFFFFFFFF - 20_000 * batches)
+    if bad_at is not None:
+        b = bytearray(data)
+        b[bad_at * stride] = 0x7A   # magic, frame.rs:26-28
+        data = bytes(b)
+    st, nf, lo, want = oracle_decode_stream(oracle, data, flen, stride, n_frames)
+    assert nf == (n_frames if bad_at is None else bad_at)
+    ntr = 3 if fmt == 4 else 4
+    cas = [sp.PsdCascade(n) for _ in range(ntr)]
+    dec = sp.FrameDecoder()
+    loss = sp.Loss()
+    if bad_at is None:
+        info = dec.process_frames(cas, data, flen, loss)
+        assert info.frames_ok == n_frames
+    else:
+        with pytest.raises(sp.DecodeError) as e:
+            dec.process_frames(cas, data, flen, loss)
+        assert e.value.frames_ok == bad_at
+    assert (loss.received, loss.dropped, loss.seq) == (lo.received, lo.dropped, lo.seq)
+    assert lo.dropped > 0
+    # a second call continues the stream (state carried by `loss` and the cascades)
+    tail, _, _, _ = make_frames(fmt, batches, 100, seed=5, start_seq=(lo.seq + 7 * batches) & 0xFFFFFFFF)
+    dec.process_frames(cas, tail, flen, loss)
+    st2, nf2, lo2, want2 = oracle_decode_stream(oracle, tail, flen, stride, 100)
+    assert loss.received == lo.received + lo2.received and loss.dropped == lo.dropped + lo2.dropped + 7 * batches
+    for t in range(ntr):
+        o = oracle.Cascade(n, 1)
+        o.process(np.concatenate(want[t] + want2[t]))
+        p, b = cas[t].psd()
+        po, bo = o.psd()
+        assert [k.count for k in b] == [k.count for k in bo]
+        assert p.size == po.size and np.max(np.abs(p - po) / np.maximum(po, 1e-30)) < 1e-4

@@ -355,8 +355,8 @@ def test_device_tensors_on_other_torch_streams(sp, oracle):
     """a handle created BEFORE torch touched CUDA used to get a private stream, and
     process() read caller tensors on it with no ordering against the torch stream that produced them; a handle
     is also legitimately used under `with torch.cuda.stream(s)` later.  The mirror now makes the handle's stream
-    wait for torch's current stream and marks the tensor (record_stream), so temporaries may be dropped right
-    after the call.  Exercised with temporaries produced on side streams and an allocator under churn."""
+    wait for torch's current stream before the call and torch's current stream wait for the handle's after it, so
+    temporaries may be dropped right after the call.  Exercised with temporaries produced on side streams and an allocator under churn."""
     import torch
     n = 512
     x = uniform_noise(400 * n, 31)
@@ -376,7 +376,7 @@ def test_device_tensors_on_other_torch_streams(sp, oracle):
             tmp = torch.stack([xd[pos:pos + block], xd[pos:pos + block]], dim=1) * 1.0
             g.process(tmp[:, 0])
             del tmp
-            # allocator churn on the same stream: would recycle the block if it were not recorded
+            # allocator churn on the same stream: would recycle the block if the side stream did not wait for the handle's
             junk = torch.full((block * 2,), float("nan"), device="cuda")
             del junk
         pos += block

@@ -20,6 +20,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
                                        ({"SSPSD_K3": "async960"}, 1, 4096), ({"SSPSD_K3": "async640"}, 0, 512),
                                        ({"SSPSD_DEFER": "1"}, 2, 4096), ({"SSPSD_DEFER": "4096"}, 0, 512),
                                        ({"SSPSD_K2": "ring1"}, 3, 4096), ({"SSPSD_K2": "ring1", "SSPSD_OVERLAP": "0"}, 1, 4096),
+                                       ({"SSPSD_K2": "ring1x5"}, 2, 4096),
                                        ({"SSPSD_K2": "r8"}, 3, 512), ({"SSPSD_K2": "ring", "SSPSD_OVERLAP": "0"}, 2, 512)])
 def test_kernel_and_stream_variants(env, det, n):
     e = dict(os.environ)
