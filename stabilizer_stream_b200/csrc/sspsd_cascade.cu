@@ -166,6 +166,15 @@ int launch_decim_async_t(const DecimParams& p, long long n_out, int num_sms, cud
     return cuda_ok(cudaGetLastError(), "decim8_async_kernel launch") ? SSPSD_OK : SSPSD_ECUDA;
 }
 
+template <int MA, int MB, int MC, int PRESET, int OB, int CTAS>
+int launch_decim_pf_t(const DecimParams& p, long long n_out, int num_sms, cudaStream_t s)
+{
+    const int ntiles = (int)((n_out + OB - 1) / OB);
+    const int grid = std::min(ntiles, num_sms * CTAS);
+    decim8_pf_kernel<MA, MB, MC, PRESET, OB, CTAS><<<grid, DEC_NT, decim_pf_smem_bytes<MA, MB, MC, OB>(), s>>>(p, ntiles);
+    return cuda_ok(cudaGetLastError(), "decim8_pf_kernel launch") ? SSPSD_OK : SSPSD_ECUDA;
+}
+
 int decim_halo(int preset)
 {
     return preset == SSPSD_HBF_98 ? DecGeom<3, 6, 15>::HALO : DecGeom<5, 10, 23>::HALO;
@@ -214,6 +223,14 @@ int upload_taps_once(int device)
                                     cudaFuncAttributeMaxDynamicSharedMemorySize, (int)decim_tma_smem_bytes<3, 6, 15, 960>()));
     SSPSD_CUDA(cudaFuncSetAttribute(decim8_tma_kernel<3, 6, 15, SSPSD_HBF_98, 640, 3>,
                                     cudaFuncAttributeMaxDynamicSharedMemorySize, (int)decim_tma_smem_bytes<3, 6, 15, 640>()));
+    SSPSD_CUDA(cudaFuncSetAttribute(decim8_pf_kernel<5, 10, 23, SSPSD_HBF_140, 960, 2>,
+                                    cudaFuncAttributeMaxDynamicSharedMemorySize, (int)decim_pf_smem_bytes<5, 10, 23, 960>()));
+    SSPSD_CUDA(cudaFuncSetAttribute(decim8_pf_kernel<5, 10, 23, SSPSD_HBF_140, 640, 3>,
+                                    cudaFuncAttributeMaxDynamicSharedMemorySize, (int)decim_pf_smem_bytes<5, 10, 23, 640>()));
+    SSPSD_CUDA(cudaFuncSetAttribute(decim8_pf_kernel<3, 6, 15, SSPSD_HBF_98, 960, 2>,
+                                    cudaFuncAttributeMaxDynamicSharedMemorySize, (int)decim_pf_smem_bytes<3, 6, 15, 960>()));
+    SSPSD_CUDA(cudaFuncSetAttribute(decim8_pf_kernel<3, 6, 15, SSPSD_HBF_98, 640, 3>,
+                                    cudaFuncAttributeMaxDynamicSharedMemorySize, (int)decim_pf_smem_bytes<3, 6, 15, 640>()));
     if (device < 64)
         done[device] = true;
     return SSPSD_OK;
@@ -409,7 +426,8 @@ int Cascade::init(const sspsd_config& cfg, uint32_t max_stages)
         // K3 variant (A/B switch): SSPSD_K3 = tiled | tma960 | tma640 | async960 | async640
         const char* e = getenv("SSPSD_K3");
         std::string m = e ? e : "tma960";
-        k3_variant_ = m == "tiled" ? 0 : m == "tma960" ? 1 : m == "tma640" ? 2 : m == "async640" ? 4 : 3;
+        k3_variant_ = m == "tiled" ? 0 : m == "tma960" ? 1 : m == "tma640" ? 2 : m == "async640" ? 4 : m == "pf960" ? 5 :
+                      m == "pf640" ? 6 : 3;
     }
     rc = prepare_stage((int)log2n_, k2_variant_ >= 1, (int)hop_, &tmax_, &nt_);
     if (rc) return rc;
@@ -697,6 +715,12 @@ int Cascade::launch_decim(size_t i, const StreamSrc& src, uint64_t m0, uint64_t 
     } else if (k3_variant_ == 3) {
         rc = cfg_.hbf == SSPSD_HBF_98 ? launch_decim_async_t<3, 6, 15, SSPSD_HBF_98, 960, 2>(p, p.m1 - lo, num_sms_, ss)
                                       : launch_decim_async_t<5, 10, 23, SSPSD_HBF_140, 960, 2>(p, p.m1 - lo, num_sms_, ss);
+    } else if (k3_variant_ == 5) {
+        rc = cfg_.hbf == SSPSD_HBF_98 ? launch_decim_pf_t<3, 6, 15, SSPSD_HBF_98, 960, 2>(p, p.m1 - lo, num_sms_, ss)
+                                      : launch_decim_pf_t<5, 10, 23, SSPSD_HBF_140, 960, 2>(p, p.m1 - lo, num_sms_, ss);
+    } else if (k3_variant_ == 6) {
+        rc = cfg_.hbf == SSPSD_HBF_98 ? launch_decim_pf_t<3, 6, 15, SSPSD_HBF_98, 640, 3>(p, p.m1 - lo, num_sms_, ss)
+                                      : launch_decim_pf_t<5, 10, 23, SSPSD_HBF_140, 640, 3>(p, p.m1 - lo, num_sms_, ss);
     } else {
         rc = cfg_.hbf == SSPSD_HBF_98 ? launch_decim_async_t<3, 6, 15, SSPSD_HBF_98, 640, 3>(p, p.m1 - lo, num_sms_, ss)
                                       : launch_decim_async_t<5, 10, 23, SSPSD_HBF_140, 640, 3>(p, p.m1 - lo, num_sms_, ss);
@@ -1429,10 +1453,16 @@ int Cascade::psd(const sspsd_merge_opts& o, float* p, size_t* p_len, sspsd_break
         set_error("null length pointer");
         return SSPSD_EINVAL;
     }
-    int rc = sync();
-    if (rc) return rc;
+    // launch what is pending and join the side streams; the one host synchronisation is behind the read-back below
+    // (the bookkeeping is closed-form host state, it does not wait for the device)
     DeviceGuard g(cfg_.device);
     if (!g.ok) return SSPSD_ECUDA;
+    int rc = flush_staged();
+    if (rc) return rc;
+    rc = flush_deferred();
+    if (rc) return rc;
+    rc = join_streams();
+    if (rc) return rc;
     const size_t ns = stages_.size();
     uint64_t book[4 * SSPSD_MAX_STAGES + 2];
     export_book(book);

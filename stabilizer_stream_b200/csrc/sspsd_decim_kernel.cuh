@@ -370,6 +370,97 @@ __global__ void __launch_bounds__(DEC_NT, CTAS) decim8_async_kernel(const DecimP
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// K3, fourth generation: persistent CTAs, the NEXT tile prefetched into REGISTERS.
+//
+// Shared-memory wavefronts per 960-output tile of the TMA-staged kernel (hbf140): TMA write of the staging buffer 255,
+// LDS.128 read-back 255, de-interleaving STS 255, stage A 528, stage B 344, stage C 229 -- the staging round trip is
+// 27 % of the traffic of the pipe that bounds the kernel (73 % busy).  Here every thread issues its 8 LDG.128 of tile
+// t + 1 right after the barrier that completes the planes of tile t, keeps them in 32 registers while stages A and B of
+// tile t run (~1.3 us, longer than an HBM round trip), and scatters them into the x planes -- free since stage A --
+// before stage C: no staging buffer, no exposed load latency.  Same arithmetic and tile geometry (hbf_stage):
+// bit-identical output.
+// ---------------------------------------------------------------------------------------------
+template <int MA, int MB, int MC, int PRESET, int OB, int CTAS>
+__global__ void __launch_bounds__(DEC_NT, CTAS) decim8_pf_kernel(const DecimParams p, const int ntiles)
+{
+    using GE = DecGeom<MA, MB, MC, OB>;
+    extern __shared__ __align__(16) float smem[];
+    float* xe = smem;
+    float* xo = xe + DEC_P * GE::SX;
+    float* ae = xo + DEC_P * GE::SX;
+    float* ao = ae + DEC_P * GE::SA;
+    float* be = ao + DEC_P * GE::SA;
+    float* bo = be + DEC_P * GE::SB;
+    constexpr int NV = GE::NX / 4;
+    constexpr int NR = (NV + DEC_NT - 1) / DEC_NT;
+    const int tid = threadIdx.x;
+    float4 pf[NR];
+    // tile t covers outputs [m1 - (t+1) OB, m1 - t OB) (counted down from the top; only the lowest one is clipped by
+    // the store guard, and what it would read below the carry buffer is zero: ld_stream4)
+    auto fetch = [&](int t) {
+        const long long g = 8 * (p.m1 - (long long)t * OB) - GE::NX;
+        if (g >= p.src.split) {
+            const float4* __restrict__ gx = reinterpret_cast<const float4*>(p.src.fresh + (g - p.src.split));
+#pragma unroll
+            for (int u = 0; u < NR; ++u) {
+                const int v = u * DEC_NT + tid;
+                if (v < NV) {
+                    SSPSD_ASSERT(g + 4ll * v + 4 <= p.src.end);
+                    pf[u] = __ldg(gx + v);
+                }
+            }
+        } else {
+#pragma unroll
+            for (int u = 0; u < NR; ++u) {
+                const int v = u * DEC_NT + tid;
+                if (v < NV) pf[u] = ld_stream4(p.src, g + 4ll * v);
+            }
+        }
+    };
+    auto scatter = [&]() {
+#pragma unroll
+        for (int u = 0; u < NR; ++u) {
+            const int v = u * DEC_NT + tid;
+            if (v < NV) {
+                const int pos = 2 * (v & 3) * GE::SX + (v >> 2);
+                xe[pos] = pf[u].x;
+                xo[pos] = pf[u].y;
+                xe[pos + GE::SX] = pf[u].z;
+                xo[pos + GE::SX] = pf[u].w;
+            }
+        }
+    };
+    int tile = blockIdx.x;
+    if (tile < ntiles) {
+        fetch(tile);
+        scatter();
+    }
+    const long long lo = p.m0 > p.drain ? p.m0 : p.drain;
+    for (; tile < ntiles; tile += gridDim.x) {
+        const long long mhi = p.m1 - (long long)tile * OB;
+        const long long c_base = mhi - OB;
+        const int next = tile + (int)gridDim.x;
+        __syncthreads();  // x planes of this tile complete; stage C of the previous tile has read be/bo
+        if (next < ntiles) fetch(next);
+        hbf_stage<MA, GE::SX, GE::SA, GE::NX / 2 - GE::NA, false, PRESET, 2>(xe, xo, GE::NA, ae, ao, nullptr, 0, 0);
+        __syncthreads();
+        hbf_stage<MB, GE::SA, GE::SB, GE::NA / 2 - GE::NB, false, PRESET, 1>(ae, ao, GE::NB, be, bo, nullptr, 0, 0);
+        __syncthreads();
+        if (next < ntiles) scatter();  // the x planes were last read by stage A, two barriers ago
+        const int rel_lo = lo > c_base ? (int)(lo - c_base) : 0;
+        hbf_stage<MC, GE::SB, GE::SB, GE::NB / 2 - OB, true, PRESET, 0>(be, bo, OB, nullptr, nullptr,
+                                                                        p.out_fresh + (c_base - p.drain - p.out_split),
+                                                                        rel_lo, OB, c_base - p.drain - p.out_split, p.out_cap);
+    }
+}
+
+template <int MA, int MB, int MC, int OB>
+constexpr size_t decim_pf_smem_bytes()
+{
+    return (size_t)DecGeom<MA, MB, MC, OB>::SMEM_FLOATS * sizeof(float);
+}
+
 template <int MA, int MB, int MC, int OB>
 constexpr size_t decim_async_smem_bytes()
 {

@@ -23,7 +23,8 @@ def _env(extra=None):
 
 
 @pytest.mark.parametrize("env", [{}, {"SSPSD_K3": "tiled"}, {"SSPSD_K3": "async640"}, {"SSPSD_K3": "tma640", "SSPSD_K2": "r8"},
-                                 {"SSPSD_K2": "r16", "SSPSD_OVERLAP": "0"}])
+                                 {"SSPSD_K2": "r16", "SSPSD_OVERLAP": "0"}, {"SSPSD_K3": "pf960", "SSPSD_K2": "ring1"},
+                                 {"SSPSD_K3": "pf640", "SSPSD_K2": "ring1x5"}])
 def test_bounds_build_smoke(env):
     if not os.path.exists(BOUNDS):
         pytest.skip("libsspsd_bounds.so not built")
