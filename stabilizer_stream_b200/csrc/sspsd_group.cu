@@ -408,18 +408,27 @@ int make_cascade(sspsd_group* g, int device, sspsd_cascade** out)
     if (rc) return rc;
     if (g->avg_set) rc = (*out)->c.set_avg(g->avg);
     if (!rc && g->detrend) rc = (*out)->c.set_detrend(g->detrend);
+    if (rc) {
+        sspsd_cascade_destroy(*out);
+        *out = nullptr;
+    }
     return rc;
 }
 
 int ensure_time_cascades(sspsd_group* g)
 {
     if (!g->tc.empty()) return SSPSD_OK;
-    g->tc.assign(g->n_local(), nullptr);
-    for (uint32_t l = 0; l < g->n_local(); ++l) {
-        int rc = make_cascade(g, g->devices[l], &g->tc[l]);
-        if (rc) return rc;
-    }
     const uint32_t nl = g->n_local();
+    std::vector<sspsd_cascade*> tc(nl, nullptr);
+    for (uint32_t l = 0; l < nl; ++l) {
+        int rc = make_cascade(g, g->devices[l], &tc[l]);
+        if (rc) {
+            // all or nothing: a half-built set would pass the "already made" test above on the next call
+            for (auto* c : tc) sspsd_cascade_destroy(c);
+            return rc;
+        }
+    }
+    g->tc = tc;
     g->fed.assign(nl, 0);
     g->d_buf.assign(nl, nullptr);
     g->d_tail.assign(nl, nullptr);
