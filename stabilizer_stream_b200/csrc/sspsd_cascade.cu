@@ -1,5 +1,9 @@
 // sspsd_cascade.cu -- host-side state machine + kernel launches of the device cascade.
 // See sspsd_cascade.cuh for the bookkeeping model and include/sspsd.h for the reference citations.
+#if defined(__x86_64__)
+#include <emmintrin.h>
+#endif
+
 #include "sspsd_cascade.cuh"
 
 #include <algorithm>
@@ -1099,6 +1103,9 @@ int Cascade::flush_staged()
     if (staged_ == 0)
         return SSPSD_OK;
     const int hb = stage_buf_;
+#if defined(__x86_64__) && defined(__SSE2__)
+    _mm_sfence();  // stage_copy's non-temporal stores must be globally visible before the DMA reads the buffer
+#endif
     // max_batch bounds every launch, also when it is smaller than the staging buffer
     const size_t chunk = (size_t)std::min<uint64_t>(host_chunk(), cfg_.max_batch);
     for (size_t pos = 0; pos < staged_; pos += chunk) {
@@ -1117,6 +1124,36 @@ int Cascade::flush_staged()
     return SSPSD_OK;
 }
 
+// Copy of a small host slice into the pinned staging buffer.  The buffer is written once and then read by the DMA engine
+// only, so slices of 16 KiB and more (the reference's 4096-sample slices, src/source.rs:116,123) are copied with
+// non-temporal stores: no read-for-ownership of the destination lines, no cache pollution; flush_staged() fences them
+// before it queues the H2D copy.  Measured with tools/small_calls.c: 3.1-3.4 GS/s against 2.55-3.0 with memcpy for
+// 4096-sample slices, but 1.40 against 1.78 GS/s for 1000-sample slices, hence the threshold.
+static inline void stage_copy(float* __restrict__ dst, const float* __restrict__ src, size_t n)
+{
+#if defined(__x86_64__) && defined(__SSE2__)
+    static const bool plain = getenv("SSPSD_STAGE_MEMCPY") != nullptr;  // A/B switch: plain memcpy
+    if (n >= 4096 && !plain) {
+        while ((reinterpret_cast<uintptr_t>(dst) & 15u) && n) {
+            *dst++ = *src++;
+            --n;
+        }
+        size_t i = 0;
+        for (; i + 16 <= n; i += 16) {
+            const __m128 a = _mm_loadu_ps(src + i), b = _mm_loadu_ps(src + i + 4), c = _mm_loadu_ps(src + i + 8),
+                         d = _mm_loadu_ps(src + i + 12);
+            _mm_stream_ps(dst + i, a);
+            _mm_stream_ps(dst + i + 4, b);
+            _mm_stream_ps(dst + i + 8, c);
+            _mm_stream_ps(dst + i + 12, d);
+        }
+        for (; i < n; ++i) dst[i] = src[i];
+        return;
+    }
+#endif
+    std::memcpy(dst, src, n * sizeof(float));
+}
+
 int Cascade::process_host(const float* x, size_t n)
 {
     if (n == 0)
@@ -1131,7 +1168,7 @@ int Cascade::process_host(const float* x, size_t n)
         }
         while (n) {
             size_t take = std::min<size_t>(n, cfg_.host_stage - staged_);
-            std::memcpy(h_stage_[stage_buf_] + staged_, x, take * sizeof(float));
+            stage_copy(h_stage_[stage_buf_] + staged_, x, take);
             staged_ += take;
             x += take;
             n -= take;
