@@ -381,7 +381,11 @@ int32_t sspsd_decode_frames(sspsd_decoder *d, const uint8_t *frames, size_t n_fr
 
 /* Fused decode -> cascades: trace t of every frame is fed to cascades[t] (one PsdCascade per trace,
  * src/bin/psd.rs:174-182) without the f32 traces ever leaving the device.  cascades[t] may be NULL
- * to drop a trace. */
+ * to drop a trace.  SSPSD_MEM_HOST frames are fully consumed (copied and decoded) when the call
+ * returns; the cascades' kernels may still be running (they are ordered on the cascades' own
+ * streams).  Large host batches are copied in sub-chunks on a private copy stream so that decode
+ * and cascades of one sub-chunk overlap the copy of the next; pass stream = NULL to
+ * sspsd_decoder_create (a private stream) unless the decoder must be ordered on a caller stream. */
 int32_t sspsd_cascade_process_frames(sspsd_decoder *d, sspsd_cascade *const *cascades, uint32_t n_cascades,
                                      const uint8_t *frames, size_t n_frames, size_t frame_len,
                                      size_t frame_stride, int32_t frames_mem, sspsd_loss *loss,

@@ -36,19 +36,7 @@ struct sspsd_decoder {
 };
 
 namespace {
-struct DevGuard {
-    int prev = -1;
-    bool ok;
-    explicit DevGuard(int dev)
-    {
-        if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
-        ok = sspsd::cuda_ok(cudaSetDevice(dev), "cudaSetDevice");
-    }
-    ~DevGuard()
-    {
-        if (prev >= 0) cudaSetDevice(prev);
-    }
-};
+using DevGuard = sspsd::DeviceGuard;
 
 float powi_f32(float x, int e)
 {

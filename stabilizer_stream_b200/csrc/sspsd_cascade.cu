@@ -34,22 +34,6 @@ bool cuda_ok(cudaError_t e, const char* what)
 
 namespace {
 
-struct DeviceGuard {
-    int prev = -1;
-    bool ok = true;
-    explicit DeviceGuard(int dev)
-    {
-        if (cudaGetDevice(&prev) != cudaSuccess)
-            prev = -1;
-        ok = cuda_ok(cudaSetDevice(dev), "cudaSetDevice");
-    }
-    ~DeviceGuard()
-    {
-        if (prev >= 0)
-            cudaSetDevice(prev);
-    }
-};
-
 inline long long floor4(long long v) { return v & ~3ll; }
 
 // ---- kernel dispatch over the FFT size ----

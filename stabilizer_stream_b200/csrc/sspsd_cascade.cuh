@@ -22,6 +22,25 @@ void set_error(const std::string& msg);
 const char* last_error();
 int hbf_info(int hbf, uint32_t* drain, uint32_t* halo);
 bool cuda_ok(cudaError_t e, const char* what);
+
+// Makes `dev` current for the scope and restores the caller's device afterwards: an entry point never leaves the
+// calling thread's current device changed (a host application -- or torch -- keeps its own notion of it).
+struct DeviceGuard {
+    int prev = -1;
+    bool ok = true;
+    explicit DeviceGuard(int dev)
+    {
+        if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
+        ok = prev == dev || cuda_ok(cudaSetDevice(dev), "cudaSetDevice");
+        if (prev == dev) prev = -1;  // nothing to restore
+    }
+    ~DeviceGuard()
+    {
+        if (prev >= 0) cudaSetDevice(prev);
+    }
+    DeviceGuard(const DeviceGuard&) = delete;
+    DeviceGuard& operator=(const DeviceGuard&) = delete;
+};
 #define SSPSD_CUDA(call)                     \
     do {                                     \
         if (!::sspsd::cuda_ok((call), #call)) return SSPSD_ECUDA; \

@@ -101,19 +101,7 @@ double now_s()
     return (double)t.tv_sec + 1e-9 * (double)t.tv_nsec;
 }
 
-struct DevGuard {
-    int prev = -1;
-    bool ok;
-    explicit DevGuard(int dev)
-    {
-        if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
-        ok = sspsd::cuda_ok(cudaSetDevice(dev), "cudaSetDevice");
-    }
-    ~DevGuard()
-    {
-        if (prev >= 0) cudaSetDevice(prev);
-    }
-};
+using DevGuard = sspsd::DeviceGuard;
 
 // ---------------------------------------------------------------------------------------------
 // Planner of the time-chunked mode.  Mirrors the integer bookkeeping of the cascade (Cascade::seek,

@@ -15,7 +15,7 @@ class Source {
 public:
     ~Source()
     {
-        cudaSetDevice(device_);
+        DeviceGuard g(device_);
         cudaFree(d_state_);
         cudaFree(d_elems_);
         cudaFree(d_init_);
@@ -46,7 +46,8 @@ public:
             set_error("unknown source kind");
             return SSPSD_EINVAL;
         }
-        SSPSD_CUDA(cudaSetDevice(device_));
+        DeviceGuard g(device_);
+        if (!g.ok) return SSPSD_ECUDA;
         if (stream) {
             stream_ = stream == (void*)1 ? cudaStreamLegacy : (cudaStream_t)stream;
         } else {
@@ -59,7 +60,8 @@ public:
 
     int reset()
     {
-        SSPSD_CUDA(cudaSetDevice(device_));
+        DeviceGuard g(device_);
+        if (!g.ok) return SSPSD_ECUDA;
         if (last_stream_) SSPSD_CUDA(cudaStreamSynchronize(last_stream_));
         SSPSD_CUDA(cudaMemsetAsync(d_state_, 0, 8 * sizeof(double), stream_));
         SSPSD_CUDA(cudaStreamSynchronize(stream_));
@@ -71,7 +73,8 @@ public:
     // produce the next n samples of the stream into device memory, in order on stream s
     int generate(float* d_out, size_t n, cudaStream_t s)
     {
-        SSPSD_CUDA(cudaSetDevice(device_));
+        DeviceGuard g(device_);
+        if (!g.ok) return SSPSD_ECUDA;
         // the recurrence state lives on the device: order this call after the previous one's stream
         if (last_stream_ && last_stream_ != s) SSPSD_CUDA(cudaStreamSynchronize(last_stream_));
         last_stream_ = s;
@@ -90,7 +93,8 @@ public:
     int scratch(size_t n, float** out)
     {
         if (n > buf_cap_) {
-            SSPSD_CUDA(cudaSetDevice(device_));
+            DeviceGuard g(device_);
+            if (!g.ok) return SSPSD_ECUDA;
             // the old buffer may still be read by the cascade the last call fed (its stream, not ours)
             SSPSD_CUDA(cudaStreamSynchronize(stream_));
             if (last_stream_) SSPSD_CUDA(cudaStreamSynchronize(last_stream_));

@@ -91,18 +91,43 @@ def test_time_chunked_group_equals_sequential(oracle, n, total, world, k, hbf, a
         check_against_sequential(sp, oracle, g, x, n, hbf, a, det)
 
 
-def test_time_chunked_group_on_the_device_generated_stream(oracle):
-    """config 5 in small: every rank generates its own range of the counter-based stream on its device"""
+@pytest.mark.parametrize("world", [3, 2])
+def test_time_chunked_group_on_the_device_generated_stream(oracle, world):
+    """config 5 in small: every rank generates its own range of the counter-based stream on its device (with one GPU
+    per rank where the box has them: the sources then live on several devices of one process)"""
     import stabilizer_stream_b200 as sp
+    import torch
     n = 512
-    for devs in device_lists(3):
+    for devs in device_lists(world):
         g = sp.Group(n, devices=devs, mode=sp.ShardMode.TIME)
         for total in (6_000_000, 4_100_003):     # a second capture reuses the group's handles and sources
             x = oracle.Source(oracle.SOURCE_NOISE, 0, 0x7654321).get(total)
             g.time_plan(total)
             g.time_process_noise(0, 0x7654321)
             g.time_finish()
+            assert torch.cuda.current_device() == 0, "the library left the caller's current device changed"
             check_against_sequential(sp, oracle, g, x, n, 1, None, 0)
+
+
+def test_entry_points_restore_the_current_device():
+    """a host application (or torch) keeps its own notion of the current device: handles that live on another GPU
+    must not leave it changed (found on an 8-GPU box: Source::generate did)"""
+    import stabilizer_stream_b200 as sp
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    torch.cuda.set_device(0)
+    src = sp.Source.noise(0, device=1)
+    x = src.get(100_000)
+    assert x.device.index == 1 and torch.cuda.current_device() == 0
+    c = sp.PsdCascade(512, device=1)
+    c.process_source(src, 300_000)
+    c.process(x)
+    p, b = c.psd()
+    assert torch.cuda.current_device() == 0 and np.all(np.isfinite(p))
+    dec = sp.FrameDecoder(device=1)
+    del src, c, dec
+    assert torch.cuda.current_device() == 0
 
 
 def test_time_chunked_group_errors():
