@@ -211,6 +211,10 @@ int upload_taps_once(int device)
                                     cudaFuncAttributeMaxDynamicSharedMemorySize, (int)decim_tma_smem_bytes<3, 6, 15, 960>()));
     SSPSD_CUDA(cudaFuncSetAttribute(decim8_tma_kernel<3, 6, 15, SSPSD_HBF_98, 640, 3>,
                                     cudaFuncAttributeMaxDynamicSharedMemorySize, (int)decim_tma_smem_bytes<3, 6, 15, 640>()));
+    SSPSD_CUDA(cudaFuncSetAttribute(decim8_tma_kernel<5, 10, 23, SSPSD_HBF_140, 768, 3>,
+                                    cudaFuncAttributeMaxDynamicSharedMemorySize, (int)decim_tma_smem_bytes<5, 10, 23, 768>()));
+    SSPSD_CUDA(cudaFuncSetAttribute(decim8_tma_kernel<3, 6, 15, SSPSD_HBF_98, 768, 3>,
+                                    cudaFuncAttributeMaxDynamicSharedMemorySize, (int)decim_tma_smem_bytes<3, 6, 15, 768>()));
     SSPSD_CUDA(cudaFuncSetAttribute(decim8_pf_kernel<5, 10, 23, SSPSD_HBF_140, 960, 2>,
                                     cudaFuncAttributeMaxDynamicSharedMemorySize, (int)decim_pf_smem_bytes<5, 10, 23, 960>()));
     SSPSD_CUDA(cudaFuncSetAttribute(decim8_pf_kernel<5, 10, 23, SSPSD_HBF_140, 640, 3>,
@@ -415,7 +419,7 @@ int Cascade::init(const sspsd_config& cfg, uint32_t max_stages)
         const char* e = getenv("SSPSD_K3");
         std::string m = e ? e : "tma960";
         k3_variant_ = m == "tiled" ? 0 : m == "tma960" ? 1 : m == "tma640" ? 2 : m == "async640" ? 4 : m == "pf960" ? 5 :
-                      m == "pf640" ? 6 : 3;
+                      m == "pf640" ? 6 : m == "tma768" ? 7 : 3;
     }
     rc = prepare_stage((int)log2n_, k2_variant_ >= 1, (int)hop_, &tmax_, &nt_);
     if (rc) return rc;
@@ -703,6 +707,9 @@ int Cascade::launch_decim(size_t i, const StreamSrc& src, uint64_t m0, uint64_t 
     } else if (k3_variant_ == 3) {
         rc = cfg_.hbf == SSPSD_HBF_98 ? launch_decim_async_t<3, 6, 15, SSPSD_HBF_98, 960, 2>(p, p.m1 - lo, num_sms_, ss)
                                       : launch_decim_async_t<5, 10, 23, SSPSD_HBF_140, 960, 2>(p, p.m1 - lo, num_sms_, ss);
+    } else if (k3_variant_ == 7) {
+        rc = cfg_.hbf == SSPSD_HBF_98 ? launch_decim_tma_t<3, 6, 15, SSPSD_HBF_98, 768, 3>(p, p.m1 - lo, num_sms_, ss)
+                                      : launch_decim_tma_t<5, 10, 23, SSPSD_HBF_140, 768, 3>(p, p.m1 - lo, num_sms_, ss);
     } else if (k3_variant_ == 5) {
         rc = cfg_.hbf == SSPSD_HBF_98 ? launch_decim_pf_t<3, 6, 15, SSPSD_HBF_98, 960, 2>(p, p.m1 - lo, num_sms_, ss)
                                       : launch_decim_pf_t<5, 10, 23, SSPSD_HBF_140, 960, 2>(p, p.m1 - lo, num_sms_, ss);
