@@ -693,6 +693,10 @@ int Cascade::launch_decim(size_t i, const StreamSrc& src, uint64_t m0, uint64_t 
         return SSPSD_OK;
     int grid = (int)((p.m1 - lo + DEC_OB - 1) / DEC_OB);
     cudaStream_t ss = stage_stream(i);
+    if (cc_valid_ && (k3_variant_ == 1 || k3_variant_ == 2 || k3_variant_ == 7)) {
+        p.cc = cc_pending_;  // the TMA-staged kernels build the stage's next carry buffer themselves
+        cc_valid_ = false;
+    }
     prof_begin(i == 0 ? SSPSD_PROF_DECIM_STAGE0 : SSPSD_PROF_DECIM_DEEP, (uint64_t)(p.m1 - lo) * 8, ss);
     int rc;
     if (k3_variant_ == 0) {
@@ -803,6 +807,34 @@ int Cascade::run_stage(size_t i, const float* fresh, long long split, uint64_t n
     const uint64_t D1 = decimated(st);
     uint64_t n_next = 0;
     long long nsplit = 0;
+    // next batch's carry: history for the decimator + pending samples, [D1 - hb, L1); the last L1 % 4
+    // samples are also copied to the head of the buffer the next batch's fresh samples will go to.  The job is
+    // handed to this stage's decimator launch when there is one below (launch_decim), else to carry_copy_kernel.
+    const long long cs = (long long)D1 - hb_;
+    {
+        const int n = (int)((long long)L1 - cs);
+        const int head_n = (int)(L1 & 3);
+        float* head_dst = nullptr;
+        if (head_n) {
+            if (i == 0) {
+                // stage 0: the next batch goes through the staging buffer d_in_[in_buf_] whenever L % 4 != 0
+                rc = ensure_in_buffers(1);
+                if (rc) return rc;
+                head_dst = d_in_[in_buf_];
+            } else {
+                head_dst = st.fresh[st.fb ^ 1];
+            }
+        }
+        if (n < 0 || n > hb_ + (int)n_ + 16) {
+            set_error("internal: carry overflow");
+            return SSPSD_EINVAL;
+        }
+        // the copy overwrites carry[cur ^ 1] and the head of fresh[fb ^ 1], which the previous batch's PSD
+        // kernel read (a wait on an event that was never recorded returns at once)
+        if (ps != ss) SSPSD_CUDA(cudaStreamWaitEvent(ss, st.ev_psd[st.fb ^ 1], 0));
+        cc_pending_ = CarryJob{cs, n, head_n, st.carry[st.cur ^ 1], head_dst, hb_ + (int)n_ + 16};
+        cc_valid_ = true;
+    }
     if (D1 > D0) {
         const uint64_t m0 = D0 / 8, m1 = D1 / 8;
         const uint64_t em1 = m1 > (uint64_t)drain_ ? m1 - drain_ : 0;
@@ -870,36 +902,18 @@ int Cascade::run_stage(size_t i, const float* fresh, long long split, uint64_t n
         }
     }
 
-    // next batch's carry: history for the decimator + pending samples, [D1 - hb, L1); the last L1 % 4
-    // samples are also copied to the head of the buffer the next batch's fresh samples will go to
     {
-        StageState& s2 = stages_[i];
-        const long long cs = (long long)D1 - hb_;
-        const int n = (int)((long long)L1 - cs);
-        const int head_n = (int)(L1 & 3);
-        float* head_dst = nullptr;
-        if (head_n) {
-            if (i == 0) {
-                // stage 0: the next batch goes through the staging buffer d_in_[in_buf_] whenever L % 4 != 0
-                rc = ensure_in_buffers(1);
-                if (rc) return rc;
-                head_dst = d_in_[in_buf_];
-            } else {
-                head_dst = s2.fresh[s2.fb ^ 1];
-            }
+        StageState& s2 = stages_[i];  // (add_stage() above may have moved the vector)
+        if (cc_valid_) {
+            // no decimator launch took the job (no new output this batch, or an A/B decimator variant)
+            const CarryJob& cj = cc_pending_;
+            prof_begin(SSPSD_PROF_OTHER, 0, ss);
+            carry_copy_kernel<<<std::max(1, std::min(64, (cj.n + 255) / 256)), 256, 0, ss>>>(src, cj.g0, cj.n, cj.dst, cj.head_dst,
+                                                                                            cj.head_n, cj.dst_cap);
+            prof_end(ss);
+            SSPSD_CUDA(cudaGetLastError());
+            cc_valid_ = false;
         }
-        // the copy overwrites carry[cur ^ 1] and the head of fresh[fb ^ 1], which the previous batch's PSD
-        // kernel read (a wait on an event that was never recorded returns at once)
-        if (ps != ss) SSPSD_CUDA(cudaStreamWaitEvent(ss, s2.ev_psd[s2.fb ^ 1], 0));
-        prof_begin(SSPSD_PROF_OTHER, 0, ss);
-        if (n < 0 || n > hb_ + (int)n_ + 16) {
-            set_error("internal: carry overflow");
-            return SSPSD_EINVAL;
-        }
-        carry_copy_kernel<<<std::max(1, std::min(64, (n + 255) / 256)), 256, 0, ss>>>(src, cs, n, s2.carry[s2.cur ^ 1],
-                                                                                     head_dst, head_n, hb_ + (int)n_ + 16);
-        prof_end(ss);
-        SSPSD_CUDA(cudaGetLastError());
         s2.cur ^= 1;
         s2.carry_start = cs;
         s2.L = L1;

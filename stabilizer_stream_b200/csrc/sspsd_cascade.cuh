@@ -179,6 +179,8 @@ private:
     int tmax_ = 1, nt_ = 256;  // largest tile (segments per CTA) and CTA size of the stage kernel
     uint64_t defer_ = 1ull << 26;  // sspsd_config::deep_defer
     uint64_t defer_window_ = 0;    // threshold in force for the stage that has just received samples
+    CarryJob cc_pending_{};    // carry copy of the stage being run, until a decimator launch (or the fallback kernel) takes it
+    bool cc_valid_ = false;
     int k3_variant_ = 1;       // SSPSD_K3 at creation: 0 = tiled, 1 = persistent TMA (960 outputs/tile), 2 = (640)
     int k2_variant_ = 2;       // SSPSD_K2 at creation: 0 = radix-8 tiled, 1 = radix-16 tiled, 2 = TMA ring (N = 4096)
     bool single_stage_avg_set_ = false;

@@ -54,7 +54,18 @@ struct DecGeom {
 // rel0 = out_base - in_base/2 (relative index of the first output).
 // If FINAL, outputs go to the next stage's stream (DecimParams) for m in [m0, m1); otherwise to
 // the padded planes oute/outo with plane index (j - out_base)/2.
+__device__ __forceinline__ void carry_job(const StreamSrc& src, const CarryJob& c)
+{
+    SSPSD_ASSERT(c.n >= 0 && c.n <= c.dst_cap && c.head_n >= 0 && c.head_n < 4);
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < c.n; i += gridDim.x * blockDim.x) {
+        const float v = ld_stream1(src, c.g0 + i);
+        c.dst[i] = v;
+        if (i >= c.n - c.head_n) c.head_dst[i - (c.n - c.head_n)] = v;
+    }
+}
+
 struct DecimParams {
+    CarryJob cc;
     StreamSrc src;
     long long m0, m1;  // outputs m in [m0, m1) are produced by this launch (m = chunk index of 8 inputs)
     long long drain;   // outputs m < drain are discarded (psd.rs:254-260)
@@ -252,6 +263,7 @@ __global__ void __launch_bounds__(DEC_NT, CTAS) decim8_tma_kernel(const DecimPar
     };
     int tile = blockIdx.x;
     if (tid == 0 && tile < ntiles) issue(tile);
+    if (p.cc.n) carry_job(p.src, p.cc);  // while the first tile is in flight
     const long long lo = p.m0 > p.drain ? p.m0 : p.drain;
     for (unsigned it = 0; tile < ntiles; tile += gridDim.x, ++it) {
         const long long mhi = p.m1 - (long long)tile * OB;
@@ -485,13 +497,7 @@ constexpr size_t decim_tma_smem_bytes()
 __global__ void carry_copy_kernel(StreamSrc src, long long g0, int n, float* __restrict__ dst,
                                   float* __restrict__ head_dst, int head_n, int dst_cap)
 {
-    SSPSD_ASSERT(n >= 0 && n <= dst_cap && head_n >= 0 && head_n < 4 && g0 >= src.carry_start - 0 * n);
-    (void)dst_cap;
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-        float v = ld_stream1(src, g0 + i);
-        dst[i] = v;
-        if (i >= n - head_n) head_dst[i - (n - head_n)] = v;
-    }
+    carry_job(src, CarryJob{g0, n, head_n, dst, head_dst, dst_cap});
 }
 
 // acc[i] *= s (EWMA rescale of the running average before a batch, psd.rs:218-232)

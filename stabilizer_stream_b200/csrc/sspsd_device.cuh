@@ -34,6 +34,17 @@ struct StreamSrc {
     long long end;  // one past the last valid sample (stream length after this batch)
 };
 
+// The next batch's carry buffer of the stage being decimated, built by the decimator launch itself when there is one
+// (one launch less per stage and batch): dst[i] = stream[g0 + i], i < n; the last head_n (< 4) samples also go to the head
+// of the buffer the next batch's fresh samples will be written to (see carry_copy_kernel).  n == 0: nothing to do.
+struct CarryJob {
+    long long g0;
+    int n, head_n;
+    float* dst;
+    float* head_dst;
+    int dst_cap;
+};
+
 __device__ __forceinline__ float4 ld_stream4(const StreamSrc& s, long long g)
 {
     SSPSD_ASSERT(g + 4 <= s.end && (g & 3) == 0);
