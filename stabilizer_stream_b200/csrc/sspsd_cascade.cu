@@ -693,7 +693,8 @@ int Cascade::launch_decim(size_t i, const StreamSrc& src, uint64_t m0, uint64_t 
         return SSPSD_OK;
     int grid = (int)((p.m1 - lo + DEC_OB - 1) / DEC_OB);
     cudaStream_t ss = stage_stream(i);
-    if (cc_valid_ && (k3_variant_ == 1 || k3_variant_ == 2 || k3_variant_ == 7)) {
+    static const bool fuse_carry = !getenv("SSPSD_CARRY_KERNEL");  // A/B switch: keep the separate carry_copy_kernel launch
+    if (cc_valid_ && fuse_carry && (k3_variant_ == 1 || k3_variant_ == 2 || k3_variant_ == 7)) {
         p.cc = cc_pending_;  // the TMA-staged kernels build the stage's next carry buffer themselves
         cc_valid_ = false;
     }
