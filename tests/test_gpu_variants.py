@@ -18,7 +18,8 @@ HERE = os.path.dirname(os.path.abspath(__file__))
                                        ({"SSPSD_OVERLAP": "2"}, 0, 4096),
                                        ({"SSPSD_K3": "tiled"}, 0, 4096), ({"SSPSD_K3": "tma640"}, 3, 4096),
                                        ({"SSPSD_K3": "async960"}, 1, 4096), ({"SSPSD_K3": "async640"}, 0, 512),
-                                       ({"SSPSD_K3": "pf960"}, 2, 4096), ({"SSPSD_K3": "tma768"}, 1, 4096), ({"SSPSD_K3": "pf640"}, 3, 512),
+                                       ({"SSPSD_K3": "pf960"}, 2, 4096), ({"SSPSD_K3": "tma768"}, 1, 4096),
+                                       ({"SSPSD_CARRY_KERNEL": "1"}, 3, 4096), ({"SSPSD_CARRY_KERNEL": "1"}, 0, 512), ({"SSPSD_K3": "pf640"}, 3, 512),
                                        ({"SSPSD_DEFER": "1"}, 2, 4096), ({"SSPSD_DEFER": "4096"}, 0, 512),
                                        ({"SSPSD_K2": "ring1"}, 3, 4096), ({"SSPSD_K2": "ring1", "SSPSD_OVERLAP": "0"}, 1, 4096),
                                        ({"SSPSD_K2": "ring1x5"}, 2, 4096),
